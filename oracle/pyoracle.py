@@ -161,10 +161,17 @@ def jpeg_histograms(y, cb, cr, w, h, color_type=RGB, subsampling=S420, restart_i
     return hist
 
 
+def _jpeg_cap(w, h) -> int:
+    # worst case: every block codes 63 sixteen-bit symbols with ten-bit amplitudes (~260 B),
+    # three components at full resolution, stuffing can double it, plus headers and RSTn
+    nb = ((int(w) + 7) // 8) * ((int(h) + 7) // 8) * 3
+    return nb * 600 + 4096
+
+
 def jpeg_encode(data, w, h, color_type=RGB, quality=80, subsampling=S420, restart_interval=0,
                 optimize_huffman=False, out: np.ndarray | None = None) -> bytes:
     d = _as_u8(data)
-    cap = int(w) * int(h) * 4 + 4096
+    cap = _jpeg_cap(w, h)
     if out is None or out.size < cap:
         out = np.empty(cap, np.uint8)
     n = lib().po_jpeg_encode(_u8(d), d.size, w, h, color_type, quality, subsampling,
@@ -176,7 +183,7 @@ def jpeg_encode(data, w, h, color_type=RGB, quality=80, subsampling=S420, restar
 
 def jpeg_encode_from_coefficients(y, cb, cr, w, h, color_type=RGB, quality=80, subsampling=S420,
                                   restart_interval=0, optimize_huffman=False) -> bytes:
-    cap = int(w) * int(h) * 4 + 4096
+    cap = _jpeg_cap(w, h)
     out = np.empty(cap, np.uint8)
     cb = cb if len(cb) else np.zeros((1, 64), np.int16)
     cr = cr if len(cr) else np.zeros((1, 64), np.int16)

@@ -1,0 +1,603 @@
+// api.cu — the extern "C" surface of libpixo_b200.so (see include/pixo_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <thread>
+
+#include "common.cuh"
+#include "jpeg_host.hpp"
+
+namespace pixo {
+
+static thread_local std::string g_thread_err;
+
+int set_error(pixo_b200_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_thread_err = buf;
+    return code;
+}
+
+int cuda_fail(pixo_b200_ctx *ctx, cudaError_t e, const char *what)
+{
+    const int code = e == cudaErrorMemoryAllocation ? PIXO_B200_ERR_OOM : PIXO_B200_ERR_CUDA;
+    return set_error(ctx, code, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+int ensure_dev(pixo_b200_ctx *ctx, Scratch &s, size_t bytes)
+{
+    if (s.cap >= bytes) return 0;
+    if (s.ptr) {
+        PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PIXO_CUDA(ctx, cudaFree(s.ptr));
+        s.ptr = nullptr;
+        s.cap = 0;
+    }
+    const size_t want = bytes + bytes / 8 + 256;
+    PIXO_CUDA(ctx, cudaMalloc(&s.ptr, want));
+    s.cap = want;
+    return 0;
+}
+
+int ensure_pinned(pixo_b200_ctx *ctx, Scratch &s, size_t bytes)
+{
+    if (s.cap >= bytes) return 0;
+    if (s.ptr) {
+        PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PIXO_CUDA(ctx, cudaFreeHost(s.ptr));
+        s.ptr = nullptr;
+        s.cap = 0;
+    }
+    const size_t want = bytes + bytes / 8 + 256;
+    PIXO_CUDA(ctx, cudaMallocHost(&s.ptr, want));
+    s.cap = want;
+    return 0;
+}
+
+static int validate_jpeg(pixo_b200_ctx *ctx, uint32_t w, uint32_t h, uint32_t color_type,
+                         uint32_t subsampling)
+{
+    // order follows encode_into, src/jpeg/mod.rs:333-373
+    if (w == 0 || h == 0)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_DIMENSIONS, "Invalid image dimensions: %ux%u", w, h);
+    if (w > 65535 || h > 65535)
+        return set_error(ctx, PIXO_B200_ERR_IMAGE_TOO_LARGE, "Image dimensions %ux%u exceed maximum 65535", w, h);
+    if (color_type != PIXO_B200_RGB && color_type != PIXO_B200_GRAY)
+        return set_error(ctx, PIXO_B200_ERR_UNSUPPORTED_COLOR, "Unsupported color type for this format");
+    if (subsampling != PIXO_B200_S444 && subsampling != PIXO_B200_S420)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "unknown subsampling %u", subsampling);
+    return 0;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace pixo
+
+using namespace pixo;
+
+extern "C" {
+
+int pixo_b200_version(void) { return PIXO_B200_VERSION; }
+
+int pixo_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pixo_b200_ctx_create(int device, pixo_b200_ctx **out)
+{
+    if (!out) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx out pointer is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_error(nullptr, PIXO_B200_ERR_CUDA,
+                         "no CUDA device available (%s); libpixo_b200 has no CPU fallback",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n)
+        return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "device %d out of range (0..%d)", device, n - 1);
+    pixo_b200_ctx *ctx = new pixo_b200_ctx();
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        const int rc = cuda_fail(nullptr, e, "cudaSetDevice");
+        delete ctx;
+        return rc;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        const int rc = cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+        delete ctx;
+        return rc;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        const int rc = cuda_fail(nullptr, e, "cudaStreamCreate");
+        delete ctx;
+        return rc;
+    }
+    ctx->stream = ctx->own_stream;
+    unsigned hc = std::thread::hardware_concurrency();
+    ctx->host_threads = hc ? (int)hc : 1;
+    *out = ctx;
+    return 0;
+}
+
+void pixo_b200_ctx_destroy(pixo_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    Scratch *dev[] = {&ctx->d_in, &ctx->d_y, &ctx->d_cb, &ctx->d_cr, &ctx->d_misc, &ctx->d_out};
+    for (Scratch *s : dev) if (s->ptr) cudaFree(s->ptr);
+    Scratch *host[] = {&ctx->h_in, &ctx->h_out, &ctx->h_misc};
+    for (Scratch *s : host) if (s->ptr) cudaFreeHost(s->ptr);
+    for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+const char *pixo_b200_last_error(const pixo_b200_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_thread_err.c_str();
+}
+
+int pixo_b200_ctx_set_stream(pixo_b200_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return 0;
+}
+
+void *pixo_b200_ctx_stream(pixo_b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int pixo_b200_ctx_sync(pixo_b200_ctx *ctx)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+uint64_t pixo_b200_ctx_launch_count(const pixo_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int pixo_b200_ctx_set_host_threads(pixo_b200_ctx *ctx, int n)
+{
+    if (!ctx || n < 1) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "bad host thread count");
+    ctx->host_threads = n;
+    return 0;
+}
+
+int pixo_b200_dev_alloc(pixo_b200_ctx *ctx, size_t bytes, void **dptr)
+{
+    if (!ctx || !dptr) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null argument");
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PIXO_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
+    return 0;
+}
+
+int pixo_b200_dev_free(pixo_b200_ctx *ctx, void *dptr)
+{
+    if (!ctx) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null argument");
+    PIXO_CUDA(ctx, cudaFree(dptr));
+    return 0;
+}
+
+int pixo_b200_host_alloc_pinned(pixo_b200_ctx *ctx, size_t bytes, void **hptr)
+{
+    if (!ctx || !hptr) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null argument");
+    PIXO_CUDA(ctx, cudaMallocHost(hptr, bytes ? bytes : 1));
+    return 0;
+}
+
+int pixo_b200_host_free_pinned(pixo_b200_ctx *ctx, void *hptr)
+{
+    if (!ctx) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null argument");
+    PIXO_CUDA(ctx, cudaFreeHost(hptr));
+    return 0;
+}
+
+int pixo_b200_upload(pixo_b200_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
+{
+    if (!ctx) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null argument");
+    PIXO_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int pixo_b200_download(pixo_b200_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
+{
+    if (!ctx) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null argument");
+    PIXO_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- JPEG ---------------------------------------------------------------------------------
+
+void pixo_b200_quant_tables(int quality, uint8_t lum_zz[64], uint8_t chr_zz[64], float lum[64],
+                            float chr[64])
+{
+    quant_tables(quality, lum_zz, chr_zz, lum, chr);
+}
+
+int pixo_b200_jpeg_block_counts(uint32_t width, uint32_t height, uint32_t color_type,
+                                uint32_t subsampling, size_t *ny, size_t *nc)
+{
+    PIXO_TRY(validate_jpeg(nullptr, width, height, color_type, subsampling));
+    const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
+    if (ny) *ny = g.ny;
+    if (nc) *nc = g.nc;
+    return 0;
+}
+
+int pixo_b200_jpeg_coefficients_dev(pixo_b200_ctx *ctx, const uint8_t *d_pixels,
+                                    size_t pixel_stride, uint32_t n_images, uint32_t width,
+                                    uint32_t height, uint32_t color_type, uint32_t subsampling,
+                                    const float lum_q[64], const float chr_q[64], int16_t *d_y,
+                                    size_t y_stride, int16_t *d_cb, int16_t *d_cr,
+                                    size_t c_stride, uint32_t flags, uint64_t *d_hist)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    PIXO_TRY(validate_jpeg(ctx, width, height, color_type, subsampling));
+    if (!d_pixels || !d_y || !lum_q || !chr_q)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    if (color_type != PIXO_B200_GRAY && (!d_cb || !d_cr))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null chroma buffer");
+    if (n_images == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(d_y) & 15) || (y_stride & 7) ||
+        (d_cb && ((reinterpret_cast<uintptr_t>(d_cb) & 15) || (reinterpret_cast<uintptr_t>(d_cr) & 15) || (c_stride & 7))))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT,
+                         "coefficient buffers must be 16-byte aligned with strides multiple of 8");
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PIXO_TRY(launch_jpeg_transform(ctx, d_pixels, pixel_stride, n_images, width, height,
+                                   color_type, subsampling, lum_q, chr_q, d_y, y_stride, d_cb,
+                                   d_cr, c_stride, flags));
+    if (d_hist) {
+        const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
+        PIXO_TRY(launch_jpeg_histogram(ctx, d_y, y_stride, d_cb, d_cr, c_stride, n_images, g.ny,
+                                       g.nc, g.y_per_mcu, 0, (flags & PIXO_B200_COEF_ZIGZAG) != 0,
+                                       d_hist));
+    }
+    return 0;
+}
+
+// shared by the host-buffer entry points: upload, transform (+hist), download coefficients
+static int transform_host(pixo_b200_ctx *ctx, const uint8_t *pixels, const FrameGeometry &g,
+                          const float lum_q[64], const float chr_q[64], uint32_t flags,
+                          uint32_t restart_interval, bool want_hist, int16_t *y, int16_t *cb,
+                          int16_t *cr, uint64_t *hist)
+{
+    const size_t bpp = g.color_type == PIXO_B200_GRAY ? 1 : 3;
+    const size_t in_bytes = (size_t)g.width * g.height * bpp;
+    const size_t yb = g.ny * 64 * sizeof(int16_t), cbb = g.nc * 64 * sizeof(int16_t);
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_in, in_bytes));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_y, yb));
+    if (cbb) {
+        PIXO_TRY(ensure_dev(ctx, ctx->d_cb, cbb));
+        PIXO_TRY(ensure_dev(ctx, ctx->d_cr, cbb));
+    }
+    PIXO_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.ptr, pixels, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    auto *dy = reinterpret_cast<int16_t *>(ctx->d_y.ptr);
+    auto *dcb = reinterpret_cast<int16_t *>(ctx->d_cb.ptr);
+    auto *dcr = reinterpret_cast<int16_t *>(ctx->d_cr.ptr);
+    PIXO_TRY(launch_jpeg_transform(ctx, reinterpret_cast<const uint8_t *>(ctx->d_in.ptr), in_bytes, 1,
+                                   g.width, g.height, g.color_type, g.subsampling, lum_q, chr_q,
+                                   dy, g.ny * 64, dcb, dcr, g.nc * 64, flags));
+    if (want_hist) {
+        PIXO_TRY(ensure_dev(ctx, ctx->d_out, kHistWords * sizeof(uint64_t)));
+        PIXO_TRY(launch_jpeg_histogram(ctx, dy, g.ny * 64, dcb, dcr, g.nc * 64, 1, g.ny, g.nc,
+                                       g.y_per_mcu, restart_interval,
+                                       (flags & PIXO_B200_COEF_ZIGZAG) != 0,
+                                       reinterpret_cast<uint64_t *>(ctx->d_out.ptr)));
+        PIXO_CUDA(ctx, cudaMemcpyAsync(hist, ctx->d_out.ptr, kHistWords * sizeof(uint64_t),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PIXO_CUDA(ctx, cudaMemcpyAsync(y, dy, yb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cbb) {
+        PIXO_CUDA(ctx, cudaMemcpyAsync(cb, dcb, cbb, cudaMemcpyDeviceToHost, ctx->stream));
+        PIXO_CUDA(ctx, cudaMemcpyAsync(cr, dcr, cbb, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int pixo_b200_jpeg_coefficients(pixo_b200_ctx *ctx, const uint8_t *pixels, uint32_t width,
+                                uint32_t height, uint32_t color_type, uint32_t subsampling,
+                                const float lum_q[64], const float chr_q[64], int16_t *y,
+                                int16_t *cb, int16_t *cr, uint32_t flags, uint64_t *hist)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    PIXO_TRY(validate_jpeg(ctx, width, height, color_type, subsampling));
+    if (!pixels || !y || !lum_q || !chr_q || (color_type != PIXO_B200_GRAY && (!cb || !cr)))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
+    return transform_host(ctx, pixels, g, lum_q, chr_q, flags, 0, hist != nullptr, y, cb, cr, hist);
+}
+
+static int entropy_from_host_arrays(pixo_b200_ctx *ctx, const int16_t *y, const int16_t *cb,
+                                    const int16_t *cr, const FrameGeometry &g, uint32_t quality,
+                                    uint32_t restart_interval, const uint64_t *hist,
+                                    uint8_t *out, size_t out_cap, size_t *out_len, int threads)
+{
+    uint8_t lum_zz[64], chr_zz[64];
+    quant_tables((int)quality, lum_zz, chr_zz, nullptr, nullptr);
+    HuffTables t;
+    // build_optimized_huffman_tables(..).unwrap_or_default(), src/jpeg/mod.rs:379-392
+    if (!(hist && huff_from_histogram(hist, g.has_chroma, t))) huff_standard(t);
+    if (out_cap < 1024 + 2)
+        return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small", out_cap);
+    size_t n = write_headers(out, g, lum_zz, chr_zz, t, restart_interval);
+    const size_t body = entropy_encode_scan(y, cb, cr, g, t, restart_interval, false, out + n,
+                                            out_cap - n - 2, threads);
+    if (body == (size_t)-1)
+        return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small", out_cap);
+    n += body;
+    out[n++] = 0xFF;
+    out[n++] = 0xD9;
+    *out_len = n;
+    return 0;
+}
+
+static int validate_encode(pixo_b200_ctx *ctx, size_t pixels_len, uint32_t width, uint32_t height,
+                           uint32_t color_type, uint32_t quality, uint32_t subsampling,
+                           uint32_t restart_interval, bool restart_given_zero)
+{
+    // encode_into validation order, src/jpeg/mod.rs:333-373
+    if (quality == 0 || quality > 100)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_QUALITY, "Invalid quality %u: must be 1-100", quality);
+    (void)restart_given_zero;
+    if (restart_interval > 65535)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_RESTART, "Invalid restart interval %u", restart_interval);
+    PIXO_TRY(validate_jpeg(ctx, width, height, color_type, subsampling));
+    const size_t bpp = color_type == PIXO_B200_GRAY ? 1 : 3;
+    const size_t expected = (size_t)width * height * bpp;
+    if (pixels_len != expected)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_DATA_LENGTH,
+                         "Invalid data length: expected %zu bytes, got %zu", expected, pixels_len);
+    return 0;
+}
+
+int pixo_b200_jpeg_encode(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t pixels_len,
+                          uint32_t width, uint32_t height, uint32_t color_type, uint32_t quality,
+                          uint32_t subsampling, uint32_t restart_interval,
+                          uint32_t optimize_huffman, uint32_t progressive, uint32_t trellis_quant,
+                          uint8_t *out, size_t out_cap, size_t *out_len)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    PIXO_TRY(validate_encode(ctx, pixels_len, width, height, color_type, quality, subsampling,
+                             restart_interval, false));
+    if (!pixels || !out || !out_len) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    if (progressive)
+        return set_error(ctx, PIXO_B200_ERR_UNSUPPORTED,
+                         "progressive scans are outside the accelerated path (sequential entropy stage)");
+    (void)trellis_quant;  // baseline encode_scan ignores use_trellis (src/jpeg/mod.rs:1408-1563)
+    const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
+    float lum[64], chr[64];
+    quant_tables((int)quality, nullptr, nullptr, lum, chr);
+    const size_t yb = g.ny * 64 * sizeof(int16_t), cbb = g.nc * 64 * sizeof(int16_t);
+    PIXO_TRY(ensure_pinned(ctx, ctx->h_out, align_up(yb, 256) + 2 * align_up(cbb, 256) + 8192));
+    auto *base = reinterpret_cast<uint8_t *>(ctx->h_out.ptr);
+    auto *hy = reinterpret_cast<int16_t *>(base);
+    auto *hcb = reinterpret_cast<int16_t *>(base + align_up(yb, 256));
+    auto *hcr = reinterpret_cast<int16_t *>(base + align_up(yb, 256) + align_up(cbb, 256));
+    auto *hhist = reinterpret_cast<uint64_t *>(base + align_up(yb, 256) + 2 * align_up(cbb, 256));
+    PIXO_TRY(transform_host(ctx, pixels, g, lum, chr, 0, restart_interval, optimize_huffman != 0,
+                            hy, hcb, hcr, hhist));
+    return entropy_from_host_arrays(ctx, hy, hcb, hcr, g, quality, restart_interval,
+                                    optimize_huffman ? hhist : nullptr, out, out_cap, out_len,
+                                    ctx->host_threads);
+}
+
+int pixo_b200_jpeg_encode_batch(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t pixels_len_each,
+                                uint32_t n_images, uint32_t width, uint32_t height,
+                                uint32_t color_type, uint32_t quality, uint32_t subsampling,
+                                uint32_t restart_interval, uint32_t optimize_huffman,
+                                uint8_t *out, size_t out_cap_each, size_t *out_lens)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    PIXO_TRY(validate_encode(ctx, pixels_len_each, width, height, color_type, quality,
+                             subsampling, restart_interval, false));
+    if (!pixels || !out || !out_lens) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    if (n_images == 0) return 0;
+    const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
+    float lum[64], chr[64];
+    quant_tables((int)quality, nullptr, nullptr, lum, chr);
+    const size_t yb = align_up(g.ny * 64 * sizeof(int16_t), 256);
+    const size_t cbb = align_up(g.nc * 64 * sizeof(int16_t), 256);
+    const size_t hb = align_up(kHistWords * sizeof(uint64_t), 256);
+    const size_t per_img = yb + 2 * cbb + hb;
+    // groups of G frames: one transform launch + one coefficient download per group, while the
+    // host entropy-codes the previous group (one thread per frame).
+    uint32_t G = (uint32_t)ctx->host_threads;
+    if (G > n_images) G = n_images;
+    if (G < 1) G = 1;
+    const size_t max_group_bytes = (size_t)1 << 30;
+    while (G > 1 && (size_t)G * (per_img + pixels_len_each) > max_group_bytes) --G;
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_in, 2 * (size_t)G * align_up(pixels_len_each, 256)));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_out, 2 * (size_t)G * per_img));
+    PIXO_TRY(ensure_pinned(ctx, ctx->h_out, 2 * (size_t)G * per_img));
+    while (ctx->events.size() < 2) {
+        cudaEvent_t ev;
+        PIXO_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->events.push_back(ev);
+    }
+    const size_t in_stride = align_up(pixels_len_each, 256);
+    struct GroupCtx {
+        pixo_b200_ctx *ctx; const FrameGeometry *g; uint32_t quality, restart; bool opt;
+        const uint8_t *hbase; size_t per_img, yb, cbb; uint8_t *out; size_t out_cap; size_t *lens;
+        uint32_t first; int rc;
+    };
+    auto encode_one = [](int i, void *arg) {
+        GroupCtx &c = *reinterpret_cast<GroupCtx *>(arg);
+        const uint8_t *b = c.hbase + (size_t)i * c.per_img;
+        const int16_t *y = reinterpret_cast<const int16_t *>(b);
+        const int16_t *cb = reinterpret_cast<const int16_t *>(b + c.yb);
+        const int16_t *cr = reinterpret_cast<const int16_t *>(b + c.yb + c.cbb);
+        const uint64_t *hist = reinterpret_cast<const uint64_t *>(b + c.yb + 2 * c.cbb);
+        const uint32_t img = c.first + (uint32_t)i;
+        const int rc = entropy_from_host_arrays(nullptr, y, cb, cr, *c.g, c.quality, c.restart,
+                                                c.opt ? hist : nullptr, c.out + (size_t)img * c.out_cap,
+                                                c.out_cap, &c.lens[img], 1);
+        if (rc) c.rc = rc;
+    };
+    const uint32_t ngroups = (n_images + G - 1) / G;
+    int final_rc = 0;
+    for (uint32_t gi = 0; gi <= ngroups; ++gi) {
+        if (gi < ngroups) {
+            const uint32_t first = gi * G, cnt = std::min(G, n_images - first);
+            const int slot = (int)(gi & 1);
+            uint8_t *din = reinterpret_cast<uint8_t *>(ctx->d_in.ptr) + (size_t)slot * G * in_stride;
+            uint8_t *dout = reinterpret_cast<uint8_t *>(ctx->d_out.ptr) + (size_t)slot * G * per_img;
+            uint8_t *hout = reinterpret_cast<uint8_t *>(ctx->h_out.ptr) + (size_t)slot * G * per_img;
+            for (uint32_t k = 0; k < cnt; ++k)
+                PIXO_CUDA(ctx, cudaMemcpyAsync(din + (size_t)k * in_stride,
+                                               pixels + (size_t)(first + k) * pixels_len_each,
+                                               pixels_len_each, cudaMemcpyHostToDevice, ctx->stream));
+            auto *dy = reinterpret_cast<int16_t *>(dout);
+            auto *dcb = reinterpret_cast<int16_t *>(dout + yb);
+            auto *dcr = reinterpret_cast<int16_t *>(dout + yb + cbb);
+            PIXO_TRY(launch_jpeg_transform(ctx, din, in_stride, cnt, width, height, color_type,
+                                           subsampling, lum, chr, dy, per_img / 2, dcb, dcr,
+                                           per_img / 2, 0));
+            if (optimize_huffman) {
+                // histograms live at the tail of each frame's slot: stride per_img bytes
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    uint8_t *fb = dout + (size_t)k * per_img;
+                    PIXO_TRY(launch_jpeg_histogram(ctx, reinterpret_cast<int16_t *>(fb), 0,
+                                                   reinterpret_cast<int16_t *>(fb + yb),
+                                                   reinterpret_cast<int16_t *>(fb + yb + cbb), 0, 1,
+                                                   g.ny, g.nc, g.y_per_mcu, restart_interval, false,
+                                                   reinterpret_cast<uint64_t *>(fb + yb + 2 * cbb)));
+                }
+            }
+            PIXO_CUDA(ctx, cudaMemcpyAsync(hout, dout, (size_t)cnt * per_img, cudaMemcpyDeviceToHost, ctx->stream));
+            PIXO_CUDA(ctx, cudaEventRecord(ctx->events[slot], ctx->stream));
+        }
+        if (gi > 0) {
+            const uint32_t pg = gi - 1;
+            const uint32_t first = pg * G, cnt = std::min(G, n_images - first);
+            const int slot = (int)(pg & 1);
+            PIXO_CUDA(ctx, cudaEventSynchronize(ctx->events[slot]));
+            GroupCtx c{ctx, &g, quality, restart_interval, optimize_huffman != 0,
+                       reinterpret_cast<uint8_t *>(ctx->h_out.ptr) + (size_t)slot * G * per_img,
+                       per_img, yb, cbb, out, out_cap_each, out_lens, first, 0};
+            parallel_jobs((int)cnt, ctx->host_threads, encode_one, &c);
+            if (c.rc && !final_rc) final_rc = c.rc;
+        }
+    }
+    if (final_rc)
+        return set_error(ctx, final_rc, "batch entropy stage failed (output capacity %zu per image?)", out_cap_each);
+    return 0;
+}
+
+int pixo_b200_jpeg_entropy_encode(pixo_b200_ctx *ctx, const int16_t *y, const int16_t *cb,
+                                  const int16_t *cr, uint32_t width, uint32_t height,
+                                  uint32_t color_type, uint32_t quality, uint32_t subsampling,
+                                  uint32_t restart_interval, uint32_t optimize_huffman,
+                                  uint8_t *out, size_t out_cap, size_t *out_len)
+{
+    if (quality == 0 || quality > 100)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_QUALITY, "Invalid quality %u: must be 1-100", quality);
+    PIXO_TRY(validate_jpeg(ctx, width, height, color_type, subsampling));
+    if (!y || !out || !out_len || (color_type != PIXO_B200_GRAY && (!cb || !cr)))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
+    uint64_t hist[536];
+    if (optimize_huffman) host_histogram(y, cb, cr, g, restart_interval, hist);
+    int threads = ctx ? ctx->host_threads : (int)std::thread::hardware_concurrency();
+    return entropy_from_host_arrays(ctx, y, cb, cr, g, quality, restart_interval,
+                                    optimize_huffman ? hist : nullptr, out, out_cap, out_len,
+                                    threads < 1 ? 1 : threads);
+}
+
+// ---- PNG ----------------------------------------------------------------------------------
+
+static int validate_png(pixo_b200_ctx *ctx, uint32_t width, uint32_t height, size_t row_bytes,
+                        uint32_t bpp, uint32_t strategy)
+{
+    if (width == 0 || height == 0 || row_bytes == 0)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_DIMENSIONS, "Invalid image dimensions: %ux%u", width, height);
+    if (width > (1u << 24) || height > (1u << 24))  // src/png/mod.rs:21
+        return set_error(ctx, PIXO_B200_ERR_IMAGE_TOO_LARGE, "Image dimensions %ux%u exceed maximum %u", width, height, 1u << 24);
+    if (bpp < 1 || bpp > 4)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "bytes_per_pixel %u not in 1..4", bpp);
+    if (strategy > PIXO_B200_FILTER_BIGRAMS)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "unknown filter strategy %u", strategy);
+    return 0;
+}
+
+int pixo_b200_png_filter_dev(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_stride,
+                             uint32_t n_images, uint32_t width, uint32_t height,
+                             size_t row_bytes, uint32_t bytes_per_pixel, uint32_t strategy,
+                             uint8_t *d_out, size_t out_stride, uint32_t *d_adler)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    PIXO_TRY(validate_png(ctx, width, height, row_bytes, bytes_per_pixel, strategy));
+    if (!d_data || !d_out) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    if (n_images == 0) return 0;
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_png_filter(ctx, d_data, in_stride, n_images, width, height, row_bytes,
+                             bytes_per_pixel, strategy, d_out, out_stride, d_adler);
+}
+
+int pixo_b200_png_filter(pixo_b200_ctx *ctx, const uint8_t *data, uint32_t width,
+                         uint32_t height, size_t row_bytes, uint32_t bytes_per_pixel,
+                         uint32_t strategy, uint8_t *out, uint32_t *adler32_out)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    PIXO_TRY(validate_png(ctx, width, height, row_bytes, bytes_per_pixel, strategy));
+    if (!data || !out) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    const size_t in_bytes = row_bytes * height, out_bytes = (row_bytes + 1) * (size_t)height;
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_in, in_bytes));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_out, out_bytes + 16));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_y, 64));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.ptr, data, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t *d_adler = adler32_out ? reinterpret_cast<uint32_t *>(ctx->d_y.ptr) : nullptr;
+    PIXO_TRY(launch_png_filter(ctx, reinterpret_cast<const uint8_t *>(ctx->d_in.ptr), in_bytes, 1,
+                               width, height, row_bytes, bytes_per_pixel, strategy,
+                               reinterpret_cast<uint8_t *>(ctx->d_out.ptr), out_bytes, d_adler));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (adler32_out)
+        PIXO_CUDA(ctx, cudaMemcpyAsync(adler32_out, d_adler, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int pixo_b200_adler32_dev(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t len, uint32_t *d_out)
+{
+    if (!ctx || !d_out || (!d_data && len))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null argument");
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_adler32(ctx, d_data, len, d_out);
+}
+
+int pixo_b200_adler32(pixo_b200_ctx *ctx, const uint8_t *data, size_t len, uint32_t *out)
+{
+    if (!ctx || !out || (!data && len))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null argument");
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_in, len + 16));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_y, 64));
+    if (len)
+        PIXO_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.ptr, data, len, cudaMemcpyHostToDevice, ctx->stream));
+    PIXO_TRY(launch_adler32(ctx, reinterpret_cast<const uint8_t *>(ctx->d_in.ptr), len,
+                            reinterpret_cast<uint32_t *>(ctx->d_y.ptr)));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_y.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// common.cuh — context object, error plumbing and small device helpers shared by the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pixo_b200.h"
+
+namespace pixo {
+
+constexpr int kHistWords = 536;  // dc_lum[12] dc_chrom[12] ac_lum[256] ac_chrom[256]
+
+// Per-table divisor / reciprocal pairs, passed by value as a __grid_constant__ kernel
+// parameter so that every use is a constant-bank operand with a static offset.
+// r[i] = RN(1/d[i]); q = fma(fma(-x*r, d, x), r, x*r) == RN(x/d) for every d in 1..255 and
+// every binary32 x (proved exhaustively by tools/verify_div.c).
+struct QuantTab {
+    float lum_d[64], lum_r[64], chr_d[64], chr_r[64];
+};
+
+struct Scratch {
+    void *ptr = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace pixo
+
+struct pixo_b200_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    int sm_count = 0;
+    int host_threads = 0;
+    uint64_t launches = 0;
+    std::string err;
+    // reusable scratch (device + pinned host)
+    pixo::Scratch d_in, d_y, d_cb, d_cr, d_misc, d_out;
+    pixo::Scratch h_in, h_out, h_misc;
+    std::vector<cudaEvent_t> events;
+};
+
+namespace pixo {
+
+int set_error(pixo_b200_ctx *ctx, int code, const char *fmt, ...);
+int cuda_fail(pixo_b200_ctx *ctx, cudaError_t e, const char *what);
+int ensure_dev(pixo_b200_ctx *ctx, Scratch &s, size_t bytes);
+int ensure_pinned(pixo_b200_ctx *ctx, Scratch &s, size_t bytes);
+
+#define PIXO_CUDA(ctx, call)                                            \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return ::pixo::cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+#define PIXO_TRY(expr)                 \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != 0) return rc__;    \
+    } while (0)
+
+// ---- launchers implemented in the .cu files ----
+int launch_jpeg_transform(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pixel_stride,
+                          uint32_t n_images, uint32_t w, uint32_t h, uint32_t color_type,
+                          uint32_t subsampling, const float *lum_q, const float *chr_q,
+                          int16_t *d_y, size_t y_stride, int16_t *d_cb, int16_t *d_cr,
+                          size_t c_stride, uint32_t flags);
+int launch_jpeg_histogram(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
+                          const int16_t *d_cb, const int16_t *d_cr, size_t c_stride,
+                          uint32_t n_images, size_t ny, size_t nc, uint32_t blocks_y_per_mcu,
+                          uint32_t restart_interval, bool zigzag_in, uint64_t *d_hist);
+int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_stride,
+                      uint32_t n_images, uint32_t width, uint32_t height, size_t row_bytes,
+                      uint32_t bpp, uint32_t strategy, uint8_t *d_out, size_t out_stride,
+                      uint32_t *d_adler);
+int launch_adler32(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t len, uint32_t *d_out);
+
+}  // namespace pixo

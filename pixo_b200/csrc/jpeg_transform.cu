@@ -1,0 +1,593 @@
+// jpeg_transform.cu — fused colour -> (4:2:0 subsample) -> 8x8 forward DCT -> quantise kernels.
+//
+// Restates, bit-for-bit, the per-MCU work of pixo's
+//   extract_block / extract_mcu_420   src/jpeg/mod.rs:1565-1656
+//   color::rgb_to_ycbcr               src/color.rs:60-77
+//   dct::dct_2d / aan_dct_1d          src/jpeg/dct.rs:591-700   (binary32, no FMA, fixed order)
+//   quantize::quantize_block          src/jpeg/quantize.rs:99-105
+//   quantize::zigzag_reorder          src/jpeg/quantize.rs:107-113 (optional, free: register renaming)
+// and emits the arrays compute_all_coefficients (src/jpeg/mod.rs:932-966) returns.
+//
+// Design (B200): one thread owns one 8x8 block entirely in registers, so both 1-D passes are
+// plain register arithmetic with no transposes or shuffles.  A CTA stages a 16-row strip of
+// interleaved RGB (32 MCUs, 24 KB) in shared memory; Y threads read their 8x24-byte rows
+// conflict-free (24-byte lane stride), colour-convert with dp4a, and leave packed 2x2 chroma
+// sums (cb | cr<<16) in a swizzled 8 KB exchange buffer from which the chroma threads build
+// their blocks.  HBM traffic is exactly the algorithmic 3 B/px in + 3 B/px out.
+#include "common.cuh"
+
+namespace pixo {
+namespace {
+
+__constant__ uint8_t kZigzag[64] = {
+    0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// compile-time copy for static register renaming
+__host__ __device__ constexpr int zz(int i)
+{
+    constexpr int t[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
+                           12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
+                           35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+                           58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    return t[i];
+}
+
+// ---- strict binary32 arithmetic: one rounding per op, never contracted ------------------
+#define FADD(a, b) __fadd_rn((a), (b))
+#define FSUB(a, b) __fsub_rn((a), (b))
+#define FMUL(a, b) __fmul_rn((a), (b))
+
+// AAN constants, src/jpeg/dct.rs:591-608 (same decimal literals)
+#define AAN_A1 0.70710678118654752440f
+#define AAN_A2 0.5411961f
+#define AAN_A3 0.70710678118654752440f
+#define AAN_A4 1.3065629f
+#define AAN_A5 0.38268343f
+#define AAN_S0 0.3535534f
+#define AAN_S1 0.2548978f
+#define AAN_S2 0.2705981f
+#define AAN_S3 0.3006724f
+#define AAN_S4 0.3535534f
+#define AAN_S5 0.4499881f
+#define AAN_S6 0.6532815f
+#define AAN_S7 1.2814578f
+
+// aan_dct_1d, src/jpeg/dct.rs:648-700 — op for op.
+__device__ __forceinline__ void aan_1d(float &d0, float &d1, float &d2, float &d3, float &d4,
+                                       float &d5, float &d6, float &d7)
+{
+    const float tmp0 = FADD(d0, d7), tmp7 = FSUB(d0, d7);
+    const float tmp1 = FADD(d1, d6), tmp6 = FSUB(d1, d6);
+    const float tmp2 = FADD(d2, d5), tmp5 = FSUB(d2, d5);
+    const float tmp3 = FADD(d3, d4), tmp4 = FSUB(d3, d4);
+
+    const float tmp10 = FADD(tmp0, tmp3), tmp13 = FSUB(tmp0, tmp3);
+    const float tmp11 = FADD(tmp1, tmp2), tmp12 = FSUB(tmp1, tmp2);
+
+    const float o0 = FADD(tmp10, tmp11);
+    const float o4 = FSUB(tmp10, tmp11);
+    const float z1 = FMUL(FADD(tmp12, tmp13), AAN_A1);
+    const float o2 = FADD(tmp13, z1);
+    const float o6 = FSUB(tmp13, z1);
+
+    const float u10 = FADD(tmp4, tmp5), u11 = FADD(tmp5, tmp6), u12 = FADD(tmp6, tmp7);
+    const float z5 = FMUL(FSUB(u10, u12), AAN_A5);
+    const float z2 = FADD(FMUL(u10, AAN_A2), z5);
+    const float z4 = FADD(FMUL(u12, AAN_A4), z5);
+    const float z3 = FMUL(u11, AAN_A3);
+    const float z11 = FADD(tmp7, z3), z13 = FSUB(tmp7, z3);
+
+    d0 = FMUL(o0, AAN_S0);
+    d1 = FMUL(FADD(z11, z4), AAN_S1);
+    d2 = FMUL(o2, AAN_S2);
+    d3 = FMUL(FSUB(z13, z2), AAN_S3);
+    d4 = FMUL(o4, AAN_S4);
+    d5 = FMUL(FADD(z13, z2), AAN_S5);
+    d6 = FMUL(o6, AAN_S6);
+    d7 = FMUL(FSUB(z11, z4), AAN_S7);
+}
+
+// dct_2d (rows then columns, src/jpeg/dct.rs:614-646) + quantize_block
+// ((x / q).round() as i16, src/jpeg/quantize.rs:99-105) + optional zig-zag, then 8x 16-byte
+// stores of the block's 64 int16.
+//   x / q : q0 = x*r; q = fma(fma(-q0, d, x), r, q0) == RN(x/d)   (tools/verify_div.c)
+//   round : trunc(RZ(q + copysign(0.5, q))) == round-half-away(q)  (tools/verify_div.c)
+// |coefficient| <= 8*128 so the i16 cast never saturates.
+template <bool ZIGZAG>
+__device__ __forceinline__ void dct_quant_store(float (&v)[64], const float *__restrict__ D,
+                                                const float *__restrict__ R,
+                                                int16_t *__restrict__ out)
+{
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        aan_1d(v[r * 8 + 0], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3], v[r * 8 + 4],
+               v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        aan_1d(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c],
+               v[56 + c]);
+
+    int n[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        const float x = v[i];
+        const float q0 = FMUL(x, R[i]);
+        const float e = __fmaf_rn(-q0, D[i], x);
+        const float q = __fmaf_rn(e, R[i], q0);
+        const float half = __int_as_float((__float_as_int(q) & 0x80000000) | 0x3F000000);
+        n[i] = __float2int_rz(__fadd_rz(q, half));
+    }
+    uint4 *o = reinterpret_cast<uint4 *>(out);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t w[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int i0 = k * 8 + m * 2;
+            const int lo = ZIGZAG ? n[zz(i0)] : n[i0];
+            const int hi = ZIGZAG ? n[zz(i0 + 1)] : n[i0 + 1];
+            w[m] = __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
+        }
+        o[k] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// ---- colour conversion on packed bytes ---------------------------------------------------
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+
+// u8 -> f32 minus `bias` without I2F: bits 0x4B0000vv are the float 2^23 + vv.
+__device__ __forceinline__ float byte1_to_float_minus(uint32_t s, float magic)
+{
+    return FSUB(__uint_as_float(__byte_perm(s, 0x4B000000u, 0x7651)), magic);
+}
+
+// One pixel, src/color.rs:60-77.  rgbb = (r,g,b,b), rgbr = (r,g,b,r) as packed bytes.
+//   y  = (77r + 150g + 29b + 128) >> 8                       (never leaves 0..255)
+//   cb = clamp(((-43r - 85g + 128b + 128) >> 8) + 128)  = min(((-43r-85g+64b+64b + 32896) >> 8), 255)
+//   cr = clamp(((128r - 107g - 21b + 128) >> 8) + 128)  = min(((127r-107g-21b+r + 32896) >> 8), 255)
+// (adding 32768 before the arithmetic shift == adding 128 after it; the lower clamp is dead.)
+// Returns Y - 128 as float; *cbcr = cb | cr << 16.
+__device__ __forceinline__ float ycc_pixel(uint32_t rgbb, uint32_t rgbr, uint32_t *cbcr)
+{
+    const uint32_t ys = __dp4a(rgbb, 0x001D964Du, 128u);            // 77,150,29,0
+    const int cbs = min(dp4a_us(rgbb, 0x4040ABD5u, 32896), 65535);  // -43,-85,64,64
+    const int crs = min(dp4a_us(rgbr, 0x01EB957Fu, 32896), 65535);  // 127,-107,-21,1
+    *cbcr = __byte_perm((uint32_t)cbs, (uint32_t)crs, 0x7531);      // cb | cr<<16 (bytes 3 are 0)
+    return byte1_to_float_minus(ys, 8388736.0f);                    // 2^23 + 128
+}
+
+// 8 RGB pixels held in six little-endian words -> (r,g,b,b) and (r,g,b,r) per pixel.
+__device__ __forceinline__ void unpack8(const uint32_t (&w)[6], uint32_t (&bb)[8],
+                                        uint32_t (&br)[8])
+{
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+        const uint32_t a = w[hlf * 3], b = w[hlf * 3 + 1], c = w[hlf * 3 + 2];
+        bb[hlf * 4 + 0] = __byte_perm(a, b, 0x2210);
+        br[hlf * 4 + 0] = __byte_perm(a, b, 0x0210);
+        bb[hlf * 4 + 1] = __byte_perm(a, b, 0x5543);
+        br[hlf * 4 + 1] = __byte_perm(a, b, 0x3543);
+        bb[hlf * 4 + 2] = __byte_perm(b, c, 0x4432);
+        br[hlf * 4 + 2] = __byte_perm(b, c, 0x2432);
+        bb[hlf * 4 + 3] = __byte_perm(c, c, 0x3321);
+        br[hlf * 4 + 3] = __byte_perm(c, c, 0x1321);
+    }
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// Stage a ROWS x (TILE_PX*BPP)-byte strip of the image in shared memory.  Pixels outside the
+// image replicate the last column / row (clamp happens in source space, before any colour
+// maths, as in extract_block: src/jpeg/mod.rs:1579-1580,1625-1626).
+template <int BPP, int ROWS, int TILE_PX, int NT>
+__device__ __forceinline__ void load_tile(uint8_t *__restrict__ smem,
+                                          const uint8_t *__restrict__ img, uint32_t w,
+                                          uint32_t h, uint32_t x0, uint32_t y0, int tid)
+{
+    constexpr int TB = TILE_PX * BPP;
+    static_assert(TB % 16 == 0, "tile row must be a whole number of 16-byte chunks");
+    const size_t pitch = (size_t)w * BPP;
+    const uint8_t *col0 = img + (size_t)x0 * BPP;
+    const bool fast = (x0 + TILE_PX <= w) && (pitch % 16 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(col0) & 15) == 0);
+    if (fast) {
+        constexpr int CH = TB / 16;
+        constexpr int TOTAL = ROWS * CH;
+#pragma unroll 4
+        for (int idx = tid; idx < TOTAL; idx += NT) {
+            const int r = idx / CH, k = idx - r * CH;
+            const uint32_t sy = min(y0 + (uint32_t)r, h - 1);
+            const uint4 val = ldg_stream(reinterpret_cast<const uint4 *>(col0 + sy * pitch) + k);
+            reinterpret_cast<uint4 *>(smem + r * TB)[k] = val;
+        }
+        return;
+    }
+    const uint32_t inside_px = min((uint32_t)TILE_PX, w - x0);
+    const int lin = (int)inside_px * BPP;
+    const uint8_t *img_lo = img;
+    const uint8_t *img_hi = img + pitch * h;
+    for (int r = 0; r < ROWS; ++r) {
+        const uint32_t sy = min(y0 + (uint32_t)r, h - 1);
+        const uint8_t *src = col0 + sy * pitch;
+        uint8_t *dst = smem + r * TB;
+        const int nwords = lin >> 2;
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+        for (int k = tid; k < nwords; k += NT) {
+            const uint8_t *p = src + 4 * k;
+            const uint8_t *a0 = p - (sh >> 3);
+            uint32_t val;
+            if (a0 >= img_lo && a0 + 8 <= img_hi) {
+                const uint32_t lo = __ldg(reinterpret_cast<const uint32_t *>(a0));
+                const uint32_t hi = sh ? __ldg(reinterpret_cast<const uint32_t *>(a0) + 1) : 0u;
+                val = __funnelshift_r(lo, hi, sh);
+            } else {
+                val = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) |
+                      ((uint32_t)p[3] << 24);
+            }
+            reinterpret_cast<uint32_t *>(dst)[k] = val;
+        }
+        for (int i = (nwords << 2) + tid; i < lin; i += NT) dst[i] = src[i];
+        const uint8_t *last = src + (inside_px - 1) * BPP;
+        for (int i = lin + tid; i < TB; i += NT) dst[i] = last[i % BPP];
+    }
+}
+
+// =========================================================================================
+// K1: RGB, 4:2:0.  CTA = 128 threads = 32 MCUs of one MCU row.
+// =========================================================================================
+constexpr int K1_THREADS = 128;
+constexpr int K1_MCUS = 32;
+constexpr int K1_TB = K1_MCUS * 16 * 3;  // 1536 bytes per tile row
+
+template <bool ZIGZAG>
+__global__ void __launch_bounds__(K1_THREADS)
+k_jpeg_420(const uint8_t *__restrict__ pixels, size_t pixel_stride, uint32_t w, uint32_t h,
+           uint32_t mcus_x, uint32_t tiles_x, int16_t *__restrict__ yout, size_t y_stride,
+           int16_t *__restrict__ cbout, int16_t *__restrict__ crout, size_t c_stride,
+           const __grid_constant__ QuantTab qt)
+{
+    __shared__ __align__(16) uint8_t tile[16 * K1_TB];
+    __shared__ __align__(16) uint32_t csum[K1_MCUS * 64];
+
+    const int tid = threadIdx.x;
+    const uint32_t tx = blockIdx.x % tiles_x;
+    const uint32_t my = blockIdx.x / tiles_x;
+    const uint32_t img = blockIdx.y;
+    const uint8_t *image = pixels + (size_t)img * pixel_stride;
+
+    load_tile<3, 16, K1_MCUS * 16, K1_THREADS>(tile, image, w, h, tx * (K1_MCUS * 16), my * 16,
+                                                tid);
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t mcu0 = tx * K1_MCUS;
+    const uint32_t n_mcu = min((uint32_t)K1_MCUS, mcus_x - mcu0);
+
+    // ---- phase 1: one Y block per thread + packed chroma quad sums ----
+    {
+        const int by = lane >> 4, l16 = lane & 15;
+        const int par = l16 >> 3, k8 = l16 & 7;
+        const int mcu = warp * 8 + (k8 >> 1) * 2 + par;  // same-parity MCUs per quarter warp
+        const int bx = k8 & 1;
+        if ((uint32_t)mcu < n_mcu) {
+            float v[64];
+            const uint8_t *base = tile + (by * 8) * K1_TB + (mcu * 2 + bx) * 24;
+            uint4 *cdst = reinterpret_cast<uint4 *>(csum) + mcu * 16;
+#pragma unroll
+            for (int rp = 0; rp < 4; ++rp) {
+                uint32_t q[4];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int r = rp * 2 + rr;
+                    const uint2 *p = reinterpret_cast<const uint2 *>(base + r * K1_TB);
+                    const uint2 a = p[0], b = p[1], c = p[2];
+                    const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+                    uint32_t bb[8], br[8], cc[8];
+                    unpack8(wds, bb, br);
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) v[r * 8 + x] = ycc_pixel(bb[x], br[x], &cc[x]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t hs = cc[2 * k] + cc[2 * k + 1];
+                        q[k] = rr == 0 ? hs : q[k] + hs;
+                    }
+                }
+                const int logical = (by * 4 + rp) * 2 + bx;
+                cdst[logical ^ (mcu & 7)] = make_uint4(q[0], q[1], q[2], q[3]);
+            }
+            const size_t blk = ((size_t)(my * mcus_x + mcu0 + mcu)) * 4 + by * 2 + bx;
+            dct_quant_store<ZIGZAG>(v, qt.lum_d, qt.lum_r,
+                                    yout + (size_t)img * y_stride + blk * 64);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: warp 0 = Cb blocks, warp 1 = Cr blocks ----
+    if (warp < 2 && (uint32_t)lane < n_mcu) {
+        const int mcu = lane;
+        const uint4 *csrc = reinterpret_cast<const uint4 *>(csum) + mcu * 16;
+        const uint32_t sel = warp == 0 ? 0x7610u : 0x7632u;
+        float v[64];
+#pragma unroll
+        for (int l = 0; l < 16; ++l) {
+            const uint4 s = csrc[l ^ (mcu & 7)];
+            const uint32_t sw[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // (sum of four u8) * 0.25 - 128.0, src/jpeg/mod.rs:1642-1653 (exact in binary32)
+                const float f = __uint_as_float(__byte_perm(sw[k], 0x4B000000u, sel));
+                v[l * 4 + k] = FMUL(FSUB(f, 8389120.0f), 0.25f);  // 2^23 + 512
+            }
+        }
+        const size_t blk = (size_t)(my * mcus_x + mcu0 + mcu);
+        int16_t *dst = (warp == 0 ? cbout : crout) + (size_t)img * c_stride + blk * 64;
+        dct_quant_store<ZIGZAG>(v, qt.chr_d, qt.chr_r, dst);
+    }
+}
+
+// =========================================================================================
+// K2: RGB 4:4:4 (192 threads: warp pairs 0-1 = Y, 2-3 = Cb, 4-5 = Cr) and Gray (64 threads).
+// CTA = 64 blocks of one block row.
+// =========================================================================================
+constexpr int K2_BLOCKS = 64;
+
+template <bool ZIGZAG>
+__global__ void __launch_bounds__(192)
+k_jpeg_444(const uint8_t *__restrict__ pixels, size_t pixel_stride, uint32_t w, uint32_t h,
+           uint32_t blocks_x, uint32_t tiles_x, int16_t *__restrict__ yout, size_t y_stride,
+           int16_t *__restrict__ cbout, int16_t *__restrict__ crout, size_t c_stride,
+           const __grid_constant__ QuantTab qt)
+{
+    constexpr int TB = K2_BLOCKS * 8 * 3;  // 1536
+    __shared__ __align__(16) uint8_t tile[8 * TB];
+    const int tid = threadIdx.x;
+    const uint32_t tx = blockIdx.x % tiles_x;
+    const uint32_t brow = blockIdx.x / tiles_x;
+    const uint32_t img = blockIdx.y;
+    const uint8_t *image = pixels + (size_t)img * pixel_stride;
+    load_tile<3, 8, K2_BLOCKS * 8, 192>(tile, image, w, h, tx * (K2_BLOCKS * 8), brow * 8, tid);
+    __syncthreads();
+
+    const int comp = tid >> 6;  // warp-uniform: 0 = Y, 1 = Cb, 2 = Cr
+    const int j = tid & 63;
+    const uint32_t b0 = tx * K2_BLOCKS;
+    if (b0 + j >= blocks_x) return;
+    float v[64];
+    const uint8_t *base = tile + j * 24;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint2 *p = reinterpret_cast<const uint2 *>(base + r * TB);
+        const uint2 a = p[0], b = p[1], c = p[2];
+        const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+        uint32_t bb[8], br[8];
+        unpack8(wds, bb, br);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            uint32_t s;
+            if (comp == 0) s = __dp4a(bb[x], 0x001D964Du, 128u);
+            else if (comp == 1) s = (uint32_t)min(dp4a_us(bb[x], 0x4040ABD5u, 32896), 65535);
+            else s = (uint32_t)min(dp4a_us(br[x], 0x01EB957Fu, 32896), 65535);
+            v[r * 8 + x] = byte1_to_float_minus(s, 8388736.0f);  // value - 128.0
+        }
+    }
+    const size_t blk = (size_t)brow * blocks_x + b0 + j;
+    if (comp == 0)
+        dct_quant_store<ZIGZAG>(v, qt.lum_d, qt.lum_r, yout + (size_t)img * y_stride + blk * 64);
+    else
+        dct_quant_store<ZIGZAG>(v, qt.chr_d, qt.chr_r,
+                                (comp == 1 ? cbout : crout) + (size_t)img * c_stride + blk * 64);
+}
+
+template <bool ZIGZAG>
+__global__ void __launch_bounds__(64)
+k_jpeg_gray(const uint8_t *__restrict__ pixels, size_t pixel_stride, uint32_t w, uint32_t h,
+            uint32_t blocks_x, uint32_t tiles_x, int16_t *__restrict__ yout, size_t y_stride,
+            const __grid_constant__ QuantTab qt)
+{
+    constexpr int TB = K2_BLOCKS * 8;  // 512
+    __shared__ __align__(16) uint8_t tile[8 * TB];
+    const int tid = threadIdx.x;
+    const uint32_t tx = blockIdx.x % tiles_x;
+    const uint32_t brow = blockIdx.x / tiles_x;
+    const uint32_t img = blockIdx.y;
+    const uint8_t *image = pixels + (size_t)img * pixel_stride;
+    load_tile<1, 8, K2_BLOCKS * 8, 64>(tile, image, w, h, tx * (K2_BLOCKS * 8), brow * 8, tid);
+    __syncthreads();
+    const int j = tid;
+    const uint32_t b0 = tx * K2_BLOCKS;
+    if (b0 + j >= blocks_x) return;
+    float v[64];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint2 a = *reinterpret_cast<const uint2 *>(tile + r * TB + j * 8);
+        const uint32_t wd[2] = {a.x, a.y};
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            // gray as f32 - 128.0, src/jpeg/mod.rs:1584-1589
+            const uint32_t bits = __byte_perm(wd[x >> 2], 0x4B000000u, 0x7650 + (x & 3));
+            v[r * 8 + x] = FSUB(__uint_as_float(bits), 8388736.0f);
+        }
+    }
+    const size_t blk = (size_t)brow * blocks_x + b0 + j;
+    dct_quant_store<ZIGZAG>(v, qt.lum_d, qt.lum_r, yout + (size_t)img * y_stride + blk * 64);
+}
+
+// =========================================================================================
+// K3: symbol pre-scan statistics (count_block, src/jpeg/mod.rs:826-860): per-table histograms
+// of DC categories and AC (run,size) symbols over a frame, from the coefficient arrays.
+// The DC predictor chain is just "previous block of the same component in scan order", which
+// is the previous element of the component's array; it resets at restart boundaries
+// (src/jpeg/mod.rs:1433-1443).  One thread per block; smem histograms, one global flush.
+// =========================================================================================
+__device__ __forceinline__ int category16(int v)
+{
+    const int a = v < 0 ? -v : v;
+    return 32 - __clz(a);  // 0 for 0
+}
+
+template <bool ZIGZAG_IN>
+__global__ void __launch_bounds__(256)
+k_jpeg_hist(const int16_t *__restrict__ ycoef, size_t y_stride, const int16_t *__restrict__ cbcoef,
+            const int16_t *__restrict__ crcoef, size_t c_stride, size_t ny, size_t nc,
+            uint32_t blocks_y_per_mcu, uint32_t restart_interval,
+            unsigned long long *__restrict__ hist)
+{
+    __shared__ uint32_t sh[kHistWords];
+    for (int i = threadIdx.x; i < kHistWords; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint32_t img = blockIdx.y;
+    const size_t total = ny + 2 * nc;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < total;
+         b += (size_t)gridDim.x * blockDim.x) {
+        const int16_t *arr;
+        size_t idx;
+        bool lum;
+        uint32_t per_mcu;
+        if (b < ny) { arr = ycoef + (size_t)img * y_stride; idx = b; lum = true; per_mcu = blocks_y_per_mcu; }
+        else if (b < ny + nc) { arr = cbcoef + (size_t)img * c_stride; idx = b - ny; lum = false; per_mcu = 1; }
+        else { arr = crcoef + (size_t)img * c_stride; idx = b - ny - nc; lum = false; per_mcu = 1; }
+        const uint4 *src = reinterpret_cast<const uint4 *>(arr + idx * 64);
+        uint32_t wv[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint4 t = __ldg(src + k);
+            wv[k * 4] = t.x; wv[k * 4 + 1] = t.y; wv[k * 4 + 2] = t.z; wv[k * 4 + 3] = t.w;
+        }
+        // DC difference against the previous block of this component
+        int prev = 0;
+        const size_t mcu = idx / per_mcu;
+        const bool first_in_mcu = (idx % per_mcu) == 0;
+        const bool reset = idx == 0 || (restart_interval && first_in_mcu && (mcu % restart_interval) == 0);
+        if (!reset) prev = arr[(idx - 1) * 64];
+        const int dc = (int)(int16_t)(wv[0] & 0xFFFF);
+        const int diff = (int)(int16_t)(dc - prev);
+        atomicAdd(&sh[(lum ? 0 : 12) + category16(diff)], 1u);
+        // AC: walk coefficients in zig-zag order
+        uint32_t *ac = sh + (lum ? 24 : 280);
+        int run = 0;
+#pragma unroll
+        for (int i = 1; i < 64; ++i) {
+            const int nat = ZIGZAG_IN ? i : zz(i);
+            const uint32_t word = wv[nat >> 1];
+            const int c = (int)(int16_t)((nat & 1) ? (word >> 16) : (word & 0xFFFF));
+            if (c == 0) {
+                ++run;
+            } else {
+                if (run >= 16) { atomicAdd(&ac[0xF0], (uint32_t)(run >> 4)); run &= 15; }
+                atomicAdd(&ac[(run << 4) | category16(c)], 1u);
+                run = 0;
+            }
+        }
+        if (run > 0) atomicAdd(&ac[0], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHistWords; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[(size_t)img * kHistWords + i], (unsigned long long)sh[i]);
+}
+
+void make_quant_tab(const float *lum_q, const float *chr_q, QuantTab *qt)
+{
+    for (int i = 0; i < 64; ++i) {
+        qt->lum_d[i] = lum_q[i];
+        qt->chr_d[i] = chr_q[i];
+        volatile float rl = 1.0f / lum_q[i];
+        volatile float rc = 1.0f / chr_q[i];
+        qt->lum_r[i] = rl;
+        qt->chr_r[i] = rc;
+    }
+}
+
+}  // namespace
+
+int launch_jpeg_transform(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pixel_stride,
+                          uint32_t n_images, uint32_t w, uint32_t h, uint32_t color_type,
+                          uint32_t subsampling, const float *lum_q, const float *chr_q,
+                          int16_t *d_y, size_t y_stride, int16_t *d_cb, int16_t *d_cr,
+                          size_t c_stride, uint32_t flags)
+{
+    QuantTab qt;
+    make_quant_tab(lum_q, chr_q, &qt);
+    const bool zigzag = (flags & PIXO_B200_COEF_ZIGZAG) != 0;
+    // the exact-division identity is proved for integer divisors 1..255 only
+    for (int i = 0; i < 64; ++i) {
+        const float a = lum_q[i], b = chr_q[i];
+        if (!(a >= 1.0f && a <= 255.0f && a == (float)(int)a && b >= 1.0f && b <= 255.0f &&
+              b == (float)(int)b))
+            return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT,
+                             "quantisation table entries must be integers in 1..255");
+    }
+    for (uint32_t i0 = 0; i0 < n_images; i0 += 65535) {
+        const uint32_t nb = n_images - i0 < 65535 ? n_images - i0 : 65535;
+        const uint8_t *px = d_pixels + (size_t)i0 * pixel_stride;
+        int16_t *y = d_y + (size_t)i0 * y_stride;
+        int16_t *cb = d_cb ? d_cb + (size_t)i0 * c_stride : nullptr;
+        int16_t *cr = d_cr ? d_cr + (size_t)i0 * c_stride : nullptr;
+        if (color_type == PIXO_B200_GRAY) {
+            const uint32_t bx = (w + 7) / 8, by = (h + 7) / 8;
+            const uint32_t tiles_x = (bx + K2_BLOCKS - 1) / K2_BLOCKS;
+            dim3 grid(tiles_x * by, nb);
+            if (zigzag) k_jpeg_gray<true><<<grid, 64, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, qt);
+            else k_jpeg_gray<false><<<grid, 64, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, qt);
+        } else if (subsampling == PIXO_B200_S444) {
+            const uint32_t bx = (w + 7) / 8, by = (h + 7) / 8;
+            const uint32_t tiles_x = (bx + K2_BLOCKS - 1) / K2_BLOCKS;
+            dim3 grid(tiles_x * by, nb);
+            if (zigzag) k_jpeg_444<true><<<grid, 192, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, cb, cr, c_stride, qt);
+            else k_jpeg_444<false><<<grid, 192, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, cb, cr, c_stride, qt);
+        } else {
+            const uint32_t mx = (w + 15) / 16, my = (h + 15) / 16;
+            const uint32_t tiles_x = (mx + K1_MCUS - 1) / K1_MCUS;
+            dim3 grid(tiles_x * my, nb);
+            if (zigzag) k_jpeg_420<true><<<grid, K1_THREADS, 0, ctx->stream>>>(px, pixel_stride, w, h, mx, tiles_x, y, y_stride, cb, cr, c_stride, qt);
+            else k_jpeg_420<false><<<grid, K1_THREADS, 0, ctx->stream>>>(px, pixel_stride, w, h, mx, tiles_x, y, y_stride, cb, cr, c_stride, qt);
+        }
+        ctx->launches++;
+        PIXO_CUDA(ctx, cudaGetLastError());
+    }
+    return 0;
+}
+
+int launch_jpeg_histogram(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
+                          const int16_t *d_cb, const int16_t *d_cr, size_t c_stride,
+                          uint32_t n_images, size_t ny, size_t nc, uint32_t blocks_y_per_mcu,
+                          uint32_t restart_interval, bool zigzag_in, uint64_t *d_hist)
+{
+    PIXO_CUDA(ctx, cudaMemsetAsync(d_hist, 0, (size_t)n_images * kHistWords * sizeof(uint64_t),
+                                   ctx->stream));
+    const size_t total = ny + 2 * nc;
+    uint32_t gx = (uint32_t)((total + 255) / 256);
+    const uint32_t cap = (uint32_t)ctx->sm_count * 8;
+    if (gx > cap) gx = cap;
+    if (gx == 0) gx = 1;
+    for (uint32_t i0 = 0; i0 < n_images; i0 += 65535) {
+        const uint32_t nb = n_images - i0 < 65535 ? n_images - i0 : 65535;
+        dim3 grid(gx, nb);
+        auto *hist = reinterpret_cast<unsigned long long *>(d_hist + (size_t)i0 * kHistWords);
+        const int16_t *y = d_y + (size_t)i0 * y_stride;
+        const int16_t *cb = d_cb ? d_cb + (size_t)i0 * c_stride : nullptr;
+        const int16_t *cr = d_cr ? d_cr + (size_t)i0 * c_stride : nullptr;
+        if (zigzag_in)
+            k_jpeg_hist<true><<<grid, 256, 0, ctx->stream>>>(y, y_stride, cb, cr, c_stride, ny, nc, blocks_y_per_mcu, restart_interval, hist);
+        else
+            k_jpeg_hist<false><<<grid, 256, 0, ctx->stream>>>(y, y_stride, cb, cr, c_stride, ny, nc, blocks_y_per_mcu, restart_interval, hist);
+        ctx->launches++;
+        PIXO_CUDA(ctx, cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace pixo

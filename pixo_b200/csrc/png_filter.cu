@@ -1,0 +1,445 @@
+// png_filter.cu — PNG per-row predictive-filter selection with fused Adler-32, and the
+// standalone Adler-32 kernel.
+//
+// Restates pixo's
+//   filter_{sub,up,average,paeth}   src/simd/fallback.rs:100-159 (normative scalar semantics;
+//                                   dispatch src/simd/mod.rs:159-236)
+//   score_filter                    src/simd/fallback.rs:93-98  (sum |i8|)
+//   adaptive_filter / minsum        src/png/filter.rs:302-404
+//   adaptive_filter_fast            src/png/filter.rs:474-527
+//   filter_row / apply_filters*     src/png/filter.rs:64-206,529-608
+//   adler32                         src/compress/adler32.rs:26-47
+//
+// Design (B200): one CTA per image row.  The raw row and the raw previous row are staged in
+// shared memory with 128-bit loads (previous row comes from L2: it is the neighbouring CTA's
+// current row, so HBM sees each raw byte once); every thread evaluates all candidate filters on
+// 4-byte words (SWAR + dp4a scoring), the CTA reduces the five scores, replays the reference's
+// decision ladder, re-derives only the winning filter from the staged rows and writes
+// `type byte + row` with aligned word stores.  The row's Adler-32 contribution
+// (A = sum d, B = sum (n-i) d, position-weighted to the end of the image) is accumulated in the
+// same pass; the last CTA of an image folds the accumulators into the checksum.
+#include "common.cuh"
+
+namespace pixo {
+namespace {
+
+constexpr uint32_t ADLER_MOD = 65521u;
+constexpr int PNG_THREADS = 256;
+constexpr int SEG_BYTES = 32768;  // bytes of a row staged per pass segment
+
+__device__ __forceinline__ uint32_t sum_abs_s8x4(uint32_t v)
+{
+    // sum over bytes of |(i8)byte|: sign mask via PRMT sign-replicate, then dp4a with +-1
+    const uint32_t neg = __byte_perm(v, 0u, 0xBA98);  // 0xFF where byte < 0
+    const uint32_t sgn = neg | 0x01010101u;           // -1 / +1 as s8
+    return (uint32_t)__dp4a((int)v, (int)sgn, 0);
+}
+
+__device__ __forceinline__ uint32_t paeth4(uint32_t a, uint32_t b, uint32_t c)
+{
+    // fallback_paeth_predictor, src/simd/fallback.rs:143-159, per byte lane
+    uint32_t r = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int aa = (a >> (8 * j)) & 0xFF, bb = (b >> (8 * j)) & 0xFF, cc = (c >> (8 * j)) & 0xFF;
+        const int t1 = bb - cc, t2 = aa - cc;
+        const int pa = abs(t1), pb = abs(t2), pc = abs(t1 + t2);
+        const int pred = (pa <= pb && pa <= pc) ? aa : (pb <= pc ? bb : cc);
+        r |= (uint32_t)pred << (8 * j);
+    }
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Copy `len` bytes src[0..len) to dst (shared, 16-byte aligned) with the widest loads the
+// source alignment allows.  lo/hi bound the readable allocation for the word path.
+__device__ __forceinline__ void stage_bytes(uint8_t *__restrict__ dst,
+                                            const uint8_t *__restrict__ src, int len,
+                                            const uint8_t *lo_bound, const uint8_t *hi_bound,
+                                            int tid)
+{
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int nv = len >> 4;
+        for (int k = tid; k < nv; k += PNG_THREADS)
+            reinterpret_cast<uint4 *>(dst)[k] = __ldg(reinterpret_cast<const uint4 *>(src) + k);
+        for (int i = (nv << 4) + tid; i < len; i += PNG_THREADS) dst[i] = src[i];
+        return;
+    }
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+    const int nw = len >> 2;
+    for (int k = tid; k < nw; k += PNG_THREADS) {
+        const uint8_t *p = src + 4 * k;
+        const uint8_t *a0 = p - (sh >> 3);
+        uint32_t val;
+        if (a0 >= lo_bound && a0 + 8 <= hi_bound) {
+            const uint32_t lo = __ldg(reinterpret_cast<const uint32_t *>(a0));
+            const uint32_t hi = sh ? __ldg(reinterpret_cast<const uint32_t *>(a0) + 1) : 0u;
+            val = __funnelshift_r(lo, hi, sh);
+        } else {
+            val = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) |
+                  ((uint32_t)p[3] << 24);
+        }
+        reinterpret_cast<uint32_t *>(dst)[k] = val;
+    }
+    for (int i = (nw << 2) + tid; i < len; i += PNG_THREADS) dst[i] = src[i];
+}
+
+struct PngParams {
+    const uint8_t *data;
+    size_t in_stride;
+    uint8_t *out;
+    size_t out_stride;
+    uint32_t height;
+    uint32_t row0;         // first row handled by this launch
+    uint32_t row_bytes_lo; // row_bytes (rows < 4 GiB)
+    uint32_t bpp;
+    uint32_t strategy;     // 0..4 fixed, 5/6 adaptive ladder, 7 adaptive-fast ladder
+    const uint8_t *forced; // per-image filter type decided earlier (sticky AdaptiveFast), or null
+    uint8_t *decided;      // per-image: row0's decision is written here when non-null
+    unsigned long long *acc; // per-image {A, B} accumulators (may be null)
+    uint32_t *counter;     // per-image CTA completion counter
+    uint32_t *adler_out;   // per-image checksum
+    uint32_t rows_total_for_adler; // rows contributing before finalisation
+};
+
+// smem layout (dynamic): cur[16 + SEGP] prev[16 + SEGP] sbuf[SEGP + 32]
+__global__ void __launch_bounds__(PNG_THREADS) k_png_filter(const PngParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const uint32_t y = P.row0 + blockIdx.x;
+    const uint32_t img = blockIdx.y;
+    const size_t rb = P.row_bytes_lo;
+    const int segcap = (int)min((size_t)SEG_BYTES, (rb + 15) & ~(size_t)15);
+    uint8_t *cur = smem;
+    uint8_t *prev = smem + 16 + segcap;
+    uint8_t *sbuf = smem + 2 * (16 + segcap);
+    __shared__ unsigned long long red[5][PNG_THREADS / 32];
+    __shared__ unsigned long long red2[2][PNG_THREADS / 32];
+    __shared__ int s_filter;
+
+    const uint8_t *image = P.data + (size_t)img * P.in_stride;
+    const uint8_t *row = image + (size_t)y * rb;
+    const uint8_t *prow = y ? row - rb : nullptr;
+    const uint8_t *lo_b = image, *hi_b = image + (size_t)P.height * rb;
+    const uint32_t bpp = P.bpp;
+    const uint32_t ashift = (4 - bpp) * 8;
+    const int nseg = (int)((rb + segcap - 1) / segcap);
+
+    int filter = (int)P.strategy;
+    if (P.forced) filter = P.forced[img];
+    const bool need_scores = filter >= 5;
+
+    uint8_t *orow = P.out + (size_t)img * P.out_stride + (size_t)y * (rb + 1);
+    const uint32_t n_out = (uint32_t)rb + 1;
+    unsigned long long adlA = 0, adlB = 0;
+
+    for (int pass = need_scores ? 0 : 1; pass < 2; ++pass) {
+        unsigned long long sc[5] = {0, 0, 0, 0, 0};
+        for (int seg = 0; seg < nseg; ++seg) {
+            const size_t s0 = (size_t)seg * segcap;
+            const int slen = (int)min((size_t)segcap, rb - s0);
+            const bool restage = !(nseg == 1 && pass == 1 && need_scores);
+            if (restage) {
+                __syncthreads();
+                // 16-byte front halo: the bpp bytes left of the segment (zeros at row start)
+                if (tid < 16) {
+                    const long long gi = (long long)s0 - 16 + tid;
+                    cur[tid] = gi >= 0 ? row[gi] : 0;
+                    prev[tid] = (gi >= 0 && prow) ? prow[gi] : 0;
+                }
+                stage_bytes(cur + 16, row + s0, slen, lo_b, hi_b, tid);
+                if (prow) stage_bytes(prev + 16, prow + s0, slen, lo_b, hi_b, tid);
+                else for (int i = tid; i < slen; i += PNG_THREADS) prev[16 + i] = 0;
+                // zero the tail of the last word so masked lanes read defined data
+                for (int i = slen + tid; i < ((slen + 3) & ~3); i += PNG_THREADS) { cur[16 + i] = 0; prev[16 + i] = 0; }
+                __syncthreads();
+            }
+            const uint32_t *c32 = reinterpret_cast<const uint32_t *>(cur) + 4;
+            const uint32_t *p32 = reinterpret_cast<const uint32_t *>(prev) + 4;
+            const int nw = (slen + 3) >> 2;
+            for (int k = tid; k < nw; k += PNG_THREADS) {
+                const uint32_t x = c32[k], b = p32[k];
+                const uint32_t a = __funnelshift_r(c32[k - 1], x, ashift);
+                const uint32_t c = __funnelshift_r(p32[k - 1], b, ashift);
+                const int valid = slen - 4 * k;
+                const uint32_t mask = valid >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - valid)));
+                if (pass == 0) {
+                    const bool fast = P.strategy == PIXO_B200_FILTER_ADAPTIVE_FAST;
+                    if (!fast) sc[0] += sum_abs_s8x4(x & mask);
+                    sc[1] += sum_abs_s8x4(__vsub4(x, a) & mask);
+                    sc[2] += sum_abs_s8x4(__vsub4(x, b) & mask);
+                    if (!fast) sc[3] += sum_abs_s8x4(__vsub4(x, __vhaddu4(a, b)) & mask);
+                    sc[4] += sum_abs_s8x4(__vsub4(x, paeth4(a, b, c)) & mask);
+                } else {
+                    uint32_t f;
+                    switch (filter) {
+                    case 0: f = x; break;
+                    case 1: f = __vsub4(x, a); break;
+                    case 2: f = __vsub4(x, b); break;
+                    case 3: f = __vsub4(x, __vhaddu4(a, b)); break;
+                    default: f = __vsub4(x, paeth4(a, b, c)); break;
+                    }
+                    f &= mask;
+                    // Adler terms: stream index q = 1 + s0 + 4k + j, weight (n_out - q)
+                    const uint32_t s4 = __dp4a(f, 0x01010101u, 0u);
+                    const uint32_t j4 = __dp4a(f, 0x03020100u, 0u);
+                    adlA += s4;
+                    adlB += (unsigned long long)(rb - s0 - 4 * (size_t)k) * s4 - j4;
+                    // place the bytes at their position in the output stream image
+                    const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(orow + 1 + s0) & 3);
+                    uint8_t *d = sbuf + off + 4 * k;
+                    d[0] = (uint8_t)f; d[1] = (uint8_t)(f >> 8); d[2] = (uint8_t)(f >> 16); d[3] = (uint8_t)(f >> 24);
+                }
+            }
+            if (pass == 1) {
+                __syncthreads();
+                // copy this segment's bytes out: stream bytes [1+s0, 1+s0+slen) live at
+                // sbuf[off ...]; aligned words in the middle, bytes at the two ends.
+                uint8_t *g0 = orow + 1 + s0;
+                const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 3);
+                uint8_t *gal = g0 - off;  // 4-byte aligned
+                const int total = (int)off + slen;
+                const int nwords = (total + 3) >> 2;
+                const uint32_t *s32 = reinterpret_cast<const uint32_t *>(sbuf);
+                for (int t = tid; t < nwords; t += PNG_THREADS) {
+                    const int lo = 4 * t, hi = 4 * t + 4;
+                    if (lo >= (int)off && hi <= total) {
+                        reinterpret_cast<uint32_t *>(gal)[t] = s32[t];
+                    } else {
+                        for (int i = max(lo, (int)off); i < min(hi, total); ++i) gal[i] = sbuf[i];
+                    }
+                }
+                if (seg == 0 && tid == 0) orow[0] = (uint8_t)filter;
+            }
+        }
+        if (pass == 0) {
+            // CTA reduction of the candidate scores, then the reference's decision ladder
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                const unsigned long long v = warp_sum(sc[f]);
+                if ((tid & 31) == 0) red[f][tid >> 5] = v;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long s[5];
+                for (int f = 0; f < 5; ++f) {
+                    unsigned long long t = 0;
+                    for (int w = 0; w < PNG_THREADS / 32; ++w) t += red[f][w];
+                    s[f] = t;
+                }
+                int best;
+                if (P.strategy == PIXO_B200_FILTER_ADAPTIVE_FAST) {
+                    // adaptive_filter_fast, src/png/filter.rs:474-527
+                    const unsigned long long early = (unsigned long long)rb / 8 + 1;
+                    best = 1;
+                    unsigned long long bs = s[1];
+                    if (bs > early) {
+                        if (s[2] < bs) { bs = s[2]; best = 2; }
+                        if (bs > early && s[4] < bs) best = 4;
+                    }
+                } else {
+                    // adaptive_filter, src/png/filter.rs:302-393: first candidate (None, Sub, Up,
+                    // Average in order) that becomes the best with a score <= early wins
+                    // outright; otherwise strict-< argmin, Paeth last.
+                    const unsigned long long early = (unsigned long long)rb / 4 + 1;
+                    best = 0;
+                    unsigned long long bs = s[0];
+                    bool done = bs <= early;  // covers the score == 0 exit as well
+                    for (int f = 1; f < 5 && !done; ++f) {
+                        if (s[f] < bs) {
+                            bs = s[f];
+                            best = f;
+                            if (f < 4 && (bs == 0 || bs <= early)) done = true;
+                        }
+                    }
+                }
+                s_filter = best;
+            }
+            __syncthreads();
+            filter = s_filter;
+        }
+    }
+    if (P.decided && blockIdx.x == 0 && tid == 0) P.decided[img] = (uint8_t)filter;
+
+    if (P.acc) {
+        // row contribution, weighted to the end of the image:
+        //   A_r = sum d ;  B_r + n_out * (H-1-y) * A_r   (Adler combine)
+        adlA = warp_sum(adlA);
+        adlB = warp_sum(adlB);
+        if ((tid & 31) == 0) { red2[0][tid >> 5] = adlA; red2[1][tid >> 5] = adlB; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long A = (unsigned long long)filter, B = (unsigned long long)filter * n_out;
+            for (int w = 0; w < PNG_THREADS / 32; ++w) { A += red2[0][w]; B += red2[1][w]; }
+            const unsigned long long after = (unsigned long long)(P.height - 1 - y) % ADLER_MOD;
+            const unsigned long long Am = A % ADLER_MOD;
+            const unsigned long long Bm = (B % ADLER_MOD + (((n_out % ADLER_MOD) * after) % ADLER_MOD) * Am) % ADLER_MOD;
+            atomicAdd(&P.acc[2 * img], Am);
+            atomicAdd(&P.acc[2 * img + 1], Bm);
+            __threadfence();
+            const uint32_t done = atomicAdd(&P.counter[img], 1u) + 1;
+            if (done == P.rows_total_for_adler) {
+                __threadfence();
+                const unsigned long long At = atomicAdd(&P.acc[2 * img], 0ull);
+                const unsigned long long Bt = atomicAdd(&P.acc[2 * img + 1], 0ull);
+                const unsigned long long N = ((unsigned long long)P.height % ADLER_MOD) * (n_out % ADLER_MOD) % ADLER_MOD;
+                const uint32_t s1 = (uint32_t)((1 + At) % ADLER_MOD);
+                const uint32_t s2 = (uint32_t)((N + Bt) % ADLER_MOD);
+                P.adler_out[img] = (s2 << 16) | s1;
+            }
+        }
+    }
+}
+
+// Standalone Adler-32 (K5): grid-stride over 16-byte vectors; per-thread A and end-weighted B.
+__global__ void __launch_bounds__(256)
+k_adler32(const uint8_t *__restrict__ data, size_t len, unsigned long long *acc,
+          uint32_t *counter, uint32_t *out)
+{
+    __shared__ unsigned long long red[2][8];
+    const int tid = threadIdx.x;
+    unsigned long long A = 0, B = 0;
+    const uintptr_t mis = reinterpret_cast<uintptr_t>(data) & 15;
+    const size_t head = mis ? min(len, (size_t)(16 - mis)) : 0;
+    const size_t nvec = (len - head) >> 4;
+    const uint4 *v = reinterpret_cast<const uint4 *>(data + head);
+    const size_t gsz = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < nvec; i += gsz) {
+        const uint4 q = __ldg(v + i);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const unsigned long long wt = (unsigned long long)(len - (head + (i << 4)));  // weight of byte 0
+        uint32_t s = 0, js = 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const uint32_t s4 = __dp4a(w[m], 0x01010101u, 0u);
+            s += s4;
+            js += __dp4a(w[m], 0x03020100u, 0u) + 4 * m * s4;
+        }
+        A += s;
+        B += (wt % ADLER_MOD) * s + (unsigned long long)ADLER_MOD * 4096 - js;  // keep positive
+        if ((B >> 60) != 0) B %= ADLER_MOD;
+    }
+    // head and tail bytes (at most 15 each) by the first thread of the grid
+    if (blockIdx.x == 0 && tid == 0) {
+        for (size_t i = 0; i < head; ++i) { A += data[i]; B += ((len - i) % ADLER_MOD) * data[i]; }
+        for (size_t i = head + (nvec << 4); i < len; ++i) { A += data[i]; B += ((len - i) % ADLER_MOD) * data[i]; }
+    }
+    A = warp_sum(A % ADLER_MOD);
+    B = warp_sum(B % ADLER_MOD);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = A; red[1][tid >> 5] = B; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long At = 0, Bt = 0;
+        for (int w = 0; w < 8; ++w) { At += red[0][w]; Bt += red[1][w]; }
+        atomicAdd(&acc[0], At % ADLER_MOD);
+        atomicAdd(&acc[1], Bt % ADLER_MOD);
+        __threadfence();
+        const uint32_t done = atomicAdd(counter, 1u) + 1;
+        if (done == gridDim.x) {
+            __threadfence();
+            const unsigned long long a = atomicAdd(&acc[0], 0ull), b = atomicAdd(&acc[1], 0ull);
+            const uint32_t s1 = (uint32_t)((1 + a) % ADLER_MOD);
+            const uint32_t s2 = (uint32_t)((len % ADLER_MOD + b) % ADLER_MOD);
+            *out = (s2 << 16) | s1;
+        }
+    }
+}
+
+}  // namespace
+
+int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_stride,
+                      uint32_t n_images, uint32_t width, uint32_t height, size_t row_bytes,
+                      uint32_t bpp, uint32_t strategy, uint8_t *d_out, size_t out_stride,
+                      uint32_t *d_adler)
+{
+    if (strategy == PIXO_B200_FILTER_BIGRAMS)
+        return set_error(ctx, PIXO_B200_ERR_UNSUPPORTED,
+                         "FilterStrategy::Bigrams is not on the GPU path yet");
+    if (row_bytes >= (1ull << 32) - 16)
+        return set_error(ctx, PIXO_B200_ERR_IMAGE_TOO_LARGE, "row_bytes too large");
+    // apply_filters_with_row_bytes pre-rules, src/png/filter.rs:72-86
+    const size_t area = (size_t)width * (size_t)height;
+    uint32_t strat = strategy;
+    if (area <= 4096 && (strat == PIXO_B200_FILTER_ADAPTIVE || strat == PIXO_B200_FILTER_ADAPTIVE_FAST))
+        strat = PIXO_B200_FILTER_SUB;
+    // default-feature build: AdaptiveFast takes the sequential (sticky) loop when height <= 32
+    const bool sticky = strat == PIXO_B200_FILTER_ADAPTIVE_FAST && height <= 32;
+
+    const size_t segcap = row_bytes + 15 < (size_t)SEG_BYTES ? ((row_bytes + 15) & ~(size_t)15) : (size_t)SEG_BYTES;
+    const size_t smem = 2 * (16 + segcap) + segcap + 32;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PIXO_CUDA(ctx, cudaFuncSetAttribute(k_png_filter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(2 * (16 + SEG_BYTES) + SEG_BYTES + 32)));
+        attr_set = true;
+    }
+    // misc scratch: per image {accA, accB} u64, counter u32, decided u8
+    const size_t per = 2 * sizeof(unsigned long long) + sizeof(uint32_t) + 4;
+    PIXO_TRY(ensure_dev(ctx, ctx->d_misc, (size_t)n_images * per + 64));
+    auto *acc = reinterpret_cast<unsigned long long *>(ctx->d_misc.ptr);
+    auto *counter = reinterpret_cast<uint32_t *>(acc + 2 * (size_t)n_images);
+    auto *decided = reinterpret_cast<uint8_t *>(counter + n_images);
+    PIXO_CUDA(ctx, cudaMemsetAsync(ctx->d_misc.ptr, 0, (size_t)n_images * per + 64, ctx->stream));
+
+    for (uint32_t i0 = 0; i0 < n_images; i0 += 65535) {
+        const uint32_t nb = n_images - i0 < 65535 ? n_images - i0 : 65535;
+        PngParams P;
+        P.data = d_data + (size_t)i0 * in_stride;
+        P.in_stride = in_stride;
+        P.out = d_out + (size_t)i0 * out_stride;
+        P.out_stride = out_stride;
+        P.height = height;
+        P.row_bytes_lo = (uint32_t)row_bytes;
+        P.bpp = bpp;
+        P.strategy = strat;
+        P.acc = d_adler ? acc + 2 * (size_t)i0 : nullptr;
+        P.counter = counter + i0;
+        P.adler_out = d_adler ? d_adler + i0 : nullptr;
+        P.rows_total_for_adler = height;
+        if (sticky) {
+            // row 0 decides (adaptive_filter_fast), every later row reuses that filter
+            P.row0 = 0; P.forced = nullptr; P.decided = decided + i0;
+            k_png_filter<<<dim3(1, nb), PNG_THREADS, smem, ctx->stream>>>(P);
+            ctx->launches++;
+            PIXO_CUDA(ctx, cudaGetLastError());
+            if (height > 1) {
+                P.row0 = 1; P.forced = decided + i0; P.decided = nullptr;
+                k_png_filter<<<dim3(height - 1, nb), PNG_THREADS, smem, ctx->stream>>>(P);
+                ctx->launches++;
+                PIXO_CUDA(ctx, cudaGetLastError());
+            }
+        } else {
+            P.row0 = 0; P.forced = nullptr; P.decided = nullptr;
+            k_png_filter<<<dim3(height, nb), PNG_THREADS, smem, ctx->stream>>>(P);
+            ctx->launches++;
+            PIXO_CUDA(ctx, cudaGetLastError());
+        }
+    }
+    return 0;
+}
+
+int launch_adler32(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t len, uint32_t *d_out)
+{
+    PIXO_TRY(ensure_dev(ctx, ctx->d_misc, 64));
+    auto *acc = reinterpret_cast<unsigned long long *>(ctx->d_misc.ptr);
+    auto *counter = reinterpret_cast<uint32_t *>(acc + 2);
+    PIXO_CUDA(ctx, cudaMemsetAsync(ctx->d_misc.ptr, 0, 64, ctx->stream));
+    size_t nvec = len / 16 + 1;
+    uint32_t grid = (uint32_t)((nvec + 256 * 8 - 1) / (256 * 8));
+    const uint32_t cap = (uint32_t)ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid == 0) grid = 1;
+    k_adler32<<<grid, 256, 0, ctx->stream>>>(d_data, len, acc, counter, d_out);
+    ctx->launches++;
+    PIXO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace pixo

@@ -1,0 +1,163 @@
+"""GPU parity: CUDA transform path (through the C ABI) vs the CPU oracle — bit-exact int16
+coefficients and byte-identical JPEG streams."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import pixo_b200
+from pixo_b200 import ColorType, jpeg
+from pixo_b200.jpeg import JpegOptions, Subsampling
+from util import EDGE_CASE_DIMENSIONS, images
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_coeffs(po, ctx, img, w, h, ct, ss, q):
+    y, cb, cr = jpeg.compute_all_coefficients(img, w, h, ColorType(ct), Subsampling(ss), q, ctx=ctx)
+    ry, rcb, rcr = po.jpeg_coefficients(img, w, h, ct, ss, q)
+    assert np.array_equal(y, ry), f"Y mismatch {w}x{h} ct={ct} ss={ss} q={q}: {(y != ry).sum()} coeffs"
+    assert np.array_equal(cb, rcb), f"Cb mismatch {w}x{h} ss={ss} q={q}: {(cb != rcb).sum()}"
+    assert np.array_equal(cr, rcr), f"Cr mismatch {w}x{h} ss={ss} q={q}: {(cr != rcr).sum()}"
+
+
+@pytest.mark.parametrize("w,h", EDGE_CASE_DIMENSIONS)
+def test_coefficients_edge_case_dimensions(po, gpu_ctx, w, h):
+    for name, img in images(po, w, h, 3).items():
+        for ss in (0, 1):
+            _check_coeffs(po, gpu_ctx, img, w, h, 2, ss, 80)
+    gray = po.gen_noise(w, h, 1, 11)
+    _check_coeffs(po, gpu_ctx, gray, w, h, 0, 0, 80)
+
+
+@pytest.mark.parametrize("q", [1, 10, 50, 75, 80, 95, 100])
+def test_coefficients_all_qualities(po, gpu_ctx, q):
+    w, h = 253, 131   # not MCU aligned, pitch not 16-byte aligned
+    for img in images(po, w, h, 3).values():
+        for ss in (0, 1):
+            _check_coeffs(po, gpu_ctx, img, w, h, 2, ss, q)
+
+
+@pytest.mark.parametrize("w,h", [(512, 16), (513, 16), (528, 33), (1040, 17), (31, 257), (3840, 32)])
+def test_coefficients_tile_boundaries(po, gpu_ctx, w, h):
+    # widths around the 32-MCU (512 px) tile and the 64-block tile of the 4:4:4 / gray kernels
+    img = po.gen_noise(w, h, 3, 5)
+    for ss in (0, 1):
+        _check_coeffs(po, gpu_ctx, img, w, h, 2, ss, 90)
+    _check_coeffs(po, gpu_ctx, po.gen_noise(w, h, 1, 6), w, h, 0, 0, 90)
+
+
+def test_c1_256_full_bitstream(po, gpu_ctx):
+    """BASELINE config C1: 256x256 RGB -> JPEG q=80, byte-identical files."""
+    w = h = 256
+    for img in images(po, w, h, 3).values():
+        for ss in (Subsampling.S420, Subsampling.S444):
+            for opt in (False, True):
+                for ri in (None, 5):
+                    o = JpegOptions(w, h, ColorType.Rgb, 80, ss, ri, opt)
+                    got = jpeg.encode(img, o, ctx=gpu_ctx)
+                    ref = po.jpeg_encode(img, w, h, 2, 80, int(ss), ri or 0, opt)
+                    assert got == ref
+
+
+def test_gray_full_bitstream(po, gpu_ctx):
+    w, h = 100, 75
+    img = po.gen_noise(w, h, 1, 2)
+    for q in (50, 95):
+        o = JpegOptions(w, h, ColorType.Gray, q, Subsampling.S444, None, True)
+        assert jpeg.encode(img, o, ctx=gpu_ctx) == po.jpeg_encode(img, w, h, 0, q, 0, 0, True)
+
+
+def test_c2_4k_coefficients_and_bitstream(po, gpu_ctx):
+    """BASELINE config C2 at full size: 3840x2160 q=80 4:2:0."""
+    w, h = 3840, 2160
+    for img in (po.gen_gradient_rgb(w, h), po.gen_noise(w, h, 3, 42)):
+        _check_coeffs(po, gpu_ctx, img, w, h, 2, 1, 80)
+        o = JpegOptions(w, h, ColorType.Rgb, 80, Subsampling.S420)
+        got = jpeg.encode(img, o, ctx=gpu_ctx)
+        ref = po.jpeg_encode(img, w, h, 2, 80, 1)
+        assert hashlib.sha256(got).digest() == hashlib.sha256(ref).digest()
+
+
+def test_c3_1080p_batch_qualities(po, gpu_ctx):
+    """BASELINE config C3 (a slice of it): 1920x1080 frames, q in {50,80,95}; height 1080 is
+    not a multiple of 16, so the last MCU row replicates."""
+    w, h, n = 1920, 1080, 6
+    frames = np.stack([po.gen_noise(w, h, 3, 42 + k) if k % 2 else np.roll(po.gen_gradient_rgb(w, h), k * w * 3)
+                       for k in range(n)])
+    for q in (50, 80, 95):
+        o = JpegOptions(w, h, ColorType.Rgb, q, Subsampling.S420)
+        got = jpeg.encode_batch(frames, o, ctx=gpu_ctx)
+        for k in range(n):
+            assert got[k] == po.jpeg_encode(frames[k], w, h, 2, q, 1), (q, k)
+    o = JpegOptions(w, h, ColorType.Rgb, 80, Subsampling.S420, None, True)
+    got = jpeg.encode_batch(frames[:3], o, ctx=gpu_ctx)
+    for k in range(3):
+        assert got[k] == po.jpeg_encode(frames[k], w, h, 2, 80, 1, 0, True)
+
+
+def test_zigzag_flag_and_histograms(po, gpu_ctx):
+    w, h = 333, 222
+    img = po.gen_noise(w, h, 3, 8)
+    for ss in (0, 1):
+        y, cb, cr, hist = jpeg.compute_all_coefficients(img, w, h, ColorType.Rgb, Subsampling(ss), 80,
+                                                        zigzag=True, histograms=True, ctx=gpu_ctx)
+        ry, rcb, rcr = po.jpeg_coefficients(img, w, h, 2, ss, 80)
+        zz = np.array([int(v) for v in po.zigzag_reorder(np.arange(64, dtype=np.int16))])
+        assert np.array_equal(y, ry[:, zz]) and np.array_equal(cb, rcb[:, zz]) and np.array_equal(cr, rcr[:, zz])
+        assert np.array_equal(hist, po.jpeg_histograms(ry, rcb, rcr, w, h, 2, ss))
+        _, _, _, hist2 = jpeg.compute_all_coefficients(img, w, h, ColorType.Rgb, Subsampling(ss), 80,
+                                                       histograms=True, ctx=gpu_ctx)
+        assert np.array_equal(hist2, hist)
+
+
+def test_custom_quant_tables_and_rejection(po, gpu_ctx):
+    w, h = 64, 64
+    img = po.gen_noise(w, h, 3, 1)
+    rng = np.random.default_rng(0)
+    lq = rng.integers(1, 256, 64).astype(np.float32); cq = rng.integers(1, 256, 64).astype(np.float32)
+    y, cb, cr = jpeg.compute_all_coefficients(img, w, h, lum_q=lq, chr_q=cq, ctx=gpu_ctx)
+    ry, rcb, rcr = po.jpeg_coefficients(img, w, h, 2, 1, lum_q=lq, chr_q=cq)
+    assert np.array_equal(y, ry) and np.array_equal(cb, rcb) and np.array_equal(cr, rcr)
+    lq[3] = 0.5
+    with pytest.raises(pixo_b200.PixoError):
+        jpeg.compute_all_coefficients(img, w, h, lum_q=lq, chr_q=cq, ctx=gpu_ctx)
+
+
+def test_error_behaviour_matches_reference(gpu_ctx):
+    # tests/jpeg_conformance.rs:242-292
+    E = pixo_b200._lib
+    for q in (0, 101):
+        with pytest.raises(pixo_b200.PixoError) as e:
+            jpeg.encode(bytes(3), JpegOptions(1, 1, ColorType.Rgb, q), ctx=gpu_ctx)
+        assert e.value.code == E.ERR_INVALID_QUALITY
+    with pytest.raises(pixo_b200.PixoError) as e:
+        jpeg.encode(bytes(3), JpegOptions(0, 1, ColorType.Rgb, 80), ctx=gpu_ctx)
+    assert e.value.code == E.ERR_INVALID_DIMENSIONS
+    with pytest.raises(pixo_b200.PixoError) as e:
+        jpeg.encode(bytes(4), JpegOptions(1, 1, ColorType.Rgba, 80), ctx=gpu_ctx)
+    assert e.value.code == E.ERR_UNSUPPORTED_COLOR
+    with pytest.raises(pixo_b200.PixoError) as e:
+        jpeg.encode(bytes(5), JpegOptions(1, 1, ColorType.Rgb, 80), ctx=gpu_ctx)
+    assert e.value.code == E.ERR_INVALID_DATA_LENGTH
+    with pytest.raises(pixo_b200.PixoError) as e:
+        jpeg.encode(bytes(3), JpegOptions(1, 1, ColorType.Rgb, 80, restart_interval=0), ctx=gpu_ctx)
+    assert e.value.code == E.ERR_INVALID_RESTART
+    with pytest.raises(pixo_b200.PixoError) as e:
+        jpeg.encode(bytes(3), JpegOptions(1, 1, ColorType.Rgb, 80, progressive=True), ctx=gpu_ctx)
+    assert e.value.code == E.ERR_UNSUPPORTED
+
+
+def test_determinism_and_decoder_acceptance(po, gpu_ctx):
+    import io
+    from PIL import Image
+    w, h = 200, 120
+    img = po.gen_gradient_rgb(w, h)
+    o = JpegOptions(w, h, ColorType.Rgb, 85, Subsampling.S420)
+    a = jpeg.encode(img, o, ctx=gpu_ctx)
+    assert a == jpeg.encode(img, o, ctx=gpu_ctx)
+    im = Image.open(io.BytesIO(a)); im.load()
+    assert im.size == (w, h)
+    sizes = [len(jpeg.encode(img, JpegOptions(w, h, ColorType.Rgb, q, Subsampling.S420), ctx=gpu_ctx))
+             for q in (10, 50, 90)]
+    assert sizes[0] < sizes[1] < sizes[2]   # tests/jpeg_conformance.rs:84

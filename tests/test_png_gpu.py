@@ -1,0 +1,101 @@
+"""GPU parity for the PNG filter-selection + Adler-32 path (through the C ABI) vs the oracle."""
+import zlib
+
+import numpy as np
+import pytest
+
+import pixo_b200
+from pixo_b200 import ColorType, png
+from pixo_b200.png import FilterStrategy, PngOptions
+
+pytestmark = pytest.mark.gpu
+
+STRATS = [FilterStrategy.NoFilter, FilterStrategy.Sub, FilterStrategy.Up, FilterStrategy.Average,
+          FilterStrategy.Paeth, FilterStrategy.MinSum, FilterStrategy.Adaptive, FilterStrategy.AdaptiveFast]
+
+
+def _smooth(w, h, bpp, seed):
+    rng = np.random.default_rng(seed)
+    x = np.cumsum(rng.integers(-2, 3, (h, w * bpp)), axis=1) + np.cumsum(rng.integers(-1, 2, (h, 1)), axis=0)
+    return (x & 255).astype(np.uint8).reshape(-1)
+
+
+@pytest.mark.parametrize("bpp", [1, 2, 3, 4])
+@pytest.mark.parametrize("w,h", [(1, 1), (3, 2), (64, 64), (65, 64), (100, 33), (257, 40), (1000, 7), (4099, 35)])
+def test_filters_match_oracle(po, gpu_ctx, w, h, bpp):
+    # tests/simd_fallback_equality.rs shape: seeded rows, bpp 1-4, assorted widths
+    for name, img in (("noise", po.gen_noise(w, h, bpp, 42)), ("smooth", _smooth(w, h, bpp, 1)),
+                      ("zeros", np.zeros(w * h * bpp, np.uint8))):
+        for st in STRATS:
+            opts = PngOptions(w, h, ColorType.Rgba, st)
+            got, ad = png.apply_filters(img, w, h, bpp, opts, with_adler=True, ctx=gpu_ctx)
+            ref = po.apply_filters(img, w, h, bpp, int(st))
+            assert np.array_equal(got, ref), (name, st, w, h, bpp, np.flatnonzero(got != ref)[:5])
+            assert ad == po.adler32(ref) == zlib.adler32(ref.tobytes())
+
+
+def test_sticky_adaptive_fast_small_height(po, gpu_ctx):
+    # height <= 32 takes the sequential path where AdaptiveFast reuses row 0's winner
+    for w, h in ((300, 32), (300, 20), (5000, 2)):
+        for img in (po.gen_noise(w, h, 4, 3), _smooth(w, h, 4, 2)):
+            got = png.apply_filters(img, w, h, 4, PngOptions(w, h, ColorType.Rgba, FilterStrategy.AdaptiveFast), ctx=gpu_ctx)
+            ref = po.apply_filters(img, w, h, 4, po.F_ADAPTIVE_FAST)
+            assert np.array_equal(got, ref)
+            assert len(set(ref.reshape(h, -1)[:, 0])) == 1
+
+
+def test_row_bytes_override_sub_byte_depth(po, gpu_ctx):
+    # palette / low-bit-depth rows: row_bytes != width*bpp (src/png/mod.rs:556-560)
+    w, h, row_bytes = 1001, 50, 126
+    img = po.gen_noise(row_bytes, h, 1, 4)
+    got = png.apply_filters_with_row_bytes(img, w, h, row_bytes, 1, PngOptions(w, h, ColorType.Gray, FilterStrategy.Adaptive), ctx=gpu_ctx)
+    assert np.array_equal(got, po.apply_filters(img, w, h, 1, po.F_ADAPTIVE, row_bytes=row_bytes))
+
+
+def test_c5_4k_rgba(po, gpu_ctx):
+    """BASELINE config C5 geometry at full size: 3840x2160 RGBA, Adaptive and AdaptiveFast."""
+    w, h = 3840, 2160
+    rgb = po.gen_gradient_rgb(w, h).reshape(h, w, 3)
+    grad = np.concatenate([rgb, np.full((h, w, 1), 255, np.uint8)], -1).reshape(-1)
+    for img in (grad, po.gen_noise(w, h, 4, 42)):
+        for st in (FilterStrategy.Adaptive, FilterStrategy.AdaptiveFast):
+            got, ad = png.apply_filters(img, w, h, 4, PngOptions(w, h, ColorType.Rgba, st), with_adler=True, ctx=gpu_ctx)
+            ref = po.apply_filters(img, w, h, 4, int(st))
+            assert np.array_equal(got, ref)
+            assert ad == zlib.adler32(ref.tobytes())
+
+
+def test_long_rows_span_segments(po, gpu_ctx):
+    # rows longer than the 32 KiB staging segment
+    w, h, bpp = 30000, 40, 4
+    img = _smooth(w, h, bpp, 5)
+    for st in (FilterStrategy.Adaptive, FilterStrategy.Paeth, FilterStrategy.AdaptiveFast):
+        got, ad = png.apply_filters(img, w, h, bpp, PngOptions(w, h, ColorType.Rgba, st), with_adler=True, ctx=gpu_ctx)
+        ref = po.apply_filters(img, w, h, bpp, int(st))
+        assert np.array_equal(got, ref)
+        assert ad == zlib.adler32(ref.tobytes())
+
+
+def test_adler32_known_answers_and_sizes(po, gpu_ctx):
+    assert png.adler32(b"", ctx=gpu_ctx) == 1
+    assert png.adler32(b"hello", ctx=gpu_ctx) == 0x062C0215
+    assert png.adler32(b"Adler-32", ctx=gpu_ctx) == 0x0C34027B
+    assert png.adler32(b"123456789", ctx=gpu_ctx) == 0x091E01DE
+    rng = np.random.default_rng(0)
+    for n in (1, 15, 16, 17, 5552, 5553, 65521, 1 << 20, (1 << 24) + 3):
+        d = rng.integers(0, 256, n, dtype=np.uint8)
+        assert png.adler32(d, ctx=gpu_ctx) == zlib.adler32(d.tobytes())
+    d = np.full(33179760, 255, np.uint8)   # C5 filtered-stream size, worst-case sums
+    assert png.adler32(d, ctx=gpu_ctx) == zlib.adler32(d.tobytes())
+
+
+def test_unsupported_and_invalid(gpu_ctx):
+    E = pixo_b200._lib
+    img = np.zeros(70 * 70 * 4, np.uint8)
+    with pytest.raises(pixo_b200.PixoError) as e:
+        png.apply_filters(img, 70, 70, 4, PngOptions(70, 70, ColorType.Rgba, FilterStrategy.Bigrams), ctx=gpu_ctx)
+    assert e.value.code == E.ERR_UNSUPPORTED
+    with pytest.raises(pixo_b200.PixoError):
+        png.apply_filters(img, 70, 70, 5, PngOptions(70, 70), ctx=gpu_ctx)
+    with pytest.raises(pixo_b200.PixoError):
+        png.apply_filters(img[:-1], 70, 70, 4, PngOptions(70, 70), ctx=gpu_ctx)
