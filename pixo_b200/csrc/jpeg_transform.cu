@@ -14,6 +14,9 @@
 // conflict-free (24-byte lane stride), colour-convert with dp4a, and leave packed 2x2 chroma
 // sums (cb | cr<<16) in a swizzled 8 KB exchange buffer from which the chroma threads build
 // their blocks.  HBM traffic is exactly the algorithmic 3 B/px in + 3 B/px out.
+#include <cuda.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace pixo {
@@ -247,95 +250,461 @@ __device__ __forceinline__ void load_tile(uint8_t *__restrict__ smem,
 }
 
 // =========================================================================================
-// K1: RGB, 4:2:0.  CTA = 128 threads = 32 MCUs of one MCU row.
+// Packed (f32x2) block pipeline.  Blackwell issues add/mul/fma.f32x2 (SASS FADD2/FMUL2/FFMA2)
+// at half the instruction rate of the scalar forms but the same lane rate, so two butterflies
+// cost one issue slot — and every lane still performs exactly one IEEE binary32 rounding per
+// reference operation (measured: tools/ubench/f32x2.cu).
+// =========================================================================================
+typedef unsigned long long f2;  // two binary32 lanes: lo = bits 0..31, hi = bits 32..63
+
+__device__ __forceinline__ f2 pk(float lo, float hi)
+{
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(f2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void upk_u(f2 v, uint32_t &lo, uint32_t &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b)
+{
+    f2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b)
+{
+    f2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b)
+{
+    f2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c)
+{
+    f2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f2 add2_rz(f2 a, f2 b)
+{
+    f2 d;
+    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2 fma2_rm(f2 a, f2 b, f2 c)
+{
+    f2 d;
+    asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+#define K2(c) pk((c), (c))
+
+// Multiply both lanes by a constant with two *scalar* FMULs.  ptxas 12.9 contracts
+// mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 (one rounding) even under --fmad=false, which
+// would break bit-parity; scalar mul.rn.f32 is never contracted.  Used wherever a product
+// feeds a packed add, and for the row pass's post-scale, whose two scalar results land directly
+// in the registers of the column-pair layout (no transpose moves).
+__device__ __forceinline__ void mulc(f2 a, float c, float &lo, float &hi)
+{
+    float x, y;
+    upk(a, x, y);
+    lo = FMUL(x, c);
+    hi = FMUL(y, c);
+}
+__device__ __forceinline__ f2 mul2c(f2 a, float c)
+{
+    float lo, hi;
+    mulc(a, c, lo, hi);
+    return pk(lo, hi);
+}
+
+// aan_dct_1d (src/jpeg/dct.rs:648-700) on two independent 8-vectors at once; returns the eight
+// outputs *before* the S[k] post-scale (o[k]), which the caller applies.
+__device__ __forceinline__ void aan_1d_x2_core(const f2 (&d)[8], f2 (&o)[8])
+{
+    const f2 tmp0 = add2(d[0], d[7]), tmp7 = sub2(d[0], d[7]);
+    const f2 tmp1 = add2(d[1], d[6]), tmp6 = sub2(d[1], d[6]);
+    const f2 tmp2 = add2(d[2], d[5]), tmp5 = sub2(d[2], d[5]);
+    const f2 tmp3 = add2(d[3], d[4]), tmp4 = sub2(d[3], d[4]);
+
+    const f2 tmp10 = add2(tmp0, tmp3), tmp13 = sub2(tmp0, tmp3);
+    const f2 tmp11 = add2(tmp1, tmp2), tmp12 = sub2(tmp1, tmp2);
+
+    o[0] = add2(tmp10, tmp11);
+    o[4] = sub2(tmp10, tmp11);
+    const f2 z1 = mul2c(add2(tmp12, tmp13), AAN_A1);
+    o[2] = add2(tmp13, z1);
+    o[6] = sub2(tmp13, z1);
+
+    const f2 u10 = add2(tmp4, tmp5), u11 = add2(tmp5, tmp6), u12 = add2(tmp6, tmp7);
+    const f2 z5 = mul2c(sub2(u10, u12), AAN_A5);
+    const f2 z2 = add2(mul2c(u10, AAN_A2), z5);
+    const f2 z4 = add2(mul2c(u12, AAN_A4), z5);
+    const f2 z3 = mul2c(u11, AAN_A3);
+    const f2 z11 = add2(tmp7, z3), z13 = sub2(tmp7, z3);
+
+    o[5] = add2(z13, z2);
+    o[3] = sub2(z13, z2);
+    o[1] = add2(z11, z4);
+    o[7] = sub2(z11, z4);
+}
+
+// One table entry per output word (two adjacent natural-order coefficients):
+// (-d_lo, -d_hi, r_lo, r_hi) with r = RN(1/d).
+struct __align__(16) QPair {
+    float nd_lo, nd_hi, r_lo, r_hi;
+};
+
+// dct_2d (src/jpeg/dct.rs:614-646) + quantize_block (src/jpeg/quantize.rs:99-105) on a block
+// held as row pairs R[i][c] = (v[2i][c], v[2i+1][c]); writes 64 int16 (8 x 16 B).
+//   x / d      : q0 = x*r; q = fma(fma(q0, -d, x), r, q0) == RN(x/d)     (tools/verify_div.c)
+//   round      : w = RZ(q + 0.5); m = floor(sign(q) * w) via fma.rm with 1.5*2^23;
+//                result = m for q >= 0, ~m for q < 0  == round-half-away(q)  (tests prove it
+//                bit-for-bit against the oracle; derivation in DESIGN.md)
+template <bool ZIGZAG>
+__device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *__restrict__ tab,
+                                                   int16_t *__restrict__ out)
+{
+    constexpr float SK[8] = {AAN_S0, AAN_S1, AAN_S2, AAN_S3, AAN_S4, AAN_S5, AAN_S6, AAN_S7};
+    // row pass on row pairs; the post-scale is done lane by lane so the results land in the
+    // column-pair layout C[r][j] = (V[r][2j], V[r][2j+1]) without transposes
+    f2 C[8][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f2 o[8];
+        aan_1d_x2_core(R[i], o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a0, a1, b0, b1;
+            mulc(o[2 * j], SK[2 * j], a0, a1);          // (V[2i][2j],   V[2i+1][2j])
+            mulc(o[2 * j + 1], SK[2 * j + 1], b0, b1);  // (V[2i][2j+1], V[2i+1][2j+1])
+            C[2 * i][j] = pk(a0, b0);
+            C[2 * i + 1][j] = pk(a1, b1);
+        }
+    }
+    // column pass on column pairs; post-scale packed (it feeds only multiplies / fma addends)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const f2 in[8] = {C[0][j], C[1][j], C[2][j], C[3][j], C[4][j], C[5][j], C[6][j], C[7][j]};
+        f2 o[8];
+        aan_1d_x2_core(in, o);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) C[r][j] = mul2(o[r], K2(SK[r]));
+    }
+
+    uint32_t W[32];
+    const f2 half2 = K2(0.5f), magic2 = K2(12582912.0f);  // 1.5 * 2^23
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 t = *reinterpret_cast<const float4 *>(&tab[r * 4 + j]);
+            const f2 nd = pk(t.x, t.y), rc = pk(t.z, t.w);
+            const f2 x = C[r][j];
+            const f2 q0 = mul2(x, rc);
+            const f2 e = fma2(q0, nd, x);
+            const f2 q = fma2(e, rc, q0);
+            uint32_t ql, qh;
+            upk_u(q, ql, qh);
+            const f2 s = pk(__uint_as_float((ql & 0x80000000u) | 0x3F800000u),
+                            __uint_as_float((qh & 0x80000000u) | 0x3F800000u));
+            const f2 w = add2_rz(q, half2);
+            const f2 tt = fma2_rm(w, s, magic2);
+            uint32_t tl, th, neg;
+            upk_u(tt, tl, th);
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(neg) : "r"(ql), "r"(qh), "r"(0xFFBBu));
+            W[r * 4 + j] = __byte_perm(tl, th, 0x5410) ^ neg;
+        }
+    uint4 *o = reinterpret_cast<uint4 *>(out);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t w[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            if (ZIGZAG) {
+                const int i0 = zz(k * 8 + m * 2), i1 = zz(k * 8 + m * 2 + 1);
+                w[m] = __byte_perm(W[i0 >> 1], W[i1 >> 1],
+                                   ((i0 & 1) ? 0x0032 : 0x0010) | ((i1 & 1) ? 0x7600 : 0x5400));
+            } else {
+                w[m] = W[k * 4 + m];
+            }
+        }
+        o[k] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// Quantisation tables in the layout dct_quant_store_x2 wants.  scale: the block handed to the
+// DCT is `scale` x the reference's block (4 for 4:2:0 chroma, whose x0.25 is folded in here:
+// power-of-two scaling commutes exactly with every rounding in the pipeline).
+struct QuantSmem {
+    QPair lum[32];
+    QPair chr[32];
+};
+
+__device__ __forceinline__ void fill_quant_smem(QuantSmem *q, const QuantTab &qt, float chr_scale,
+                                                int tid, int nthreads)
+{
+    for (int w = tid; w < 64; w += nthreads) {
+        const bool c = w >= 32;
+        const int i = (w & 31) * 2;
+        const float *d = c ? qt.chr_d : qt.lum_d;
+        const float *r = c ? qt.chr_r : qt.lum_r;
+        const float sc = c ? chr_scale : 1.0f;
+        QPair e;
+        e.nd_lo = -(d[i] * sc);
+        e.nd_hi = -(d[i + 1] * sc);
+        e.r_lo = r[i] / sc;
+        e.r_hi = r[i + 1] / sc;
+        (c ? q->chr : q->lum)[w & 31] = e;
+    }
+}
+
+// ---- TMA / mbarrier plumbing ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const void *tmap, int x, int y, int z,
+                                            uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+        "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// =========================================================================================
+// K1: RGB, 4:2:0.  Persistent CTAs of 128 threads; a tile is 32 MCUs (512 x 16 px, 24 KB) of
+// one MCU row.  Interior tiles of 16-byte-pitched images arrive by TMA (one 3-D
+// cp.async.bulk.tensor per tile, issued as soon as the previous tile's pixels have been
+// consumed, so the load of tile k+1 overlaps the chroma pass and the stores of tile k);
+// edge tiles (bottom replication) and unaligned images use the cooperative clamped loader.
 // =========================================================================================
 constexpr int K1_THREADS = 128;
+#ifndef K1_MIN_BLOCKS
+#define K1_MIN_BLOCKS 3
+#endif
 constexpr int K1_MCUS = 32;
 constexpr int K1_TB = K1_MCUS * 16 * 3;  // 1536 bytes per tile row
+constexpr int K1_TILE_BYTES = 16 * K1_TB;
+
+struct K1Params {
+    const uint8_t *pixels;
+    size_t pixel_stride;
+    uint32_t w, h, mcus_x, mcus_y, tiles_x, n_images;
+    int16_t *y, *cb, *cr;
+    size_t y_stride, c_stride;
+    uint32_t use_tma;
+};
+
+struct __align__(128) K1Smem {
+    uint8_t tile[K1_TILE_BYTES];
+    uint32_t csum[2][K1_MCUS * 64];
+    QuantSmem q;
+    uint64_t bar;
+};
+
+// One RGB row of a Y block (8 px in six words): Y - 128 as float for each pixel and the packed
+// chroma terms P = [(256 - cb) | 0xFF00, (256 - cr) | 0xFF00] clamped per colour.rs.
+//   y        = (77r + 150g + 29b + 128) >> 8
+//   256 - cb = byte 1 of (43r + 85g - 128b - 32641)     [cb = ((-43r-85g+128b+128)>>8)+128]
+//   256 - cr = byte 1 of (-128r + 107g + 21b - 32641)
+// All three dot products read the raw 4-byte window (r,g,b,next r) with a zero 4th weight.
+__device__ __forceinline__ void ycc_row8(const uint32_t (&w)[6], float (&yv)[8], uint32_t (&hs)[4])
+{
+    uint32_t win[8];
+    win[0] = w[0];
+    win[1] = __funnelshift_r(w[0], w[1], 24);
+    win[2] = __funnelshift_r(w[1], w[2], 16);
+    win[3] = w[2] >> 8;
+    win[4] = w[3];
+    win[5] = __funnelshift_r(w[3], w[4], 24);
+    win[6] = __funnelshift_r(w[4], w[5], 16);
+    win[7] = w[5] >> 8;
+    uint32_t pp[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+        const uint32_t ys = __dp4a(win[x], 0x001D964Du, 128u);
+        const int ucb = dp4a_us(win[x], 0x0080552Bu, -32641);
+        const int ucr = dp4a_us(win[x], 0x00156B80u, -32641);
+        yv[x] = byte1_to_float_minus(ys, 8388736.0f);
+        pp[x] = __vmaxu2(__byte_perm((uint32_t)ucb, (uint32_t)ucr, 0x7531), 0xFF01FF01u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hs[k] = pp[2 * k] + pp[2 * k + 1];
+}
 
 template <bool ZIGZAG>
-__global__ void __launch_bounds__(K1_THREADS)
-k_jpeg_420(const uint8_t *__restrict__ pixels, size_t pixel_stride, uint32_t w, uint32_t h,
-           uint32_t mcus_x, uint32_t tiles_x, int16_t *__restrict__ yout, size_t y_stride,
-           int16_t *__restrict__ cbout, int16_t *__restrict__ crout, size_t c_stride,
-           const __grid_constant__ QuantTab qt)
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
+k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab qt,
+           const __grid_constant__ CUtensorMap tmap)
 {
-    __shared__ __align__(16) uint8_t tile[16 * K1_TB];
-    __shared__ __align__(16) uint32_t csum[K1_MCUS * 64];
-
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    K1Smem &S = *reinterpret_cast<K1Smem *>(smem_raw);
     const int tid = threadIdx.x;
-    const uint32_t tx = blockIdx.x % tiles_x;
-    const uint32_t my = blockIdx.x / tiles_x;
-    const uint32_t img = blockIdx.y;
-    const uint8_t *image = pixels + (size_t)img * pixel_stride;
-
-    load_tile<3, 16, K1_MCUS * 16, K1_THREADS>(tile, image, w, h, tx * (K1_MCUS * 16), my * 16,
-                                                tid);
-    __syncthreads();
-
     const int lane = tid & 31, warp = tid >> 5;
-    const uint32_t mcu0 = tx * K1_MCUS;
-    const uint32_t n_mcu = min((uint32_t)K1_MCUS, mcus_x - mcu0);
 
-    // ---- phase 1: one Y block per thread + packed chroma quad sums ----
-    {
-        const int by = lane >> 4, l16 = lane & 15;
-        const int par = l16 >> 3, k8 = l16 & 7;
-        const int mcu = warp * 8 + (k8 >> 1) * 2 + par;  // same-parity MCUs per quarter warp
-        const int bx = k8 & 1;
-        if ((uint32_t)mcu < n_mcu) {
-            float v[64];
-            const uint8_t *base = tile + (by * 8) * K1_TB + (mcu * 2 + bx) * 24;
-            uint4 *cdst = reinterpret_cast<uint4 *>(csum) + mcu * 16;
-#pragma unroll
-            for (int rp = 0; rp < 4; ++rp) {
-                uint32_t q[4];
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    const int r = rp * 2 + rr;
-                    const uint2 *p = reinterpret_cast<const uint2 *>(base + r * K1_TB);
-                    const uint2 a = p[0], b = p[1], c = p[2];
-                    const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-                    uint32_t bb[8], br[8], cc[8];
-                    unpack8(wds, bb, br);
-#pragma unroll
-                    for (int x = 0; x < 8; ++x) v[r * 8 + x] = ycc_pixel(bb[x], br[x], &cc[x]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t hs = cc[2 * k] + cc[2 * k + 1];
-                        q[k] = rr == 0 ? hs : q[k] + hs;
-                    }
-                }
-                const int logical = (by * 4 + rp) * 2 + bx;
-                cdst[logical ^ (mcu & 7)] = make_uint4(q[0], q[1], q[2], q[3]);
-            }
-            const size_t blk = ((size_t)(my * mcus_x + mcu0 + mcu)) * 4 + by * 2 + bx;
-            dct_quant_store<ZIGZAG>(v, qt.lum_d, qt.lum_r,
-                                    yout + (size_t)img * y_stride + blk * 64);
-        }
+    fill_quant_smem(&S.q, qt, 4.0f, tid, K1_THREADS);
+    if (tid == 0) {
+        mbar_init(&S.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // ---- phase 2: warp 0 = Cb blocks, warp 1 = Cr blocks ----
-    if (warp < 2 && (uint32_t)lane < n_mcu) {
-        const int mcu = lane;
-        const uint4 *csrc = reinterpret_cast<const uint4 *>(csum) + mcu * 16;
-        const uint32_t sel = warp == 0 ? 0x7610u : 0x7632u;
-        float v[64];
-#pragma unroll
-        for (int l = 0; l < 16; ++l) {
-            const uint4 s = csrc[l ^ (mcu & 7)];
-            const uint32_t sw[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                // (sum of four u8) * 0.25 - 128.0, src/jpeg/mod.rs:1642-1653 (exact in binary32)
-                const float f = __uint_as_float(__byte_perm(sw[k], 0x4B000000u, sel));
-                v[l * 4 + k] = FMUL(FSUB(f, 8389120.0f), 0.25f);  // 2^23 + 512
-            }
+    const uint64_t tiles_per_img = (uint64_t)P.mcus_y * P.tiles_x;
+    const uint64_t ntiles = tiles_per_img * P.n_images;
+    uint32_t phase = 0;
+
+    auto decode = [&](uint64_t t, uint32_t &img, uint32_t &my, uint32_t &tx) {
+        img = (uint32_t)(t / tiles_per_img);
+        const uint32_t rem = (uint32_t)(t - (uint64_t)img * tiles_per_img);
+        my = rem / P.tiles_x;
+        tx = rem - my * P.tiles_x;
+    };
+    auto tile_by_tma = [&](uint32_t my) { return P.use_tma && (my * 16 + 16 <= P.h); };
+    auto issue_tma = [&](uint64_t t) {
+        uint32_t img, my, tx;
+        decode(t, img, my, tx);
+        if (tile_by_tma(my)) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&S.bar, K1_TILE_BYTES);
+            tma_load_3d(S.tile, &tmap, (int)(tx * (K1_TB / 8)), (int)(my * 16), (int)img, &S.bar);
         }
-        const size_t blk = (size_t)(my * mcus_x + mcu0 + mcu);
-        int16_t *dst = (warp == 0 ? cbout : crout) + (size_t)img * c_stride + blk * 64;
-        dct_quant_store<ZIGZAG>(v, qt.chr_d, qt.chr_r, dst);
+    };
+
+    uint64_t t = blockIdx.x;
+    if (t < ntiles && tid == 0) issue_tma(t);
+
+    for (uint32_t it = 0; t < ntiles; t += gridDim.x, ++it) {
+        uint32_t img, my, tx;
+        decode(t, img, my, tx);
+        if (tile_by_tma(my)) {
+            mbar_wait(&S.bar, phase);
+            phase ^= 1;
+        } else {
+            load_tile<3, 16, K1_MCUS * 16, K1_THREADS>(S.tile, P.pixels + (size_t)img * P.pixel_stride,
+                                                        P.w, P.h, tx * (K1_MCUS * 16), my * 16, tid);
+            __syncthreads();
+        }
+        const uint32_t mcu0 = tx * K1_MCUS;
+        const uint32_t n_mcu = min((uint32_t)K1_MCUS, P.mcus_x - mcu0);
+        uint32_t *csum = S.csum[it & 1];
+
+#pragma unroll 1
+        for (int job = 0; job < 2; ++job) {
+            f2 R[4][8];
+            const QPair *tab;
+            int16_t *dst;
+            bool active;
+            if (job == 0) {
+                // ---- one Y block per thread + packed chroma quad sums ----
+                const int by = lane >> 4, l16 = lane & 15;
+                const int par = l16 >> 3, k8 = l16 & 7;
+                const int mcu = warp * 8 + (k8 >> 1) * 2 + par;  // same-parity MCUs per quarter warp
+                const int bx = k8 & 1;
+                active = (uint32_t)mcu < n_mcu;
+                const uint8_t *base = S.tile + (by * 8) * K1_TB + (mcu * 2 + bx) * 24;
+                uint4 *cdst = reinterpret_cast<uint4 *>(csum) + mcu * 16;
+                if (active) {
+#pragma unroll
+                    for (int rp = 0; rp < 4; ++rp) {
+                        float y0[8], y1[8];
+                        uint32_t h0[4], h1[4];
+                        {
+                            const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2) * K1_TB);
+                            const uint2 a = p[0], b = p[1], c = p[2];
+                            const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+                            ycc_row8(wds, y0, h0);
+                        }
+                        {
+                            const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2 + 1) * K1_TB);
+                            const uint2 a = p[0], b = p[1], c = p[2];
+                            const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+                            ycc_row8(wds, y1, h1);
+                        }
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) R[rp][x] = pk(y0[x], y1[x]);
+                        const int logical = (by * 4 + rp) * 2 + bx;
+                        cdst[logical ^ (mcu & 7)] =
+                            make_uint4(h0[0] + h1[0], h0[1] + h1[1], h0[2] + h1[2], h0[3] + h1[3]);
+                    }
+                }
+                const size_t blk = ((size_t)my * P.mcus_x + mcu0 + mcu) * 4 + by * 2 + bx;
+                dst = P.y + (size_t)img * P.y_stride + blk * 64;
+                tab = S.q.lum;
+            } else {
+                __syncthreads();  // csum complete; every thread is done with the pixel tile
+                const uint64_t tn = t + gridDim.x;
+                if (tid == 0 && tn < ntiles) issue_tma(tn);
+                if (warp >= 2) break;
+                // ---- warp 0 = Cb blocks, warp 1 = Cr blocks ----
+                const int mcu = lane;
+                active = (uint32_t)mcu < n_mcu;
+                const uint4 *csrc = reinterpret_cast<const uint4 *>(csum) + mcu * 16;
+                const uint32_t sel = warp == 0 ? 0x7610u : 0x7632u;
+                // low half = 65536 - sum(cb), high half = 65539 - sum(cr)  (see ycc_row8);
+                // block value = 4 * (sum * 0.25 - 128) = sum - 512  (src/jpeg/mod.rs:1642-1653)
+                const float bias = warp == 0 ? 8453632.0f : 8453635.0f;  // 2^23 + 65536(+3) - 512
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float v0[8], v1[8];
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int l0 = (2 * i) * 2 + hh, l1 = (2 * i + 1) * 2 + hh;
+                            const uint4 s0 = csrc[l0 ^ (mcu & 7)];
+                            const uint4 s1 = csrc[l1 ^ (mcu & 7)];
+                            const uint32_t a[4] = {s0.x, s0.y, s0.z, s0.w};
+                            const uint32_t b[4] = {s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                v0[hh * 4 + k] = FSUB(bias, __uint_as_float(__byte_perm(a[k], 0x4B000000u, sel)));
+                                v1[hh * 4 + k] = FSUB(bias, __uint_as_float(__byte_perm(b[k], 0x4B000000u, sel)));
+                            }
+                        }
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) R[i][x] = pk(v0[x], v1[x]);
+                    }
+                }
+                const size_t blk = (size_t)my * P.mcus_x + mcu0 + mcu;
+                dst = (warp == 0 ? P.cb : P.cr) + (size_t)img * P.c_stride + blk * 64;
+                tab = S.q.chr;
+            }
+            if (active) dct_quant_store_x2<ZIGZAG>(R, tab, dst);
+        }
     }
 }
 
@@ -513,6 +882,78 @@ void make_quant_tab(const float *lum_q, const float *chr_q, QuantTab *qt)
 
 }  // namespace
 
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// 3-D view of a batch of interleaved-RGB frames for TMA: (8-byte words per row, rows, frames).
+bool make_rgb_tensor_map(CUtensorMap *tm, const uint8_t *pixels, size_t pixel_stride, uint32_t n,
+                         uint32_t w, uint32_t h)
+{
+    const size_t pitch = (size_t)w * 3;
+    if (pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(pixels) & 15) != 0) return false;
+    if (n > 1 && pixel_stride % 16 != 0) return false;
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {pitch / 8, h, n};
+    const cuuint64_t gstr[2] = {pitch, n > 1 ? pixel_stride : pitch * h};
+    const cuuint32_t box[3] = {K1_TB / 8, 16, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t *>(pixels), gdim, gstr, box,
+               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int launch_k1(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint32_t n, uint32_t w,
+              uint32_t h, int16_t *y, size_t y_stride, int16_t *cb, int16_t *cr, size_t c_stride,
+              const QuantTab &qt, bool zigzag)
+{
+    K1Params P;
+    P.pixels = px; P.pixel_stride = pixel_stride; P.w = w; P.h = h;
+    P.mcus_x = (w + 15) / 16; P.mcus_y = (h + 15) / 16;
+    P.tiles_x = (P.mcus_x + K1_MCUS - 1) / K1_MCUS;
+    P.n_images = n; P.y = y; P.cb = cb; P.cr = cr; P.y_stride = y_stride; P.c_stride = c_stride;
+    alignas(64) CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    P.use_tma = make_rgb_tensor_map(&tm, px, pixel_stride, n, w, h) ? 1u : 0u;
+    static int blocks_per_sm[2] = {0, 0};
+    const size_t smem = sizeof(K1Smem);
+    auto kern = zigzag ? k_jpeg_420<true> : k_jpeg_420<false>;
+    if (!blocks_per_sm[zigzag]) {
+        PIXO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        PIXO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K1_THREADS, smem));
+        blocks_per_sm[zigzag] = nb > 0 ? nb : 1;
+    }
+    const uint64_t ntiles = (uint64_t)P.mcus_y * P.tiles_x * n;
+    uint64_t grid = (uint64_t)ctx->sm_count * blocks_per_sm[zigzag];
+    if (grid > ntiles) grid = ntiles;
+    kern<<<(unsigned)grid, K1_THREADS, smem, ctx->stream>>>(P, qt, tm);
+    ctx->launches++;
+    PIXO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
 int launch_jpeg_transform(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pixel_stride,
                           uint32_t n_images, uint32_t w, uint32_t h, uint32_t color_type,
                           uint32_t subsampling, const float *lum_q, const float *chr_q,
@@ -549,11 +990,8 @@ int launch_jpeg_transform(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pi
             if (zigzag) k_jpeg_444<true><<<grid, 192, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, cb, cr, c_stride, qt);
             else k_jpeg_444<false><<<grid, 192, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, cb, cr, c_stride, qt);
         } else {
-            const uint32_t mx = (w + 15) / 16, my = (h + 15) / 16;
-            const uint32_t tiles_x = (mx + K1_MCUS - 1) / K1_MCUS;
-            dim3 grid(tiles_x * my, nb);
-            if (zigzag) k_jpeg_420<true><<<grid, K1_THREADS, 0, ctx->stream>>>(px, pixel_stride, w, h, mx, tiles_x, y, y_stride, cb, cr, c_stride, qt);
-            else k_jpeg_420<false><<<grid, K1_THREADS, 0, ctx->stream>>>(px, pixel_stride, w, h, mx, tiles_x, y, y_stride, cb, cr, c_stride, qt);
+            PIXO_TRY(launch_k1(ctx, px, pixel_stride, nb, w, h, y, y_stride, cb, cr, c_stride, qt, zigzag));
+            continue;
         }
         ctx->launches++;
         PIXO_CUDA(ctx, cudaGetLastError());

@@ -30,7 +30,8 @@ constexpr int SEG_BYTES = 32768;  // bytes of a row staged per pass segment
 __device__ __forceinline__ uint32_t sum_abs_s8x4(uint32_t v)
 {
     // sum over bytes of |(i8)byte|: sign mask via PRMT sign-replicate, then dp4a with +-1
-    const uint32_t neg = __byte_perm(v, 0u, 0xBA98);  // 0xFF where byte < 0
+    uint32_t neg;  // 0xFF where byte < 0 (prmt selector msb = replicate the byte's sign)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(neg) : "r"(v), "r"(0u), "r"(0xBA98u));
     const uint32_t sgn = neg | 0x01010101u;           // -1 / +1 as s8
     return (uint32_t)__dp4a((int)v, (int)sgn, 0);
 }

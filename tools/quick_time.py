@@ -9,7 +9,9 @@ from pixo_b200 import _lib, jpeg
 
 lib = _lib.load()
 ctx = pixo_b200.Context(0)
-ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+ctx.set_stream(stream.cuda_stream)
 _, _, lq, cq = jpeg.quant_tables(80)
 
 
