@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libpixo_b200.so")
+SO_PATH = os.environ.get("PIXO_B200_SO") or os.path.join(_HERE, "libpixo_b200.so")
 
 u8p = C.POINTER(C.c_uint8)
 i16p = C.POINTER(C.c_int16)

@@ -330,8 +330,20 @@ __device__ __forceinline__ f2 mul2c(f2 a, float c)
 
 // aan_dct_1d (src/jpeg/dct.rs:648-700) on two independent 8-vectors at once; returns the eight
 // outputs *before* the S[k] post-scale (o[k]), which the caller applies.
-__device__ __forceinline__ void aan_1d_x2_core(const f2 (&d)[8], f2 (&o)[8])
+// Products that feed an add are written as fma(x, c, z) with z an opaque +0.0 pair (a kernel
+// parameter): RN(x*c + 0) == RN(x*c), and ptxas cannot contract an FFMA2 into the following
+// FADD2 the way it contracts FMUL2 (see mulc above).  The only observable difference is that a
+// zero product is always +0 — which can only ever change the sign of a zero downstream.
+__device__ __forceinline__ void aan_1d_x2_core(const f2 (&d)[8], f2 (&o)[8], const f2 zero2)
 {
+#ifndef OPT_MULZ
+#define OPT_MULZ 1
+#endif
+#if OPT_MULZ
+#define MULZ(a, c) fma2((a), K2(c), zero2)
+#else
+#define MULZ(a, c) mul2c((a), (c))
+#endif
     const f2 tmp0 = add2(d[0], d[7]), tmp7 = sub2(d[0], d[7]);
     const f2 tmp1 = add2(d[1], d[6]), tmp6 = sub2(d[1], d[6]);
     const f2 tmp2 = add2(d[2], d[5]), tmp5 = sub2(d[2], d[5]);
@@ -342,21 +354,22 @@ __device__ __forceinline__ void aan_1d_x2_core(const f2 (&d)[8], f2 (&o)[8])
 
     o[0] = add2(tmp10, tmp11);
     o[4] = sub2(tmp10, tmp11);
-    const f2 z1 = mul2c(add2(tmp12, tmp13), AAN_A1);
+    const f2 z1 = MULZ(add2(tmp12, tmp13), AAN_A1);
     o[2] = add2(tmp13, z1);
     o[6] = sub2(tmp13, z1);
 
     const f2 u10 = add2(tmp4, tmp5), u11 = add2(tmp5, tmp6), u12 = add2(tmp6, tmp7);
-    const f2 z5 = mul2c(sub2(u10, u12), AAN_A5);
-    const f2 z2 = add2(mul2c(u10, AAN_A2), z5);
-    const f2 z4 = add2(mul2c(u12, AAN_A4), z5);
-    const f2 z3 = mul2c(u11, AAN_A3);
+    const f2 z5 = MULZ(sub2(u10, u12), AAN_A5);
+    const f2 z2 = add2(MULZ(u10, AAN_A2), z5);
+    const f2 z4 = add2(MULZ(u12, AAN_A4), z5);
+    const f2 z3 = MULZ(u11, AAN_A3);
     const f2 z11 = add2(tmp7, z3), z13 = sub2(tmp7, z3);
 
     o[5] = add2(z13, z2);
     o[3] = sub2(z13, z2);
     o[1] = add2(z11, z4);
     o[7] = sub2(z11, z4);
+#undef MULZ
 }
 
 // One table entry per output word (two adjacent natural-order coefficients):
@@ -373,7 +386,7 @@ struct __align__(16) QPair {
 //                bit-for-bit against the oracle; derivation in DESIGN.md)
 template <bool ZIGZAG>
 __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *__restrict__ tab,
-                                                   int16_t *__restrict__ out)
+                                                   int16_t *__restrict__ out, const f2 zero2)
 {
     constexpr float SK[8] = {AAN_S0, AAN_S1, AAN_S2, AAN_S3, AAN_S4, AAN_S5, AAN_S6, AAN_S7};
     // row pass on row pairs; the post-scale is done lane by lane so the results land in the
@@ -382,7 +395,7 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *_
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         f2 o[8];
-        aan_1d_x2_core(R[i], o);
+        aan_1d_x2_core(R[i], o, zero2);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float a0, a1, b0, b1;
@@ -397,13 +410,16 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *_
     for (int j = 0; j < 4; ++j) {
         const f2 in[8] = {C[0][j], C[1][j], C[2][j], C[3][j], C[4][j], C[5][j], C[6][j], C[7][j]};
         f2 o[8];
-        aan_1d_x2_core(in, o);
+        aan_1d_x2_core(in, o, zero2);
 #pragma unroll
         for (int r = 0; r < 8; ++r) C[r][j] = mul2(o[r], K2(SK[r]));
     }
 
     uint32_t W[32];
     const f2 half2 = K2(0.5f), magic2 = K2(12582912.0f);  // 1.5 * 2^23
+    uint32_t kSign, kOne;  // held in registers so copysign(1.0, q) is ONE lop3: (q & sign) | one
+    asm volatile("mov.b32 %0, 0x80000000;" : "=r"(kSign));
+    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(kOne));
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -416,8 +432,18 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *_
             const f2 q = fma2(e, rc, q0);
             uint32_t ql, qh;
             upk_u(q, ql, qh);
+#ifndef OPT_LOP1
+#define OPT_LOP1 0
+#endif
+#if OPT_LOP1
+            uint32_t sl, sh;
+            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(sl) : "r"(ql), "r"(kSign), "r"(kOne));
+            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(sh) : "r"(qh), "r"(kSign), "r"(kOne));
+            const f2 s = pk(__uint_as_float(sl), __uint_as_float(sh));
+#else
             const f2 s = pk(__uint_as_float((ql & 0x80000000u) | 0x3F800000u),
                             __uint_as_float((qh & 0x80000000u) | 0x3F800000u));
+#endif
             const f2 w = add2_rz(q, half2);
             const f2 tt = fma2_rm(w, s, magic2);
             uint32_t tl, th, neg;
@@ -507,34 +533,44 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const void *tmap, int x, 
 }
 
 // =========================================================================================
-// K1: RGB, 4:2:0.  Persistent CTAs of 128 threads; a tile is 32 MCUs (512 x 16 px, 24 KB) of
-// one MCU row.  Interior tiles of 16-byte-pitched images arrive by TMA (one 3-D
-// cp.async.bulk.tensor per tile, issued as soon as the previous tile's pixels have been
-// consumed, so the load of tile k+1 overlaps the chroma pass and the stores of tile k);
-// edge tiles (bottom replication) and unaligned images use the cooperative clamped loader.
+// K1: RGB, 4:2:0.  Persistent, warp-autonomous: every warp is an independent worker that owns
+// a private 12 KB pixel buffer, a 4 KB chroma exchange buffer and an mbarrier, and loops over
+// "units" of 16 MCUs (256 x 16 px) of one MCU row:
+//     wait for the unit's pixels (TMA)           -> 2 x (32 Y blocks: colour + DCT + quant)
+//     issue the TMA load of the warp's next unit -> 32 chroma blocks (16 Cb + 16 Cr)
+// so each lane runs exactly three block pipelines per unit, no CTA-wide barrier exists, and
+// the next unit's pixels stream in underneath the chroma pass.  Interior units of
+// 16-byte-pitched images arrive by one 3-D cp.async.bulk.tensor (TMA); bottom-edge units
+// (row replication) and unaligned images use the warp-cooperative clamped loader.
 // =========================================================================================
-constexpr int K1_THREADS = 128;
+constexpr int K1_WARPS = 4;
+constexpr int K1_THREADS = K1_WARPS * 32;
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS 3
 #endif
-constexpr int K1_MCUS = 32;
-constexpr int K1_TB = K1_MCUS * 16 * 3;  // 1536 bytes per tile row
+constexpr int K1_MCUS = 16;
+constexpr int K1_TB = K1_MCUS * 16 * 3;  // 768 bytes per tile row
 constexpr int K1_TILE_BYTES = 16 * K1_TB;
 
 struct K1Params {
     const uint8_t *pixels;
     size_t pixel_stride;
-    uint32_t w, h, mcus_x, mcus_y, tiles_x, n_images;
+    uint32_t w, h, mcus_x, mcus_y, units_x, n_images;
     int16_t *y, *cb, *cr;
     size_t y_stride, c_stride;
     uint32_t use_tma;
+    float zero[2];  // +0.0, +0.0: opaque to the compiler (see aan_1d_x2_core)
+};
+
+struct __align__(128) K1WarpSmem {
+    uint8_t tile[K1_TILE_BYTES];
+    uint32_t csum[K1_MCUS * 64];
+    uint64_t bar;
 };
 
 struct __align__(128) K1Smem {
-    uint8_t tile[K1_TILE_BYTES];
-    uint32_t csum[2][K1_MCUS * 64];
+    K1WarpSmem w[K1_WARPS];
     QuantSmem q;
-    uint64_t bar;
 };
 
 // One RGB row of a Y block (8 px in six words): Y - 128 as float for each pixel and the packed
@@ -560,11 +596,27 @@ __device__ __forceinline__ void ycc_row8(const uint32_t (&w)[6], float (&yv)[8],
         const uint32_t ys = __dp4a(win[x], 0x001D964Du, 128u);
         const int ucb = dp4a_us(win[x], 0x0080552Bu, -32641);
         const int ucr = dp4a_us(win[x], 0x00156B80u, -32641);
+#ifndef OPT_PKSHIFT
+#define OPT_PKSHIFT 1
+#endif
+#if OPT_PKSHIFT
+        yv[x] = __uint_as_float(__byte_perm(ys, 0x4B000000u, 0x7651));  // 2^23 + y
+#else
         yv[x] = byte1_to_float_minus(ys, 8388736.0f);
+#endif
         pp[x] = __vmaxu2(__byte_perm((uint32_t)ucb, (uint32_t)ucr, 0x7531), 0xFF01FF01u);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) hs[k] = pp[2 * k] + pp[2 * k + 1];
+}
+
+// Warp-cooperative version of load_tile: ROWS x (TILE_PX*3) bytes with edge replication.
+template <int ROWS, int TILE_PX>
+__device__ __forceinline__ void warp_load_tile_rgb(uint8_t *__restrict__ smem,
+                                                   const uint8_t *__restrict__ img, uint32_t w,
+                                                   uint32_t h, uint32_t x0, uint32_t y0, int lane)
+{
+    load_tile<3, ROWS, TILE_PX, 32>(smem, img, w, h, x0, y0, lane);
 }
 
 template <bool ZIGZAG>
@@ -576,68 +628,71 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
     K1Smem &S = *reinterpret_cast<K1Smem *>(smem_raw);
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    K1WarpSmem &WS = S.w[warp];
 
     fill_quant_smem(&S.q, qt, 4.0f, tid, K1_THREADS);
-    if (tid == 0) {
-        mbar_init(&S.bar, 1);
+    if (lane == 0) {
+        mbar_init(&WS.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    const uint64_t tiles_per_img = (uint64_t)P.mcus_y * P.tiles_x;
-    const uint64_t ntiles = tiles_per_img * P.n_images;
+    const f2 zero2 = pk(P.zero[0], P.zero[1]);
+    const uint64_t units_per_img = (uint64_t)P.mcus_y * P.units_x;
+    const uint64_t nunits = units_per_img * P.n_images;
+    const uint64_t stride = (uint64_t)gridDim.x * K1_WARPS;
     uint32_t phase = 0;
 
-    auto decode = [&](uint64_t t, uint32_t &img, uint32_t &my, uint32_t &tx) {
-        img = (uint32_t)(t / tiles_per_img);
-        const uint32_t rem = (uint32_t)(t - (uint64_t)img * tiles_per_img);
-        my = rem / P.tiles_x;
-        tx = rem - my * P.tiles_x;
+    auto decode = [&](uint64_t u, uint32_t &img, uint32_t &my, uint32_t &ux) {
+        img = (uint32_t)(u / units_per_img);
+        const uint32_t rem = (uint32_t)(u - (uint64_t)img * units_per_img);
+        my = rem / P.units_x;
+        ux = rem - my * P.units_x;
     };
-    auto tile_by_tma = [&](uint32_t my) { return P.use_tma && (my * 16 + 16 <= P.h); };
-    auto issue_tma = [&](uint64_t t) {
-        uint32_t img, my, tx;
-        decode(t, img, my, tx);
-        if (tile_by_tma(my)) {
+    auto unit_by_tma = [&](uint32_t my) { return P.use_tma && (my * 16 + 16 <= P.h); };
+    auto issue_tma = [&](uint64_t u) {
+        uint32_t img, my, ux;
+        decode(u, img, my, ux);
+        if (unit_by_tma(my)) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&S.bar, K1_TILE_BYTES);
-            tma_load_3d(S.tile, &tmap, (int)(tx * (K1_TB / 8)), (int)(my * 16), (int)img, &S.bar);
+            mbar_expect_tx(&WS.bar, K1_TILE_BYTES);
+            tma_load_3d(WS.tile, &tmap, (int)(ux * (K1_TB / 8)), (int)(my * 16), (int)img, &WS.bar);
         }
     };
 
-    uint64_t t = blockIdx.x;
-    if (t < ntiles && tid == 0) issue_tma(t);
+    uint64_t u = (uint64_t)blockIdx.x * K1_WARPS + warp;
+    if (u < nunits && lane == 0) issue_tma(u);
 
-    for (uint32_t it = 0; t < ntiles; t += gridDim.x, ++it) {
-        uint32_t img, my, tx;
-        decode(t, img, my, tx);
-        if (tile_by_tma(my)) {
-            mbar_wait(&S.bar, phase);
+    for (; u < nunits; u += stride) {
+        uint32_t img, my, ux;
+        decode(u, img, my, ux);
+        if (unit_by_tma(my)) {
+            mbar_wait(&WS.bar, phase);
             phase ^= 1;
         } else {
-            load_tile<3, 16, K1_MCUS * 16, K1_THREADS>(S.tile, P.pixels + (size_t)img * P.pixel_stride,
-                                                        P.w, P.h, tx * (K1_MCUS * 16), my * 16, tid);
-            __syncthreads();
+            warp_load_tile_rgb<16, K1_MCUS * 16>(WS.tile, P.pixels + (size_t)img * P.pixel_stride, P.w,
+                                                 P.h, ux * (K1_MCUS * 16), my * 16, lane);
+            __syncwarp();
         }
-        const uint32_t mcu0 = tx * K1_MCUS;
+        const uint32_t mcu0 = ux * K1_MCUS;
         const uint32_t n_mcu = min((uint32_t)K1_MCUS, P.mcus_x - mcu0);
-        uint32_t *csum = S.csum[it & 1];
+        const size_t mcu_base = (size_t)my * P.mcus_x + mcu0;
 
 #pragma unroll 1
-        for (int job = 0; job < 2; ++job) {
+        for (int job = 0; job < 3; ++job) {
             f2 R[4][8];
             const QPair *tab;
             int16_t *dst;
             bool active;
-            if (job == 0) {
-                // ---- one Y block per thread + packed chroma quad sums ----
+            if (job < 2) {
+                // ---- 32 Y blocks (8 MCUs) + their packed chroma quad sums ----
                 const int by = lane >> 4, l16 = lane & 15;
                 const int par = l16 >> 3, k8 = l16 & 7;
-                const int mcu = warp * 8 + (k8 >> 1) * 2 + par;  // same-parity MCUs per quarter warp
+                const int mcu = job * 8 + (k8 >> 1) * 2 + par;  // same-parity MCUs per quarter warp
                 const int bx = k8 & 1;
                 active = (uint32_t)mcu < n_mcu;
-                const uint8_t *base = S.tile + (by * 8) * K1_TB + (mcu * 2 + bx) * 24;
-                uint4 *cdst = reinterpret_cast<uint4 *>(csum) + mcu * 16;
+                const uint8_t *base = WS.tile + (by * 8) * K1_TB + (mcu * 2 + bx) * 24;
+                uint4 *cdst = reinterpret_cast<uint4 *>(WS.csum) + mcu * 16;
                 if (active) {
 #pragma unroll
                     for (int rp = 0; rp < 4; ++rp) {
@@ -656,28 +711,32 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
                             ycc_row8(wds, y1, h1);
                         }
 #pragma unroll
-                        for (int x = 0; x < 8; ++x) R[rp][x] = pk(y0[x], y1[x]);
+                        for (int x = 0; x < 8; ++x)  // (2^23 + y) - (2^23 + 128) = y - 128, exact
+#if OPT_PKSHIFT
+                            R[rp][x] = sub2(pk(y0[x], y1[x]), K2(8388736.0f));
+#else
+                            R[rp][x] = pk(y0[x], y1[x]);
+#endif
                         const int logical = (by * 4 + rp) * 2 + bx;
                         cdst[logical ^ (mcu & 7)] =
                             make_uint4(h0[0] + h1[0], h0[1] + h1[1], h0[2] + h1[2], h0[3] + h1[3]);
                     }
                 }
-                const size_t blk = ((size_t)my * P.mcus_x + mcu0 + mcu) * 4 + by * 2 + bx;
+                const size_t blk = (mcu_base + mcu) * 4 + by * 2 + bx;
                 dst = P.y + (size_t)img * P.y_stride + blk * 64;
                 tab = S.q.lum;
             } else {
-                __syncthreads();  // csum complete; every thread is done with the pixel tile
-                const uint64_t tn = t + gridDim.x;
-                if (tid == 0 && tn < ntiles) issue_tma(tn);
-                if (warp >= 2) break;
-                // ---- warp 0 = Cb blocks, warp 1 = Cr blocks ----
-                const int mcu = lane;
+                __syncwarp();  // chroma sums complete; every lane is done with the pixel tile
+                const uint64_t un = u + stride;
+                if (lane == 0 && un < nunits) issue_tma(un);
+                // ---- lanes 0-15: Cb of MCU lane, lanes 16-31: Cr of MCU lane-16 ----
+                const int comp = lane >> 4, mcu = lane & 15;
                 active = (uint32_t)mcu < n_mcu;
-                const uint4 *csrc = reinterpret_cast<const uint4 *>(csum) + mcu * 16;
-                const uint32_t sel = warp == 0 ? 0x7610u : 0x7632u;
+                const uint4 *csrc = reinterpret_cast<const uint4 *>(WS.csum) + mcu * 16;
+                const uint32_t sel = comp == 0 ? 0x7610u : 0x7632u;
                 // low half = 65536 - sum(cb), high half = 65539 - sum(cr)  (see ycc_row8);
                 // block value = 4 * (sum * 0.25 - 128) = sum - 512  (src/jpeg/mod.rs:1642-1653)
-                const float bias = warp == 0 ? 8453632.0f : 8453635.0f;  // 2^23 + 65536(+3) - 512
+                const float bias = comp == 0 ? 8453632.0f : 8453635.0f;  // 2^23 + 65536(+3) - 512
                 if (active) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -691,20 +750,29 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
                             const uint32_t b[4] = {s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
+#if OPT_PKSHIFT
+                                v0[hh * 4 + k] = __uint_as_float(__byte_perm(a[k], 0x4B000000u, sel));
+                                v1[hh * 4 + k] = __uint_as_float(__byte_perm(b[k], 0x4B000000u, sel));
+#else
                                 v0[hh * 4 + k] = FSUB(bias, __uint_as_float(__byte_perm(a[k], 0x4B000000u, sel)));
                                 v1[hh * 4 + k] = FSUB(bias, __uint_as_float(__byte_perm(b[k], 0x4B000000u, sel)));
+#endif
                             }
                         }
 #pragma unroll
+#if OPT_PKSHIFT
+                        for (int x = 0; x < 8; ++x) R[i][x] = sub2(K2(bias), pk(v0[x], v1[x]));
+#else
                         for (int x = 0; x < 8; ++x) R[i][x] = pk(v0[x], v1[x]);
+#endif
                     }
                 }
-                const size_t blk = (size_t)my * P.mcus_x + mcu0 + mcu;
-                dst = (warp == 0 ? P.cb : P.cr) + (size_t)img * P.c_stride + blk * 64;
+                dst = (comp == 0 ? P.cb : P.cr) + (size_t)img * P.c_stride + (mcu_base + mcu) * 64;
                 tab = S.q.chr;
             }
-            if (active) dct_quant_store_x2<ZIGZAG>(R, tab, dst);
+            if (active) dct_quant_store_x2<ZIGZAG>(R, tab, dst, zero2);
         }
+        __syncwarp();  // all lanes have read the chroma sums before the next unit overwrites them
     }
 }
 
@@ -929,8 +997,9 @@ int launch_k1(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint32
     K1Params P;
     P.pixels = px; P.pixel_stride = pixel_stride; P.w = w; P.h = h;
     P.mcus_x = (w + 15) / 16; P.mcus_y = (h + 15) / 16;
-    P.tiles_x = (P.mcus_x + K1_MCUS - 1) / K1_MCUS;
+    P.units_x = (P.mcus_x + K1_MCUS - 1) / K1_MCUS;
     P.n_images = n; P.y = y; P.cb = cb; P.cr = cr; P.y_stride = y_stride; P.c_stride = c_stride;
+    P.zero[0] = 0.0f; P.zero[1] = 0.0f;
     alignas(64) CUtensorMap tm;
     memset(&tm, 0, sizeof tm);
     P.use_tma = make_rgb_tensor_map(&tm, px, pixel_stride, n, w, h) ? 1u : 0u;
@@ -943,9 +1012,9 @@ int launch_k1(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint32
         PIXO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K1_THREADS, smem));
         blocks_per_sm[zigzag] = nb > 0 ? nb : 1;
     }
-    const uint64_t ntiles = (uint64_t)P.mcus_y * P.tiles_x * n;
+    const uint64_t nunits = (uint64_t)P.mcus_y * P.units_x * n;
     uint64_t grid = (uint64_t)ctx->sm_count * blocks_per_sm[zigzag];
-    if (grid > ntiles) grid = ntiles;
+    if (grid > (nunits + K1_WARPS - 1) / K1_WARPS) grid = (nunits + K1_WARPS - 1) / K1_WARPS;
     kern<<<(unsigned)grid, K1_THREADS, smem, ctx->stream>>>(P, qt, tm);
     ctx->launches++;
     PIXO_CUDA(ctx, cudaGetLastError());

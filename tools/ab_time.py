@@ -1,0 +1,7 @@
+"""A/B timing of library variants: python tools/ab_time.py lib1.so lib2.so ... (dev aid)."""
+import os, subprocess, sys
+for so in sys.argv[1:]:
+    env = dict(os.environ, PIXO_B200_SO=os.path.abspath(so))
+    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "quick_time.py"), "short"],
+                         env=env, capture_output=True, text=True).stdout
+    print(os.path.basename(so), "|", " | ".join(l.split(":")[1].strip() for l in out.strip().splitlines()[:3]))

@@ -38,6 +38,9 @@ def run(w, h, n, ct=2, ss=1, reps=20):
     print(f"{w}x{h} x{n} ct={ct} ss={ss}: {ms*1e3:.1f} us/launch  {n*w*h/ms/1e3:.1f} Mpix/s  {byts/ms/1e6:.1f} GB/s")
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "short":
+    run(3840, 2160, 1); run(3840, 2160, 32, reps=30); run(3840, 2160, 32, reps=30)
+    sys.exit(0)
 run(3840, 2160, 1)
 run(3840, 2160, 16)
 run(3840, 2160, 32)
