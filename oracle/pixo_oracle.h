@@ -11,10 +11,11 @@
  *   gcc -O2 -ffp-contract=off -fno-fast-math -msse2 -mfpmath=sse
  * so every float op is one rounded IEEE-754 binary32 operation, as in the Rust reference.
  *
- * Parity pinning: see oracle/README.md — the restatement is checked against (a) every
- * known-answer test the reference holds for this path (tests/test_oracle_kat.py) and
- * (b) byte streams produced by the reference's own compiled artefact (pixo_bg.wasm) executed
- * in the build container by oracle/wasm_ref (fixtures under tests/golden).
+ * Parity: PINNED (oracle/README.md).  The restatement is checked against (a) every known-answer
+ * test the reference holds for this path (tests/test_oracle_kat.py) and (b) complete JPEG / PNG
+ * files produced by the reference's own compiled artefact (pixo_bg.wasm) executed in the build
+ * container by oracle/wasm_ref: 71 JPEG + 63 PNG fixtures under tests/golden, reproduced byte
+ * for byte (tests/test_golden_reference.py).
  */
 #ifndef PIXO_ORACLE_H
 #define PIXO_ORACLE_H
