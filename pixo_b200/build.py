@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libpixo_b200.so")
-SOURCES = ["api.cu", "jpeg_transform.cu", "png_filter.cu", "jpeg_host.cpp"]
+SOURCES = ["api.cu", "jpeg_transform.cu", "jpeg_entropy.cu", "png_filter.cu", "jpeg_host.cpp"]
 HEADERS = ["common.cuh", "jpeg_host.hpp", os.path.join("..", "..", "include", "pixo_b200.h")]
 
 NVCC_FLAGS = [

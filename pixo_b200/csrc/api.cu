@@ -2,7 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
 #include <thread>
+#include <vector>
 
 #include "common.cuh"
 #include "jpeg_host.hpp"
@@ -137,7 +139,7 @@ void pixo_b200_ctx_destroy(pixo_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    Scratch *dev[] = {&ctx->d_in, &ctx->d_y, &ctx->d_cb, &ctx->d_cr, &ctx->d_misc, &ctx->d_out};
+    Scratch *dev[] = {&ctx->d_in, &ctx->d_y, &ctx->d_cb, &ctx->d_cr, &ctx->d_misc, &ctx->d_out, &ctx->d_ent, &ctx->d_coef};
     for (Scratch *s : dev) if (s->ptr) cudaFree(s->ptr);
     Scratch *host[] = {&ctx->h_in, &ctx->h_out, &ctx->h_misc};
     for (Scratch *s : host) if (s->ptr) cudaFreeHost(s->ptr);
@@ -368,6 +370,179 @@ static int validate_encode(pixo_b200_ctx *ctx, size_t pixels_len, uint32_t width
     return 0;
 }
 
+// Encode n frames of identical geometry and options.  GPU: colour/DCT/quantise (K1/K2), symbol
+// statistics when optimize_huffman (K3), Huffman bit packing + 0xFF stuffing (jpeg_entropy.cu);
+// host: headers, optimised-table construction, EOI.  Frames are processed in groups; the H2D
+// copy of group g+1 runs on the copy stream under the kernels of group g, and only finished
+// scan bytes come back over PCIe.  restart_interval != 0 (per-interval padding) and capacity
+// overflows (pathological inputs whose JPEG exceeds half the raw size) take the host entropy
+// coder instead, which consumes the same GPU coefficient arrays.
+static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_each, uint32_t n_images,
+                         const FrameGeometry &g, uint32_t quality, uint32_t restart_interval,
+                         bool optimize, uint8_t *out, size_t out_cap_each, size_t *out_lens)
+{
+    float lum[64], chr[64];
+    uint8_t lum_zz[64], chr_zz[64];
+    quant_tables((int)quality, lum_zz, chr_zz, lum, chr);
+    const size_t yb = align_up(g.ny * 64 * sizeof(int16_t), 256);
+    const size_t cbb = align_up(g.nc * 64 * sizeof(int16_t), 256);
+    const size_t coef_each = yb + 2 * cbb;
+    const size_t in_stride = align_up(len_each, 256);
+    const uint64_t raw_cap = align_up(len_each / 2 + 65536, 4096);
+    const uint64_t scan_cap = align_up(raw_cap + raw_cap / 8, 256);
+    const bool gpu_entropy = restart_interval == 0;
+
+    uint32_t G = n_images < 16 ? n_images : 16;
+    const size_t budget = (size_t)3 << 30;
+    auto group_bytes = [&](uint32_t k) {
+        return 2 * (size_t)k * in_stride + (size_t)k * coef_each + entropy_scratch_bytes(k, g, raw_cap) +
+               2 * (size_t)k * scan_cap;
+    };
+    while (G > 1 && group_bytes(G) > budget) --G;
+    const uint32_t ngroups = (n_images + G - 1) / G;
+
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_in, 2 * (size_t)G * in_stride));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_coef, (size_t)G * coef_each));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(G, g, raw_cap)));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_out, 2 * (size_t)G * scan_cap));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_misc, (size_t)G * kHistWords * sizeof(uint64_t) + 256));
+    PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, (size_t)G * (kHistWords * sizeof(uint64_t) + 32) + 256));
+    while (ctx->events.size() < 6) {
+        cudaEvent_t ev;
+        PIXO_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->events.push_back(ev);
+    }
+    cudaEvent_t *ev_in = &ctx->events[0];    // [2] input slot filled
+    cudaEvent_t *ev_used = &ctx->events[2];  // [2] input slot consumed by the transform kernel
+    cudaEvent_t *ev_out = &ctx->events[4];   // [2] scan bytes of the slot copied back
+    auto *d_in = reinterpret_cast<uint8_t *>(ctx->d_in.ptr);
+    auto *d_coef = reinterpret_cast<uint8_t *>(ctx->d_coef.ptr);
+    auto *d_scan = reinterpret_cast<uint8_t *>(ctx->d_out.ptr);
+    auto *h_meta = reinterpret_cast<uint8_t *>(ctx->h_misc.ptr);
+    auto *h_len = reinterpret_cast<uint64_t *>(h_meta);
+    auto *h_ovf = reinterpret_cast<uint32_t *>(h_meta + (size_t)G * 8);
+    auto *h_hist = reinterpret_cast<uint64_t *>(h_meta + align_up((size_t)G * 12, 256));
+
+    auto upload = [&](uint32_t gi) -> int {
+        const uint32_t first = gi * G, cnt = std::min(G, n_images - first);
+        const int slot = (int)(gi & 1);
+        if (gi >= 2) PIXO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev_used[slot], 0));
+        for (uint32_t k = 0; k < cnt; ++k)
+            PIXO_CUDA(ctx, cudaMemcpyAsync(d_in + ((size_t)slot * G + k) * in_stride,
+                                           pixels + (size_t)(first + k) * len_each, len_each,
+                                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        PIXO_CUDA(ctx, cudaEventRecord(ev_in[slot], ctx->copy_stream));
+        return 0;
+    };
+
+    // make the copy stream start after whatever the caller already queued on the main stream
+    PIXO_CUDA(ctx, cudaEventRecord(ev_out[0], ctx->stream));
+    PIXO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev_out[0], 0));
+    PIXO_TRY(upload(0));
+    for (uint32_t gi = 0; gi < ngroups; ++gi) {
+        const uint32_t first = gi * G, cnt = std::min(G, n_images - first);
+        const int slot = (int)(gi & 1);
+        if (gi + 1 < ngroups) PIXO_TRY(upload(gi + 1));
+        PIXO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_in[slot], 0));
+        auto *dy = reinterpret_cast<int16_t *>(d_coef);
+        auto *dcb = reinterpret_cast<int16_t *>(d_coef + yb);
+        auto *dcr = reinterpret_cast<int16_t *>(d_coef + yb + cbb);
+        const size_t cstride = coef_each / 2;
+        PIXO_TRY(launch_jpeg_transform(ctx, d_in + (size_t)slot * G * in_stride, in_stride, cnt, g.width,
+                                       g.height, g.color_type, g.subsampling, lum, chr, dy, cstride,
+                                       g.has_chroma ? dcb : nullptr, g.has_chroma ? dcr : nullptr, cstride, 0));
+        PIXO_CUDA(ctx, cudaEventRecord(ev_used[slot], ctx->stream));
+        std::vector<HuffTables> tables(optimize ? cnt : 1);
+        if (optimize) {
+            auto *d_hist = reinterpret_cast<uint64_t *>(ctx->d_misc.ptr);
+            PIXO_TRY(launch_jpeg_histogram(ctx, dy, cstride, dcb, dcr, cstride, cnt, g.ny, g.nc, g.y_per_mcu,
+                                           restart_interval, false, d_hist));
+            PIXO_CUDA(ctx, cudaMemcpyAsync(h_hist, d_hist, (size_t)cnt * kHistWords * sizeof(uint64_t),
+                                           cudaMemcpyDeviceToHost, ctx->stream));
+            PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (uint32_t k = 0; k < cnt; ++k)  // unwrap_or_default, src/jpeg/mod.rs:379-392
+                if (!huff_from_histogram(h_hist + (size_t)k * kHistWords, g.has_chroma, tables[k])) huff_standard(tables[k]);
+        } else {
+            huff_standard(tables[0]);
+        }
+        uint8_t *scan = d_scan + (size_t)slot * G * scan_cap;
+        bool fallback_all = !gpu_entropy;
+        if (gpu_entropy) {
+            if (gi >= 2) PIXO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_out[slot], 0));
+            uint64_t *d_len = nullptr;
+            uint32_t *d_ovf = nullptr;
+            auto *ent = reinterpret_cast<uint8_t *>(ctx->d_ent.ptr);
+            if (!optimize) {
+                PIXO_TRY(launch_jpeg_entropy(ctx, dy, cstride, dcb, dcr, cstride, cnt, g, tables[0], ent, raw_cap,
+                                             scan, scan_cap, &d_len, &d_ovf));
+                PIXO_CUDA(ctx, cudaMemcpyAsync(h_len, d_len, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+                PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf, d_ovf, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            } else {
+                const size_t per = entropy_scratch_bytes(1, g, raw_cap);
+                for (uint32_t k = 0; k < cnt; ++k) {  // per-image tables: one pass per image
+                    PIXO_TRY(launch_jpeg_entropy(ctx, dy + (size_t)k * cstride, cstride, dcb + (size_t)k * cstride,
+                                                 dcr + (size_t)k * cstride, cstride, 1, g, tables[k],
+                                                 ent + (size_t)k * per, raw_cap, scan + (size_t)k * scan_cap,
+                                                 scan_cap, &d_len, &d_ovf));
+                    PIXO_CUDA(ctx, cudaMemcpyAsync(h_len + k, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                    PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf + k, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                }
+            }
+            PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        // assemble: headers on the host, scan bytes straight from the device, EOI
+        std::vector<size_t> hdr(cnt);
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const uint32_t img = first + k;
+            uint8_t *o = out + (size_t)img * out_cap_each;
+            const HuffTables &t = tables[optimize ? k : 0];
+            if (out_cap_each < 1024 + 2)
+                return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small", out_cap_each);
+            hdr[k] = write_headers(o, g, lum_zz, chr_zz, t, restart_interval);
+            if (!fallback_all && !h_ovf[k]) {
+                const size_t body = (size_t)h_len[k];
+                if (hdr[k] + body + 2 > out_cap_each)
+                    return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small (need %zu)",
+                                     out_cap_each, hdr[k] + body + 2);
+                PIXO_CUDA(ctx, cudaMemcpyAsync(o + hdr[k], scan + (size_t)k * scan_cap, body,
+                                               cudaMemcpyDeviceToHost, ctx->stream));
+                o[hdr[k] + body] = 0xFF;
+                o[hdr[k] + body + 1] = 0xD9;
+                out_lens[img] = hdr[k] + body + 2;
+            }
+        }
+        PIXO_CUDA(ctx, cudaEventRecord(ev_out[slot], ctx->stream));
+        // host entropy coder for the frames the GPU stage did not finish
+        bool any_host = fallback_all;
+        for (uint32_t k = 0; k < cnt && !any_host; ++k) any_host = h_ovf[k] != 0;
+        if (any_host) {
+            PIXO_TRY(ensure_pinned(ctx, ctx->h_out, coef_each));
+            auto *hc = reinterpret_cast<uint8_t *>(ctx->h_out.ptr);
+            for (uint32_t k = 0; k < cnt; ++k) {
+                if (!fallback_all && !h_ovf[k]) continue;
+                const uint32_t img = first + k;
+                uint8_t *o = out + (size_t)img * out_cap_each;
+                PIXO_CUDA(ctx, cudaMemcpyAsync(hc, d_coef + (size_t)k * coef_each, coef_each,
+                                               cudaMemcpyDeviceToHost, ctx->stream));
+                PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                const size_t body = entropy_encode_scan(reinterpret_cast<int16_t *>(hc),
+                                                        reinterpret_cast<int16_t *>(hc + yb),
+                                                        reinterpret_cast<int16_t *>(hc + yb + cbb), g,
+                                                        tables[optimize ? k : 0], restart_interval, false,
+                                                        o + hdr[k], out_cap_each - hdr[k] - 2, ctx->host_threads);
+                if (body == (size_t)-1)
+                    return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small", out_cap_each);
+                o[hdr[k] + body] = 0xFF;
+                o[hdr[k] + body + 1] = 0xD9;
+                out_lens[img] = hdr[k] + body + 2;
+            }
+        }
+    }
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int pixo_b200_jpeg_encode(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t pixels_len,
                           uint32_t width, uint32_t height, uint32_t color_type, uint32_t quality,
                           uint32_t subsampling, uint32_t restart_interval,
@@ -383,20 +558,8 @@ int pixo_b200_jpeg_encode(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t pixe
                          "progressive scans are outside the accelerated path (sequential entropy stage)");
     (void)trellis_quant;  // baseline encode_scan ignores use_trellis (src/jpeg/mod.rs:1408-1563)
     const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
-    float lum[64], chr[64];
-    quant_tables((int)quality, nullptr, nullptr, lum, chr);
-    const size_t yb = g.ny * 64 * sizeof(int16_t), cbb = g.nc * 64 * sizeof(int16_t);
-    PIXO_TRY(ensure_pinned(ctx, ctx->h_out, align_up(yb, 256) + 2 * align_up(cbb, 256) + 8192));
-    auto *base = reinterpret_cast<uint8_t *>(ctx->h_out.ptr);
-    auto *hy = reinterpret_cast<int16_t *>(base);
-    auto *hcb = reinterpret_cast<int16_t *>(base + align_up(yb, 256));
-    auto *hcr = reinterpret_cast<int16_t *>(base + align_up(yb, 256) + align_up(cbb, 256));
-    auto *hhist = reinterpret_cast<uint64_t *>(base + align_up(yb, 256) + 2 * align_up(cbb, 256));
-    PIXO_TRY(transform_host(ctx, pixels, g, lum, chr, 0, restart_interval, optimize_huffman != 0,
-                            hy, hcb, hcr, hhist));
-    return entropy_from_host_arrays(ctx, hy, hcb, hcr, g, quality, restart_interval,
-                                    optimize_huffman ? hhist : nullptr, out, out_cap, out_len,
-                                    ctx->host_threads);
+    return encode_frames(ctx, pixels, pixels_len, 1, g, quality, restart_interval, optimize_huffman != 0, out,
+                         out_cap, out_len);
 }
 
 int pixo_b200_jpeg_encode_batch(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t pixels_len_each,
@@ -411,95 +574,8 @@ int pixo_b200_jpeg_encode_batch(pixo_b200_ctx *ctx, const uint8_t *pixels, size_
     if (!pixels || !out || !out_lens) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
     if (n_images == 0) return 0;
     const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
-    float lum[64], chr[64];
-    quant_tables((int)quality, nullptr, nullptr, lum, chr);
-    const size_t yb = align_up(g.ny * 64 * sizeof(int16_t), 256);
-    const size_t cbb = align_up(g.nc * 64 * sizeof(int16_t), 256);
-    const size_t hb = align_up(kHistWords * sizeof(uint64_t), 256);
-    const size_t per_img = yb + 2 * cbb + hb;
-    // groups of G frames: one transform launch + one coefficient download per group, while the
-    // host entropy-codes the previous group (one thread per frame).
-    uint32_t G = (uint32_t)ctx->host_threads;
-    if (G > n_images) G = n_images;
-    if (G < 1) G = 1;
-    const size_t max_group_bytes = (size_t)1 << 30;
-    while (G > 1 && (size_t)G * (per_img + pixels_len_each) > max_group_bytes) --G;
-    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
-    PIXO_TRY(ensure_dev(ctx, ctx->d_in, 2 * (size_t)G * align_up(pixels_len_each, 256)));
-    PIXO_TRY(ensure_dev(ctx, ctx->d_out, 2 * (size_t)G * per_img));
-    PIXO_TRY(ensure_pinned(ctx, ctx->h_out, 2 * (size_t)G * per_img));
-    while (ctx->events.size() < 2) {
-        cudaEvent_t ev;
-        PIXO_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        ctx->events.push_back(ev);
-    }
-    const size_t in_stride = align_up(pixels_len_each, 256);
-    struct GroupCtx {
-        pixo_b200_ctx *ctx; const FrameGeometry *g; uint32_t quality, restart; bool opt;
-        const uint8_t *hbase; size_t per_img, yb, cbb; uint8_t *out; size_t out_cap; size_t *lens;
-        uint32_t first; int rc;
-    };
-    auto encode_one = [](int i, void *arg) {
-        GroupCtx &c = *reinterpret_cast<GroupCtx *>(arg);
-        const uint8_t *b = c.hbase + (size_t)i * c.per_img;
-        const int16_t *y = reinterpret_cast<const int16_t *>(b);
-        const int16_t *cb = reinterpret_cast<const int16_t *>(b + c.yb);
-        const int16_t *cr = reinterpret_cast<const int16_t *>(b + c.yb + c.cbb);
-        const uint64_t *hist = reinterpret_cast<const uint64_t *>(b + c.yb + 2 * c.cbb);
-        const uint32_t img = c.first + (uint32_t)i;
-        const int rc = entropy_from_host_arrays(nullptr, y, cb, cr, *c.g, c.quality, c.restart,
-                                                c.opt ? hist : nullptr, c.out + (size_t)img * c.out_cap,
-                                                c.out_cap, &c.lens[img], 1);
-        if (rc) c.rc = rc;
-    };
-    const uint32_t ngroups = (n_images + G - 1) / G;
-    int final_rc = 0;
-    for (uint32_t gi = 0; gi <= ngroups; ++gi) {
-        if (gi < ngroups) {
-            const uint32_t first = gi * G, cnt = std::min(G, n_images - first);
-            const int slot = (int)(gi & 1);
-            uint8_t *din = reinterpret_cast<uint8_t *>(ctx->d_in.ptr) + (size_t)slot * G * in_stride;
-            uint8_t *dout = reinterpret_cast<uint8_t *>(ctx->d_out.ptr) + (size_t)slot * G * per_img;
-            uint8_t *hout = reinterpret_cast<uint8_t *>(ctx->h_out.ptr) + (size_t)slot * G * per_img;
-            for (uint32_t k = 0; k < cnt; ++k)
-                PIXO_CUDA(ctx, cudaMemcpyAsync(din + (size_t)k * in_stride,
-                                               pixels + (size_t)(first + k) * pixels_len_each,
-                                               pixels_len_each, cudaMemcpyHostToDevice, ctx->stream));
-            auto *dy = reinterpret_cast<int16_t *>(dout);
-            auto *dcb = reinterpret_cast<int16_t *>(dout + yb);
-            auto *dcr = reinterpret_cast<int16_t *>(dout + yb + cbb);
-            PIXO_TRY(launch_jpeg_transform(ctx, din, in_stride, cnt, width, height, color_type,
-                                           subsampling, lum, chr, dy, per_img / 2, dcb, dcr,
-                                           per_img / 2, 0));
-            if (optimize_huffman) {
-                // histograms live at the tail of each frame's slot: stride per_img bytes
-                for (uint32_t k = 0; k < cnt; ++k) {
-                    uint8_t *fb = dout + (size_t)k * per_img;
-                    PIXO_TRY(launch_jpeg_histogram(ctx, reinterpret_cast<int16_t *>(fb), 0,
-                                                   reinterpret_cast<int16_t *>(fb + yb),
-                                                   reinterpret_cast<int16_t *>(fb + yb + cbb), 0, 1,
-                                                   g.ny, g.nc, g.y_per_mcu, restart_interval, false,
-                                                   reinterpret_cast<uint64_t *>(fb + yb + 2 * cbb)));
-                }
-            }
-            PIXO_CUDA(ctx, cudaMemcpyAsync(hout, dout, (size_t)cnt * per_img, cudaMemcpyDeviceToHost, ctx->stream));
-            PIXO_CUDA(ctx, cudaEventRecord(ctx->events[slot], ctx->stream));
-        }
-        if (gi > 0) {
-            const uint32_t pg = gi - 1;
-            const uint32_t first = pg * G, cnt = std::min(G, n_images - first);
-            const int slot = (int)(pg & 1);
-            PIXO_CUDA(ctx, cudaEventSynchronize(ctx->events[slot]));
-            GroupCtx c{ctx, &g, quality, restart_interval, optimize_huffman != 0,
-                       reinterpret_cast<uint8_t *>(ctx->h_out.ptr) + (size_t)slot * G * per_img,
-                       per_img, yb, cbb, out, out_cap_each, out_lens, first, 0};
-            parallel_jobs((int)cnt, ctx->host_threads, encode_one, &c);
-            if (c.rc && !final_rc) final_rc = c.rc;
-        }
-    }
-    if (final_rc)
-        return set_error(ctx, final_rc, "batch entropy stage failed (output capacity %zu per image?)", out_cap_each);
-    return 0;
+    return encode_frames(ctx, pixels, pixels_len_each, n_images, g, quality, restart_interval,
+                         optimize_huffman != 0, out, out_cap_each, out_lens);
 }
 
 int pixo_b200_jpeg_entropy_encode(pixo_b200_ctx *ctx, const int16_t *y, const int16_t *cb,

@@ -40,7 +40,7 @@ struct pixo_b200_ctx {
     uint64_t launches = 0;
     std::string err;
     // reusable scratch (device + pinned host)
-    pixo::Scratch d_in, d_y, d_cb, d_cr, d_misc, d_out;
+    pixo::Scratch d_in, d_y, d_cb, d_cr, d_misc, d_out, d_ent, d_coef;
     pixo::Scratch h_in, h_out, h_misc;
     std::vector<cudaEvent_t> events;
 };
@@ -79,5 +79,13 @@ int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_strid
                       uint32_t bpp, uint32_t strategy, uint8_t *d_out, size_t out_stride,
                       uint32_t *d_adler);
 int launch_adler32(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t len, uint32_t *d_out);
+
+struct FrameGeometry;
+struct HuffTables;
+size_t entropy_scratch_bytes(uint32_t n, const FrameGeometry &g, uint64_t raw_cap);
+int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride, const int16_t *d_cb,
+                        const int16_t *d_cr, size_t c_stride, uint32_t n, const FrameGeometry &g,
+                        const HuffTables &t, uint8_t *d_scratch, uint64_t raw_cap, uint8_t *d_out,
+                        uint64_t out_cap, uint64_t **d_out_len, uint32_t **d_overflow);
 
 }  // namespace pixo
