@@ -5,8 +5,9 @@
 A "step" is one pass of the hot path over one batch of FRAMES distinct synthetic 4K frames
 (a ring larger than the 126 MB L2, so no step finds its input or output resident).
 
- value     device-resident throughput of the fused colour->subsample->DCT->quantise kernel
-           (inputs already in HBM, coefficient arrays left in HBM), whole job, Mpix/s.
+ value     device-resident throughput of the whole hot path: pixo_b200_jpeg_encode_dev =
+           fused colour->subsample->DCT->quantise kernel + Huffman length/scan/emit/stuffing
+           kernels, RGB frames already in HBM -> entropy-coded scan bytes left in HBM; Mpix/s.
  e2e       the same metric through the reference-facing C ABI call with HOST buffers:
            pixo_b200_jpeg_encode_batch(pinned RGB frames) -> finished JPEG byte streams in host
            memory; H2D of the pixels, transform + Huffman/stuffing kernels, D2H of the scan bytes
@@ -205,6 +206,17 @@ def run_ours(args):
     _, _, lq, cq = jpeg.quant_tables(QUALITY)
     lqp, cqp = lq.ctypes.data_as(_lib.f32p), cq.ctypes.data_as(_lib.f32p)
 
+    scan_cap = IN_BYTES // 2 + 65536 + 8192
+    scan_cap -= scan_cap % 256
+    d_scan = torch.empty((F, scan_cap), dtype=torch.uint8, device=dev)
+    d_slen = torch.zeros(F, dtype=torch.int64, device=dev)
+    d_sovf = torch.zeros(F, dtype=torch.int32, device=dev)
+
+    def encode_step():
+        rc = lib.pixo_b200_jpeg_encode_dev(ctx.handle, d_px.data_ptr(), IN_BYTES, F, W, H, 2, QUALITY, 1,
+                                           d_scan.data_ptr(), scan_cap, d_slen.data_ptr(), d_sovf.data_ptr())
+        _lib.check(ctx.handle, rc)
+
     def kernel_step():
         rc = lib.pixo_b200_jpeg_coefficients_dev(ctx.handle, d_px.data_ptr(), IN_BYTES, F, W, H, 2, 1, lqp, cqp,
                                                  d_y.data_ptr(), ny * 64, d_cb.data_ptr(), d_cr.data_ptr(),
@@ -216,8 +228,27 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident kernel throughput (value + roofline) ----
+    # ---- device-resident whole path (value) ----
     for _ in range(max(args.warmup, 3)):
+        encode_step()
+    barrier()
+    assert int(d_sovf.sum()) == 0, "scan capacity overflow"
+    launches_enc0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        encode_step()
+    ev1.record(stream)
+    barrier()
+    enc_launches = ctx.launch_count - launches_enc0
+    tenc = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tenc, op=dist.ReduceOp.MAX)
+    enc_ms = float(tenc[0])
+
+    # ---- the dominant kernel alone (roofline) ----
+    for _ in range(3):
         kernel_step()
     barrier()
     sampler = ClockSampler(local_rank)
@@ -239,7 +270,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, per_launch_ms = float(t[0]), float(t[1])
-    value = world * F * args.steps * PIX / (total_ms * 1e-3) / 1e6
+    value = world * F * args.steps * PIX / (enc_ms * 1e-3) / 1e6
+    k1_value = world * F * args.steps * PIX / (total_ms * 1e-3) / 1e6
 
     # ---- end-to-end through the C ABI with host buffers ----
     e2e_frames = min(F, args.e2e_frames)
@@ -290,7 +322,7 @@ def run_ours(args):
                 traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "warmup": max(args.warmup, 3), "ms_per_step": enc_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C2: 3840x2160 RGB -> JPEG q=80 4:2:0; step = ring of {F} distinct frames per GPU "
                                    f"({F * IN_BYTES / 1e6:.0f} MB in + same out, larger than L2: no flush needed)",
@@ -300,12 +332,15 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_jpeg_420", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * F,
-                         "kernel_ms_per_launch": per_launch_ms},
+                         "kernel_ms_per_launch": per_launch_ms, "kernel_only_mpix_s": k1_value,
+                         "share_of_step": per_launch_ms / (enc_ms / args.steps),
+                         "note": "k_jpeg_420 timed alone (pixo_b200_jpeg_coefficients_dev) on the same ring; "
+                                 "the rest of a step is the Huffman length/scan/emit/stuffing kernels"},
             "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": e2e_frames * IN_BYTES,
                     "d2h_bytes_per_step": jpeg_bytes + e2e_frames * 12,
                     "frames_per_step": e2e_frames, "steps": e2e_steps, "jpeg_bytes_last_step": jpeg_bytes,
                     "api": "pixo_b200_jpeg_encode_batch (host RGB in pinned memory -> JPEG bytes on host)"},
-            "gpu_launches": int(kernel_launches + e2e_launches),
+            "gpu_launches": int(enc_launches + kernel_launches + e2e_launches),
             "clocks": clocks,
         }
         if cpu:

@@ -150,6 +150,18 @@ int pixo_b200_jpeg_encode_batch(pixo_b200_ctx *ctx, const uint8_t *pixels, size_
                                 uint32_t restart_interval, uint32_t optimize_huffman,
                                 uint8_t *out, size_t out_cap_each, size_t *out_lens);
 
+/* Device-resident variant of the whole hot path (asynchronous on the context's stream):
+ * frame i at d_pixels + i*pixel_stride -> entropy-coded scan bytes (what encode_scan appends
+ * between the SOS header and EOI, src/jpeg/mod.rs:1408-1563) at d_scan + i*scan_cap_each, byte
+ * count in d_scan_len[i]; d_overflow[i] != 0 when scan_cap_each (or the internal raw-bit
+ * capacity of half the frame size) was too small.  Baseline, standard Huffman tables, no
+ * restart interval.  Headers/EOI are the caller's (pixo_b200_jpeg_encode* add them). */
+int pixo_b200_jpeg_encode_dev(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pixel_stride,
+                              uint32_t n_images, uint32_t width, uint32_t height,
+                              uint32_t color_type, uint32_t quality, uint32_t subsampling,
+                              uint8_t *d_scan, size_t scan_cap_each, uint64_t *d_scan_len,
+                              uint32_t *d_overflow);
+
 /* Entropy-code caller-provided coefficient arrays (host) into a baseline JPEG: the host half of
  * pixo_b200_jpeg_encode on its own (src/jpeg/mod.rs:395-447,1408-1563 consuming arrays shaped
  * like compute_all_coefficients' result).  Host-only, no device needed. */

@@ -578,6 +578,53 @@ int pixo_b200_jpeg_encode_batch(pixo_b200_ctx *ctx, const uint8_t *pixels, size_
                          optimize_huffman != 0, out, out_cap_each, out_lens);
 }
 
+int pixo_b200_jpeg_encode_dev(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pixel_stride,
+                              uint32_t n_images, uint32_t width, uint32_t height,
+                              uint32_t color_type, uint32_t quality, uint32_t subsampling,
+                              uint8_t *d_scan, size_t scan_cap_each, uint64_t *d_scan_len,
+                              uint32_t *d_overflow)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    if (quality == 0 || quality > 100)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_QUALITY, "Invalid quality %u: must be 1-100", quality);
+    PIXO_TRY(validate_jpeg(ctx, width, height, color_type, subsampling));
+    if (!d_pixels || !d_scan || !d_scan_len || !d_overflow)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    if (n_images == 0) return 0;
+    if (n_images > 65535) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "at most 65535 frames per call");
+    if (scan_cap_each % 4 || (reinterpret_cast<uintptr_t>(d_scan) & 15))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "scan buffer must be 16-byte aligned, capacity multiple of 4");
+    const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
+    float lum[64], chr[64];
+    quant_tables((int)quality, nullptr, nullptr, lum, chr);
+    const size_t bpp = color_type == PIXO_B200_GRAY ? 1 : 3;
+    const size_t len_each = (size_t)width * height * bpp;
+    const size_t yb = align_up(g.ny * 64 * sizeof(int16_t), 256);
+    const size_t cbb = align_up(g.nc * 64 * sizeof(int16_t), 256);
+    const size_t coef_each = yb + 2 * cbb;
+    const uint64_t raw_cap = align_up(len_each / 2 + 65536, 4096);
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_coef, (size_t)n_images * coef_each));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(n_images, g, raw_cap)));
+    auto *d_coef = reinterpret_cast<uint8_t *>(ctx->d_coef.ptr);
+    auto *dy = reinterpret_cast<int16_t *>(d_coef);
+    auto *dcb = reinterpret_cast<int16_t *>(d_coef + yb);
+    auto *dcr = reinterpret_cast<int16_t *>(d_coef + yb + cbb);
+    PIXO_TRY(launch_jpeg_transform(ctx, d_pixels, pixel_stride, n_images, width, height, color_type, subsampling,
+                                   lum, chr, dy, coef_each / 2, g.has_chroma ? dcb : nullptr,
+                                   g.has_chroma ? dcr : nullptr, coef_each / 2, 0));
+    HuffTables t;
+    huff_standard(t);
+    uint64_t *len_src = nullptr;
+    uint32_t *ovf_src = nullptr;
+    PIXO_TRY(launch_jpeg_entropy(ctx, dy, coef_each / 2, dcb, dcr, coef_each / 2, n_images, g, t,
+                                 reinterpret_cast<uint8_t *>(ctx->d_ent.ptr), raw_cap, d_scan, scan_cap_each,
+                                 &len_src, &ovf_src));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(d_scan_len, len_src, (size_t)n_images * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(d_overflow, ovf_src, (size_t)n_images * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
 int pixo_b200_jpeg_entropy_encode(pixo_b200_ctx *ctx, const int16_t *y, const int16_t *cb,
                                   const int16_t *cr, uint32_t width, uint32_t height,
                                   uint32_t color_type, uint32_t quality, uint32_t subsampling,
