@@ -336,14 +336,7 @@ __device__ __forceinline__ f2 mul2c(f2 a, float c)
 // zero product is always +0 — which can only ever change the sign of a zero downstream.
 __device__ __forceinline__ void aan_1d_x2_core(const f2 (&d)[8], f2 (&o)[8], const f2 zero2)
 {
-#ifndef OPT_MULZ
-#define OPT_MULZ 1
-#endif
-#if OPT_MULZ
 #define MULZ(a, c) fma2((a), K2(c), zero2)
-#else
-#define MULZ(a, c) mul2c((a), (c))
-#endif
     const f2 tmp0 = add2(d[0], d[7]), tmp7 = sub2(d[0], d[7]);
     const f2 tmp1 = add2(d[1], d[6]), tmp6 = sub2(d[1], d[6]);
     const f2 tmp2 = add2(d[2], d[5]), tmp5 = sub2(d[2], d[5]);
@@ -384,9 +377,13 @@ struct __align__(16) QPair {
 //   round      : w = RZ(q + 0.5); m = floor(sign(q) * w) via fma.rm with 1.5*2^23;
 //                result = m for q >= 0, ~m for q < 0  == round-half-away(q)  (tests prove it
 //                bit-for-bit against the oracle; derivation in DESIGN.md)
+// `out` is the block's 128-byte slot in a warp-private shared-memory stage; its eight 16-byte
+// chunks are written at chunk index (k ^ swz) so that the lanes of a quarter warp hit distinct
+// banks (the caller then copies the stage out with fully coalesced 512-byte warp stores).
 template <bool ZIGZAG>
 __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *__restrict__ tab,
-                                                   int16_t *__restrict__ out, const f2 zero2)
+                                                   uint4 *__restrict__ out, const int swz,
+                                                   const f2 zero2)
 {
     constexpr float SK[8] = {AAN_S0, AAN_S1, AAN_S2, AAN_S3, AAN_S4, AAN_S5, AAN_S6, AAN_S7};
     // row pass on row pairs; the post-scale is done lane by lane so the results land in the
@@ -417,9 +414,11 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *_
 
     uint32_t W[32];
     const f2 half2 = K2(0.5f), magic2 = K2(12582912.0f);  // 1.5 * 2^23
-    uint32_t kSign, kOne;  // held in registers so copysign(1.0, q) is ONE lop3: (q & sign) | one
-    asm volatile("mov.b32 %0, 0x80000000;" : "=r"(kSign));
-    asm volatile("mov.b32 %0, 0x3F800000;" : "=r"(kOne));
+    uint32_t kSign, kOne, kHalf;  // in registers so copysign(c, q) is ONE lop3: (q & sign) | c
+    asm("mov.b32 %0, 0x80000000;" : "=r"(kSign));
+    asm("mov.b32 %0, 0x3F800000;" : "=r"(kOne));
+    asm("mov.b32 %0, 0x3F000000;" : "=r"(kHalf));
+    (void)kOne; (void)kHalf;
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -432,18 +431,10 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *_
             const f2 q = fma2(e, rc, q0);
             uint32_t ql, qh;
             upk_u(q, ql, qh);
-#ifndef OPT_LOP1
-#define OPT_LOP1 0
-#endif
-#if OPT_LOP1
             uint32_t sl, sh;
             asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(sl) : "r"(ql), "r"(kSign), "r"(kOne));
             asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(sh) : "r"(qh), "r"(kSign), "r"(kOne));
             const f2 s = pk(__uint_as_float(sl), __uint_as_float(sh));
-#else
-            const f2 s = pk(__uint_as_float((ql & 0x80000000u) | 0x3F800000u),
-                            __uint_as_float((qh & 0x80000000u) | 0x3F800000u));
-#endif
             const f2 w = add2_rz(q, half2);
             const f2 tt = fma2_rm(w, s, magic2);
             uint32_t tl, th, neg;
@@ -451,7 +442,6 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *_
             asm("prmt.b32 %0, %1, %2, %3;" : "=r"(neg) : "r"(ql), "r"(qh), "r"(0xFFBBu));
             W[r * 4 + j] = __byte_perm(tl, th, 0x5410) ^ neg;
         }
-    uint4 *o = reinterpret_cast<uint4 *>(out);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         uint32_t w[4];
@@ -465,8 +455,25 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *_
                 w[m] = W[k * 4 + m];
             }
         }
-        o[k] = make_uint4(w[0], w[1], w[2], w[3]);
+        out[k ^ swz] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+}
+
+// Copy a warp's 32-slot stage (4 KB, swizzled as above) to global memory: instruction j moves
+// slots 4j..4j+3, i.e. 512 contiguous bytes per warp store.
+template <typename SwzFn, typename DstFn>
+__device__ __forceinline__ void flush_stage(const uint4 *__restrict__ stage, int lane, SwzFn swz_of,
+                                            DstFn dst_of)
+{
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int s = j * 4 + (lane >> 3), k = lane & 7;
+        const uint4 v = stage[s * 8 + (k ^ swz_of(s))];
+        uint4 *d = dst_of(s);
+        if (d) d[k] = v;
+    }
+    __syncwarp();
 }
 
 // Quantisation tables in the layout dct_quant_store_x2 wants.  scale: the block handed to the
@@ -543,14 +550,18 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const void *tmap, int x, 
 // 16-byte-pitched images arrive by one 3-D cp.async.bulk.tensor (TMA); bottom-edge units
 // (row replication) and unaligned images use the warp-cooperative clamped loader.
 // =========================================================================================
-constexpr int K1_WARPS = 4;
+#ifndef K1_WARPS_N
+#define K1_WARPS_N 4
+#endif
+constexpr int K1_WARPS = K1_WARPS_N;
 constexpr int K1_THREADS = K1_WARPS * 32;
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS 3
 #endif
-constexpr int K1_MCUS = 16;
-constexpr int K1_TB = K1_MCUS * 16 * 3;  // 768 bytes per tile row
-constexpr int K1_TILE_BYTES = 16 * K1_TB;
+constexpr int K1_MCUS = 16;             // MCUs per unit, staged as two half tiles of 8 MCUs
+constexpr int K1_HB = 8 * 16 * 3;        // 384 bytes per half-tile row
+constexpr int K1_HALF_BYTES = 16 * K1_HB;  // 6 KB; also hosts that half's 4 KB output stage
+constexpr int K1_TILE_BYTES = 2 * K1_HALF_BYTES;
 
 struct K1Params {
     const uint8_t *pixels;
@@ -563,8 +574,8 @@ struct K1Params {
 };
 
 struct __align__(128) K1WarpSmem {
-    uint8_t tile[K1_TILE_BYTES];
-    uint32_t csum[K1_MCUS * 64];
+    uint8_t tile[2][K1_HALF_BYTES];  // pixels of MCUs 0-7 / 8-15; reused as output stage once read
+    uint32_t csum[K1_MCUS * 64];     // chroma quad sums; reused as the chroma pass's output stage
     uint64_t bar;
 };
 
@@ -596,14 +607,7 @@ __device__ __forceinline__ void ycc_row8(const uint32_t (&w)[6], float (&yv)[8],
         const uint32_t ys = __dp4a(win[x], 0x001D964Du, 128u);
         const int ucb = dp4a_us(win[x], 0x0080552Bu, -32641);
         const int ucr = dp4a_us(win[x], 0x00156B80u, -32641);
-#ifndef OPT_PKSHIFT
-#define OPT_PKSHIFT 1
-#endif
-#if OPT_PKSHIFT
         yv[x] = __uint_as_float(__byte_perm(ys, 0x4B000000u, 0x7651));  // 2^23 + y
-#else
-        yv[x] = byte1_to_float_minus(ys, 8388736.0f);
-#endif
         pp[x] = __vmaxu2(__byte_perm((uint32_t)ucb, (uint32_t)ucr, 0x7531), 0xFF01FF01u);
     }
 #pragma unroll
@@ -650,13 +654,26 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
         ux = rem - my * P.units_x;
     };
     auto unit_by_tma = [&](uint32_t my) { return P.use_tma && (my * 16 + 16 <= P.h); };
-    auto issue_tma = [&](uint64_t u) {
-        uint32_t img, my, ux;
-        decode(u, img, my, ux);
-        if (unit_by_tma(my)) {
+    auto issue_tma = [&](uint64_t u_) {
+        uint32_t img_, my_, ux_;   // both halves under ONE barrier phase (one arrival, 12 KB)
+        decode(u_, img_, my_, ux_);
+        if (unit_by_tma(my_)) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&WS.bar, K1_TILE_BYTES);
-            tma_load_3d(WS.tile, &tmap, (int)(ux * (K1_TB / 8)), (int)(my * 16), (int)img, &WS.bar);
+            tma_load_3d(WS.tile[0], &tmap, (int)(ux_ * (2 * K1_HB / 8)), (int)(my_ * 16), (int)img_, &WS.bar);
+            tma_load_3d(WS.tile[1], &tmap, (int)(ux_ * (2 * K1_HB / 8) + K1_HB / 8), (int)(my_ * 16), (int)img_, &WS.bar);
+        }
+    };
+    // wait for / synchronously load half `half` of the current unit
+    auto acquire_half = [&](uint32_t img_, uint32_t my_, uint32_t ux_, int half) {
+        if (unit_by_tma(my_)) {
+            mbar_wait(&WS.bar, phase);
+            phase ^= 1;
+        } else {
+            const uint8_t *image = P.pixels + (size_t)img_ * P.pixel_stride;
+            const uint32_t x0 = ux_ * (K1_MCUS * 16) + half * 128;
+            if (x0 < P.w) warp_load_tile_rgb<16, 128>(WS.tile[half], image, P.w, P.h, x0, my_ * 16, lane);
+            __syncwarp();
         }
     };
 
@@ -670,9 +687,8 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
             mbar_wait(&WS.bar, phase);
             phase ^= 1;
         } else {
-            warp_load_tile_rgb<16, K1_MCUS * 16>(WS.tile, P.pixels + (size_t)img * P.pixel_stride, P.w,
-                                                 P.h, ux * (K1_MCUS * 16), my * 16, lane);
-            __syncwarp();
+            acquire_half(img, my, ux, 0);
+            acquire_half(img, my, ux, 1);
         }
         const uint32_t mcu0 = ux * K1_MCUS;
         const uint32_t n_mcu = min((uint32_t)K1_MCUS, P.mcus_x - mcu0);
@@ -682,16 +698,18 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
         for (int job = 0; job < 3; ++job) {
             f2 R[4][8];
             const QPair *tab;
-            int16_t *dst;
+            uint4 *stage;   // this warp's 32 x 128-byte output stage for the job
+            int slot, swz;
             bool active;
             if (job < 2) {
                 // ---- 32 Y blocks (8 MCUs) + their packed chroma quad sums ----
                 const int by = lane >> 4, l16 = lane & 15;
                 const int par = l16 >> 3, k8 = l16 & 7;
-                const int mcu = job * 8 + (k8 >> 1) * 2 + par;  // same-parity MCUs per quarter warp
+                const int mj = (k8 >> 1) * 2 + par;   // MCU within the job; same parity per quarter warp
+                const int mcu = job * 8 + mj;
                 const int bx = k8 & 1;
                 active = (uint32_t)mcu < n_mcu;
-                const uint8_t *base = WS.tile + (by * 8) * K1_TB + (mcu * 2 + bx) * 24;
+                const uint8_t *base = WS.tile[job] + (by * 8) * K1_HB + (mj * 2 + bx) * 24;
                 uint4 *cdst = reinterpret_cast<uint4 *>(WS.csum) + mcu * 16;
                 if (active) {
 #pragma unroll
@@ -699,36 +717,33 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
                         float y0[8], y1[8];
                         uint32_t h0[4], h1[4];
                         {
-                            const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2) * K1_TB);
+                            const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2) * K1_HB);
                             const uint2 a = p[0], b = p[1], c = p[2];
                             const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
                             ycc_row8(wds, y0, h0);
                         }
                         {
-                            const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2 + 1) * K1_TB);
+                            const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2 + 1) * K1_HB);
                             const uint2 a = p[0], b = p[1], c = p[2];
                             const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
                             ycc_row8(wds, y1, h1);
                         }
 #pragma unroll
                         for (int x = 0; x < 8; ++x)  // (2^23 + y) - (2^23 + 128) = y - 128, exact
-#if OPT_PKSHIFT
                             R[rp][x] = sub2(pk(y0[x], y1[x]), K2(8388736.0f));
-#else
-                            R[rp][x] = pk(y0[x], y1[x]);
-#endif
                         const int logical = (by * 4 + rp) * 2 + bx;
                         cdst[logical ^ (mcu & 7)] =
                             make_uint4(h0[0] + h1[0], h0[1] + h1[1], h0[2] + h1[2], h0[3] + h1[3]);
                     }
                 }
-                const size_t blk = (mcu_base + mcu) * 4 + by * 2 + bx;
-                dst = P.y + (size_t)img * P.y_stride + blk * 64;
+                __syncwarp();  // every lane is done with this half tile
+                stage = reinterpret_cast<uint4 *>(WS.tile[job]);  // the consumed half becomes the stage
+                slot = mj * 4 + by * 2 + bx;                  // = block index within the job's 32
+                swz = ((slot >> 3) << 1) | (slot & 1);        // distinct across a quarter warp
                 tab = S.q.lum;
             } else {
-                __syncwarp();  // chroma sums complete; every lane is done with the pixel tile
                 const uint64_t un = u + stride;
-                if (lane == 0 && un < nunits) issue_tma(un);
+                if (lane == 0 && un < nunits) issue_tma(un);   // both half tiles were flushed
                 // ---- lanes 0-15: Cb of MCU lane, lanes 16-31: Cr of MCU lane-16 ----
                 const int comp = lane >> 4, mcu = lane & 15;
                 active = (uint32_t)mcu < n_mcu;
@@ -750,29 +765,38 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
                             const uint32_t b[4] = {s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-#if OPT_PKSHIFT
                                 v0[hh * 4 + k] = __uint_as_float(__byte_perm(a[k], 0x4B000000u, sel));
                                 v1[hh * 4 + k] = __uint_as_float(__byte_perm(b[k], 0x4B000000u, sel));
-#else
-                                v0[hh * 4 + k] = FSUB(bias, __uint_as_float(__byte_perm(a[k], 0x4B000000u, sel)));
-                                v1[hh * 4 + k] = FSUB(bias, __uint_as_float(__byte_perm(b[k], 0x4B000000u, sel)));
-#endif
                             }
                         }
 #pragma unroll
-#if OPT_PKSHIFT
                         for (int x = 0; x < 8; ++x) R[i][x] = sub2(K2(bias), pk(v0[x], v1[x]));
-#else
-                        for (int x = 0; x < 8; ++x) R[i][x] = pk(v0[x], v1[x]);
-#endif
                     }
                 }
-                dst = (comp == 0 ? P.cb : P.cr) + (size_t)img * P.c_stride + (mcu_base + mcu) * 64;
+                __syncwarp();  // every lane has read its chroma sums: the buffer becomes the stage
+                stage = reinterpret_cast<uint4 *>(WS.csum);
+                slot = lane;                                  // 0-15 Cb, 16-31 Cr
+                swz = slot & 7;
                 tab = S.q.chr;
             }
-            if (active) dct_quant_store_x2<ZIGZAG>(R, tab, dst, zero2);
+            if (active) dct_quant_store_x2<ZIGZAG>(R, tab, stage + slot * 8, swz, zero2);
+            if (job < 2) {
+                uint4 *ybase = reinterpret_cast<uint4 *>(P.y + (size_t)img * P.y_stride +
+                                                         (mcu_base + job * 8) * 4 * 64);
+                const uint32_t first = job * 8;
+                flush_stage(
+                    stage, lane, [](int s) { return ((s >> 3) << 1) | (s & 1); },
+                    [&](int s) -> uint4 * { return first + (s >> 2) < n_mcu ? ybase + s * 8 : nullptr; });
+            } else {
+                uint4 *cbb = reinterpret_cast<uint4 *>(P.cb + (size_t)img * P.c_stride + mcu_base * 64);
+                uint4 *crb = reinterpret_cast<uint4 *>(P.cr + (size_t)img * P.c_stride + mcu_base * 64);
+                flush_stage(
+                    stage, lane, [](int s) { return s & 7; },
+                    [&](int s) -> uint4 * {
+                        return (uint32_t)(s & 15) < n_mcu ? (s < 16 ? cbb : crb) + (s & 15) * 8 : nullptr;
+                    });
+            }
         }
-        __syncwarp();  // all lanes have read the chroma sums before the next unit overwrites them
     }
 }
 
@@ -983,7 +1007,7 @@ bool make_rgb_tensor_map(CUtensorMap *tm, const uint8_t *pixels, size_t pixel_st
     if (!enc) return false;
     const cuuint64_t gdim[3] = {pitch / 8, h, n};
     const cuuint64_t gstr[2] = {pitch, n > 1 ? pixel_stride : pitch * h};
-    const cuuint32_t box[3] = {K1_TB / 8, 16, 1};
+    const cuuint32_t box[3] = {K1_HB / 8, 16, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t *>(pixels), gdim, gstr, box,
                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -1003,17 +1027,18 @@ int launch_k1(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint32
     alignas(64) CUtensorMap tm;
     memset(&tm, 0, sizeof tm);
     P.use_tma = make_rgb_tensor_map(&tm, px, pixel_stride, n, w, h) ? 1u : 0u;
-    static int blocks_per_sm[2] = {0, 0};
+    static int blocks_per_sm[64][2];  // function attributes are per device
     const size_t smem = sizeof(K1Smem);
     auto kern = zigzag ? k_jpeg_420<true> : k_jpeg_420<false>;
-    if (!blocks_per_sm[zigzag]) {
+    int &bps = blocks_per_sm[ctx->device & 63][zigzag];
+    if (!bps) {
         PIXO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
         PIXO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K1_THREADS, smem));
-        blocks_per_sm[zigzag] = nb > 0 ? nb : 1;
+        bps = nb > 0 ? nb : 1;
     }
     const uint64_t nunits = (uint64_t)P.mcus_y * P.units_x * n;
-    uint64_t grid = (uint64_t)ctx->sm_count * blocks_per_sm[zigzag];
+    uint64_t grid = (uint64_t)ctx->sm_count * bps;
     if (grid > (nunits + K1_WARPS - 1) / K1_WARPS) grid = (nunits + K1_WARPS - 1) / K1_WARPS;
     kern<<<(unsigned)grid, K1_THREADS, smem, ctx->stream>>>(P, qt, tm);
     ctx->launches++;

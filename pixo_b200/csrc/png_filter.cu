@@ -375,7 +375,8 @@ int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_strid
 
     const size_t segcap = row_bytes + 15 < (size_t)SEG_BYTES ? ((row_bytes + 15) & ~(size_t)15) : (size_t)SEG_BYTES;
     const size_t smem = 2 * (16 + segcap) + segcap + 32;
-    static bool attr_set = false;
+    static bool attr_set_dev[64];  // function attributes are per device
+    bool &attr_set = attr_set_dev[ctx->device & 63];
     if (!attr_set) {
         PIXO_CUDA(ctx, cudaFuncSetAttribute(k_png_filter, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(2 * (16 + SEG_BYTES) + SEG_BYTES + 32)));
