@@ -8,12 +8,12 @@
 //   quantize::zigzag_reorder          src/jpeg/quantize.rs:107-113 (optional, free: register renaming)
 // and emits the arrays compute_all_coefficients (src/jpeg/mod.rs:932-966) returns.
 //
-// Design (B200): one thread owns one 8x8 block entirely in registers, so both 1-D passes are
-// plain register arithmetic with no transposes or shuffles.  A CTA stages a 16-row strip of
-// interleaved RGB (32 MCUs, 24 KB) in shared memory; Y threads read their 8x24-byte rows
-// conflict-free (24-byte lane stride), colour-convert with dp4a, and leave packed 2x2 chroma
-// sums (cb | cr<<16) in a swizzled 8 KB exchange buffer from which the chroma threads build
-// their blocks.  HBM traffic is exactly the algorithmic 3 B/px in + 3 B/px out.
+// Design (B200): one thread owns one 8x8 block entirely in registers (both 1-D passes are plain
+// packed-f32x2 register arithmetic, no shuffles).  K1 (4:2:0) runs persistent warp-autonomous
+// workers fed by TMA; a warp colour-converts with dp4a straight out of its shared-memory pixel
+// tile, exchanges packed 2x2 chroma sums through a swizzled warp-private buffer, and writes
+// coefficients through a swizzled stage with 512-byte coalesced warp stores.  HBM traffic is
+// exactly the algorithmic 3 B/px in + 3 B/px out (ncu: profiles/).
 #include <cuda.h>
 #include <string.h>
 
@@ -22,12 +22,7 @@
 namespace pixo {
 namespace {
 
-__constant__ uint8_t kZigzag[64] = {
-    0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
-    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
-    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-
-// compile-time copy for static register renaming
+// zig-zag order (src/jpeg/quantize.rs:18-22) as a compile-time table: static register renaming
 __host__ __device__ constexpr int zz(int i)
 {
     constexpr int t[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
@@ -57,86 +52,6 @@ __host__ __device__ constexpr int zz(int i)
 #define AAN_S6 0.6532815f
 #define AAN_S7 1.2814578f
 
-// aan_dct_1d, src/jpeg/dct.rs:648-700 — op for op.
-__device__ __forceinline__ void aan_1d(float &d0, float &d1, float &d2, float &d3, float &d4,
-                                       float &d5, float &d6, float &d7)
-{
-    const float tmp0 = FADD(d0, d7), tmp7 = FSUB(d0, d7);
-    const float tmp1 = FADD(d1, d6), tmp6 = FSUB(d1, d6);
-    const float tmp2 = FADD(d2, d5), tmp5 = FSUB(d2, d5);
-    const float tmp3 = FADD(d3, d4), tmp4 = FSUB(d3, d4);
-
-    const float tmp10 = FADD(tmp0, tmp3), tmp13 = FSUB(tmp0, tmp3);
-    const float tmp11 = FADD(tmp1, tmp2), tmp12 = FSUB(tmp1, tmp2);
-
-    const float o0 = FADD(tmp10, tmp11);
-    const float o4 = FSUB(tmp10, tmp11);
-    const float z1 = FMUL(FADD(tmp12, tmp13), AAN_A1);
-    const float o2 = FADD(tmp13, z1);
-    const float o6 = FSUB(tmp13, z1);
-
-    const float u10 = FADD(tmp4, tmp5), u11 = FADD(tmp5, tmp6), u12 = FADD(tmp6, tmp7);
-    const float z5 = FMUL(FSUB(u10, u12), AAN_A5);
-    const float z2 = FADD(FMUL(u10, AAN_A2), z5);
-    const float z4 = FADD(FMUL(u12, AAN_A4), z5);
-    const float z3 = FMUL(u11, AAN_A3);
-    const float z11 = FADD(tmp7, z3), z13 = FSUB(tmp7, z3);
-
-    d0 = FMUL(o0, AAN_S0);
-    d1 = FMUL(FADD(z11, z4), AAN_S1);
-    d2 = FMUL(o2, AAN_S2);
-    d3 = FMUL(FSUB(z13, z2), AAN_S3);
-    d4 = FMUL(o4, AAN_S4);
-    d5 = FMUL(FADD(z13, z2), AAN_S5);
-    d6 = FMUL(o6, AAN_S6);
-    d7 = FMUL(FSUB(z11, z4), AAN_S7);
-}
-
-// dct_2d (rows then columns, src/jpeg/dct.rs:614-646) + quantize_block
-// ((x / q).round() as i16, src/jpeg/quantize.rs:99-105) + optional zig-zag, then 8x 16-byte
-// stores of the block's 64 int16.
-//   x / q : q0 = x*r; q = fma(fma(-q0, d, x), r, q0) == RN(x/d)   (tools/verify_div.c)
-//   round : trunc(RZ(q + copysign(0.5, q))) == round-half-away(q)  (tools/verify_div.c)
-// |coefficient| <= 8*128 so the i16 cast never saturates.
-template <bool ZIGZAG>
-__device__ __forceinline__ void dct_quant_store(float (&v)[64], const float *__restrict__ D,
-                                                const float *__restrict__ R,
-                                                int16_t *__restrict__ out)
-{
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-        aan_1d(v[r * 8 + 0], v[r * 8 + 1], v[r * 8 + 2], v[r * 8 + 3], v[r * 8 + 4],
-               v[r * 8 + 5], v[r * 8 + 6], v[r * 8 + 7]);
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        aan_1d(v[c], v[8 + c], v[16 + c], v[24 + c], v[32 + c], v[40 + c], v[48 + c],
-               v[56 + c]);
-
-    int n[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) {
-        const float x = v[i];
-        const float q0 = FMUL(x, R[i]);
-        const float e = __fmaf_rn(-q0, D[i], x);
-        const float q = __fmaf_rn(e, R[i], q0);
-        const float half = __int_as_float((__float_as_int(q) & 0x80000000) | 0x3F000000);
-        n[i] = __float2int_rz(__fadd_rz(q, half));
-    }
-    uint4 *o = reinterpret_cast<uint4 *>(out);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        uint32_t w[4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int i0 = k * 8 + m * 2;
-            const int lo = ZIGZAG ? n[zz(i0)] : n[i0];
-            const int hi = ZIGZAG ? n[zz(i0 + 1)] : n[i0 + 1];
-            w[m] = __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
-        }
-        o[k] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-}
-
 // ---- colour conversion on packed bytes ---------------------------------------------------
 __device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c)
 {
@@ -149,39 +64,6 @@ __device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c)
 __device__ __forceinline__ float byte1_to_float_minus(uint32_t s, float magic)
 {
     return FSUB(__uint_as_float(__byte_perm(s, 0x4B000000u, 0x7651)), magic);
-}
-
-// One pixel, src/color.rs:60-77.  rgbb = (r,g,b,b), rgbr = (r,g,b,r) as packed bytes.
-//   y  = (77r + 150g + 29b + 128) >> 8                       (never leaves 0..255)
-//   cb = clamp(((-43r - 85g + 128b + 128) >> 8) + 128)  = min(((-43r-85g+64b+64b + 32896) >> 8), 255)
-//   cr = clamp(((128r - 107g - 21b + 128) >> 8) + 128)  = min(((127r-107g-21b+r + 32896) >> 8), 255)
-// (adding 32768 before the arithmetic shift == adding 128 after it; the lower clamp is dead.)
-// Returns Y - 128 as float; *cbcr = cb | cr << 16.
-__device__ __forceinline__ float ycc_pixel(uint32_t rgbb, uint32_t rgbr, uint32_t *cbcr)
-{
-    const uint32_t ys = __dp4a(rgbb, 0x001D964Du, 128u);            // 77,150,29,0
-    const int cbs = min(dp4a_us(rgbb, 0x4040ABD5u, 32896), 65535);  // -43,-85,64,64
-    const int crs = min(dp4a_us(rgbr, 0x01EB957Fu, 32896), 65535);  // 127,-107,-21,1
-    *cbcr = __byte_perm((uint32_t)cbs, (uint32_t)crs, 0x7531);      // cb | cr<<16 (bytes 3 are 0)
-    return byte1_to_float_minus(ys, 8388736.0f);                    // 2^23 + 128
-}
-
-// 8 RGB pixels held in six little-endian words -> (r,g,b,b) and (r,g,b,r) per pixel.
-__device__ __forceinline__ void unpack8(const uint32_t (&w)[6], uint32_t (&bb)[8],
-                                        uint32_t (&br)[8])
-{
-#pragma unroll
-    for (int hlf = 0; hlf < 2; ++hlf) {
-        const uint32_t a = w[hlf * 3], b = w[hlf * 3 + 1], c = w[hlf * 3 + 2];
-        bb[hlf * 4 + 0] = __byte_perm(a, b, 0x2210);
-        br[hlf * 4 + 0] = __byte_perm(a, b, 0x0210);
-        bb[hlf * 4 + 1] = __byte_perm(a, b, 0x5543);
-        br[hlf * 4 + 1] = __byte_perm(a, b, 0x3543);
-        bb[hlf * 4 + 2] = __byte_perm(b, c, 0x4432);
-        br[hlf * 4 + 2] = __byte_perm(b, c, 0x2432);
-        bb[hlf * 4 + 3] = __byte_perm(c, c, 0x3321);
-        br[hlf * 4 + 3] = __byte_perm(c, c, 0x1321);
-    }
 }
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
@@ -321,13 +203,6 @@ __device__ __forceinline__ void mulc(f2 a, float c, float &lo, float &hi)
     lo = FMUL(x, c);
     hi = FMUL(y, c);
 }
-__device__ __forceinline__ f2 mul2c(f2 a, float c)
-{
-    float lo, hi;
-    mulc(a, c, lo, hi);
-    return pk(lo, hi);
-}
-
 // aan_dct_1d (src/jpeg/dct.rs:648-700) on two independent 8-vectors at once; returns the eight
 // outputs *before* the S[k] post-scale (o[k]), which the caller applies.
 // Products that feed an add are written as fma(x, c, z) with z an opaque +0.0 pair (a kernel
@@ -801,90 +676,138 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
 }
 
 // =========================================================================================
-// K2: RGB 4:4:4 (192 threads: warp pairs 0-1 = Y, 2-3 = Cb, 4-5 = Cr) and Gray (64 threads).
-// CTA = 64 blocks of one block row.
+// K2: RGB 4:4:4 (192 threads: warps 0-1 = Y, 2-3 = Cb, 4-5 = Cr of the same 64 blocks) and
+// Gray (64 threads).  CTA = 64 blocks of one block row; every warp owns 32 consecutive blocks of
+// one component, runs the same packed block pipeline as K1 and flushes its 4 KB stage with
+// coalesced stores.
 // =========================================================================================
 constexpr int K2_BLOCKS = 64;
+
+// 8 RGB pixels in six words -> (value - 128) as float for component `comp` (0 Y, 1 Cb, 2 Cr)
+__device__ __forceinline__ void comp_row8(const uint32_t (&w)[6], int comp, float (&v)[8])
+{
+    uint32_t win[8];
+    win[0] = w[0];
+    win[1] = __funnelshift_r(w[0], w[1], 24);
+    win[2] = __funnelshift_r(w[1], w[2], 16);
+    win[3] = w[2] >> 8;
+    win[4] = w[3];
+    win[5] = __funnelshift_r(w[3], w[4], 24);
+    win[6] = __funnelshift_r(w[4], w[5], 16);
+    win[7] = w[5] >> 8;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+        if (comp == 0) {
+            const uint32_t ys = __dp4a(win[x], 0x001D964Du, 128u);
+            v[x] = byte1_to_float_minus(ys, 8388736.0f);              // y - 128
+        } else {
+            // byte 1 of u = 256 - c (c = cb or cr before the clamp); c <= 255 <=> u >= -65280
+            const int u = max(dp4a_us(win[x], comp == 1 ? 0x0080552Bu : 0x00156B80u, -32641), -65280);
+            v[x] = FSUB(8388736.0f, __uint_as_float(__byte_perm((uint32_t)u, 0x4B000000u, 0x7651)));  // c - 128
+        }
+    }
+}
 
 template <bool ZIGZAG>
 __global__ void __launch_bounds__(192)
 k_jpeg_444(const uint8_t *__restrict__ pixels, size_t pixel_stride, uint32_t w, uint32_t h,
            uint32_t blocks_x, uint32_t tiles_x, int16_t *__restrict__ yout, size_t y_stride,
            int16_t *__restrict__ cbout, int16_t *__restrict__ crout, size_t c_stride,
-           const __grid_constant__ QuantTab qt)
+           const __grid_constant__ QuantTab qt, const float zero_lo, const float zero_hi)
 {
     constexpr int TB = K2_BLOCKS * 8 * 3;  // 1536
     __shared__ __align__(16) uint8_t tile[8 * TB];
-    const int tid = threadIdx.x;
+    __shared__ __align__(16) uint4 stage[6][256];
+    __shared__ QuantSmem qs;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tx = blockIdx.x % tiles_x;
     const uint32_t brow = blockIdx.x / tiles_x;
     const uint32_t img = blockIdx.y;
     const uint8_t *image = pixels + (size_t)img * pixel_stride;
+    fill_quant_smem(&qs, qt, 1.0f, tid, 192);
     load_tile<3, 8, K2_BLOCKS * 8, 192>(tile, image, w, h, tx * (K2_BLOCKS * 8), brow * 8, tid);
     __syncthreads();
 
-    const int comp = tid >> 6;  // warp-uniform: 0 = Y, 1 = Cb, 2 = Cr
-    const int j = tid & 63;
+    const int comp = warp >> 1;            // warp-uniform: 0 = Y, 1 = Cb, 2 = Cr
+    const int j = (warp & 1) * 32 + lane;  // block within the tile
     const uint32_t b0 = tx * K2_BLOCKS;
-    if (b0 + j >= blocks_x) return;
-    float v[64];
-    const uint8_t *base = tile + j * 24;
+    const bool active = b0 + j < blocks_x;
+    const f2 zero2 = pk(zero_lo, zero_hi);
+    if (active) {
+        f2 R[4][8];
+        const uint8_t *base = tile + j * 24;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const uint2 *p = reinterpret_cast<const uint2 *>(base + r * TB);
-        const uint2 a = p[0], b = p[1], c = p[2];
-        const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-        uint32_t bb[8], br[8];
-        unpack8(wds, bb, br);
+        for (int rp = 0; rp < 4; ++rp) {
+            float v0[8], v1[8];
+            {
+                const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2) * TB);
+                const uint2 a = p[0], b = p[1], c = p[2];
+                const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+                comp_row8(wds, comp, v0);
+            }
+            {
+                const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2 + 1) * TB);
+                const uint2 a = p[0], b = p[1], c = p[2];
+                const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+                comp_row8(wds, comp, v1);
+            }
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            uint32_t s;
-            if (comp == 0) s = __dp4a(bb[x], 0x001D964Du, 128u);
-            else if (comp == 1) s = (uint32_t)min(dp4a_us(bb[x], 0x4040ABD5u, 32896), 65535);
-            else s = (uint32_t)min(dp4a_us(br[x], 0x01EB957Fu, 32896), 65535);
-            v[r * 8 + x] = byte1_to_float_minus(s, 8388736.0f);  // value - 128.0
+            for (int x = 0; x < 8; ++x) R[rp][x] = pk(v0[x], v1[x]);
         }
+        dct_quant_store_x2<ZIGZAG>(R, comp == 0 ? qs.lum : qs.chr, stage[warp] + lane * 8, lane & 7, zero2);
     }
-    const size_t blk = (size_t)brow * blocks_x + b0 + j;
-    if (comp == 0)
-        dct_quant_store<ZIGZAG>(v, qt.lum_d, qt.lum_r, yout + (size_t)img * y_stride + blk * 64);
-    else
-        dct_quant_store<ZIGZAG>(v, qt.chr_d, qt.chr_r,
-                                (comp == 1 ? cbout : crout) + (size_t)img * c_stride + blk * 64);
+    int16_t *arr = comp == 0 ? yout + (size_t)img * y_stride
+                             : (comp == 1 ? cbout : crout) + (size_t)img * c_stride;
+    const uint32_t first = b0 + (warp & 1) * 32;
+    uint4 *dbase = reinterpret_cast<uint4 *>(arr + ((size_t)brow * blocks_x + first) * 64);
+    flush_stage(
+        stage[warp], lane, [](int s) { return s & 7; },
+        [&](int s) -> uint4 * { return first + s < blocks_x ? dbase + s * 8 : nullptr; });
 }
 
 template <bool ZIGZAG>
 __global__ void __launch_bounds__(64)
 k_jpeg_gray(const uint8_t *__restrict__ pixels, size_t pixel_stride, uint32_t w, uint32_t h,
             uint32_t blocks_x, uint32_t tiles_x, int16_t *__restrict__ yout, size_t y_stride,
-            const __grid_constant__ QuantTab qt)
+            const __grid_constant__ QuantTab qt, const float zero_lo, const float zero_hi)
 {
     constexpr int TB = K2_BLOCKS * 8;  // 512
     __shared__ __align__(16) uint8_t tile[8 * TB];
-    const int tid = threadIdx.x;
+    __shared__ __align__(16) uint4 stage[2][256];
+    __shared__ QuantSmem qs;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tx = blockIdx.x % tiles_x;
     const uint32_t brow = blockIdx.x / tiles_x;
     const uint32_t img = blockIdx.y;
     const uint8_t *image = pixels + (size_t)img * pixel_stride;
+    fill_quant_smem(&qs, qt, 1.0f, tid, 64);
     load_tile<1, 8, K2_BLOCKS * 8, 64>(tile, image, w, h, tx * (K2_BLOCKS * 8), brow * 8, tid);
     __syncthreads();
     const int j = tid;
     const uint32_t b0 = tx * K2_BLOCKS;
-    if (b0 + j >= blocks_x) return;
-    float v[64];
+    const f2 zero2 = pk(zero_lo, zero_hi);
+    if (b0 + j < blocks_x) {
+        f2 R[4][8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const uint2 a = *reinterpret_cast<const uint2 *>(tile + r * TB + j * 8);
-        const uint32_t wd[2] = {a.x, a.y};
+        for (int rp = 0; rp < 4; ++rp) {
+            const uint2 a = *reinterpret_cast<const uint2 *>(tile + (rp * 2) * TB + j * 8);
+            const uint2 b = *reinterpret_cast<const uint2 *>(tile + (rp * 2 + 1) * TB + j * 8);
+            const uint32_t wa[2] = {a.x, a.y}, wb[2] = {b.x, b.y};
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            // gray as f32 - 128.0, src/jpeg/mod.rs:1584-1589
-            const uint32_t bits = __byte_perm(wd[x >> 2], 0x4B000000u, 0x7650 + (x & 3));
-            v[r * 8 + x] = FSUB(__uint_as_float(bits), 8388736.0f);
+            for (int x = 0; x < 8; ++x) {
+                // gray as f32 - 128.0, src/jpeg/mod.rs:1584-1589
+                const float f0 = __uint_as_float(__byte_perm(wa[x >> 2], 0x4B000000u, 0x7650 + (x & 3)));
+                const float f1 = __uint_as_float(__byte_perm(wb[x >> 2], 0x4B000000u, 0x7650 + (x & 3)));
+                R[rp][x] = sub2(pk(f0, f1), K2(8388736.0f));
+            }
         }
+        dct_quant_store_x2<ZIGZAG>(R, qs.lum, stage[warp] + lane * 8, lane & 7, zero2);
     }
-    const size_t blk = (size_t)brow * blocks_x + b0 + j;
-    dct_quant_store<ZIGZAG>(v, qt.lum_d, qt.lum_r, yout + (size_t)img * y_stride + blk * 64);
+    const uint32_t first = b0 + warp * 32;
+    uint4 *dbase = reinterpret_cast<uint4 *>(yout + (size_t)img * y_stride + ((size_t)brow * blocks_x + first) * 64);
+    flush_stage(
+        stage[warp], lane, [](int s) { return s & 7; },
+        [&](int s) -> uint4 * { return first + s < blocks_x ? dbase + s * 8 : nullptr; });
 }
 
 // =========================================================================================
@@ -1075,14 +998,14 @@ int launch_jpeg_transform(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pi
             const uint32_t bx = (w + 7) / 8, by = (h + 7) / 8;
             const uint32_t tiles_x = (bx + K2_BLOCKS - 1) / K2_BLOCKS;
             dim3 grid(tiles_x * by, nb);
-            if (zigzag) k_jpeg_gray<true><<<grid, 64, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, qt);
-            else k_jpeg_gray<false><<<grid, 64, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, qt);
+            if (zigzag) k_jpeg_gray<true><<<grid, 64, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, qt, 0.0f, 0.0f);
+            else k_jpeg_gray<false><<<grid, 64, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, qt, 0.0f, 0.0f);
         } else if (subsampling == PIXO_B200_S444) {
             const uint32_t bx = (w + 7) / 8, by = (h + 7) / 8;
             const uint32_t tiles_x = (bx + K2_BLOCKS - 1) / K2_BLOCKS;
             dim3 grid(tiles_x * by, nb);
-            if (zigzag) k_jpeg_444<true><<<grid, 192, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, cb, cr, c_stride, qt);
-            else k_jpeg_444<false><<<grid, 192, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, cb, cr, c_stride, qt);
+            if (zigzag) k_jpeg_444<true><<<grid, 192, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, cb, cr, c_stride, qt, 0.0f, 0.0f);
+            else k_jpeg_444<false><<<grid, 192, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, cb, cr, c_stride, qt, 0.0f, 0.0f);
         } else {
             PIXO_TRY(launch_k1(ctx, px, pixel_stride, nb, w, h, y, y_stride, cb, cr, c_stride, qt, zigzag));
             continue;
