@@ -141,12 +141,88 @@ __global__ void __launch_bounds__(PNG_THREADS) k_png_filter(const PngParams P)
     const uint32_t n_out = (uint32_t)rb + 1;
     unsigned long long adlA = 0, adlB = 0;
 
-    for (int pass = need_scores ? 0 : 1; pass < 2; ++pass) {
+    if (filter == PIXO_B200_FILTER_BIGRAMS) {
+        // bigrams_filter / score_bigrams (src/png/filter.rs:410-471,635-649): the candidate with
+        // the fewest DISTINCT adjacent byte pairs wins (strict <, order None,Sub,Up,Avg,Paeth).
+        // One 65 536-bit "seen" bitmap in shared memory per candidate; a thread counts the bits
+        // it is the first to set.
+        uint32_t *bitmap = reinterpret_cast<uint32_t *>(sbuf + segcap + 32);
+        __shared__ uint32_t bg_cnt[PNG_THREADS / 32];
+        __shared__ uint32_t bg_last;
+        unsigned long long best_score = ~0ull;
+        int best = 0;
+        for (int f = 0; f < 5; ++f) {
+            for (int i = tid; i < 2048; i += PNG_THREADS) bitmap[i] = 0;
+            uint32_t cnt = 0;
+            for (int seg = 0; seg < nseg; ++seg) {
+                const size_t s0 = (size_t)seg * segcap;
+                const int slen = (int)min((size_t)segcap, rb - s0);
+                __syncthreads();
+                if (nseg > 1 || f == 0) {
+                    if (tid < 16) {
+                        const long long gi = (long long)s0 - 16 + tid;
+                        cur[tid] = gi >= 0 ? row[gi] : 0;
+                        prev[tid] = (gi >= 0 && prow) ? prow[gi] : 0;
+                    }
+                    stage_bytes(cur + 16, row + s0, slen, lo_b, hi_b, tid);
+                    if (prow) stage_bytes(prev + 16, prow + s0, slen, lo_b, hi_b, tid);
+                    else for (int i = tid; i < slen; i += PNG_THREADS) prev[16 + i] = 0;
+                    __syncthreads();
+                }
+                const uint32_t *c32 = reinterpret_cast<const uint32_t *>(cur) + 4;
+                const uint32_t *p32 = reinterpret_cast<const uint32_t *>(prev) + 4;
+                const int nw = (slen + 3) >> 2;
+                for (int k = tid; k < nw; k += PNG_THREADS) {
+                    const uint32_t x = c32[k], b = p32[k];
+                    const uint32_t a = __funnelshift_r(c32[k - 1], x, ashift);
+                    const uint32_t c = __funnelshift_r(p32[k - 1], b, ashift);
+                    uint32_t v;
+                    switch (f) {
+                    case 0: v = x; break;
+                    case 1: v = __vsub4(x, a); break;
+                    case 2: v = __vsub4(x, b); break;
+                    case 3: v = __vsub4(x, __vhaddu4(a, b)); break;
+                    default: v = __vsub4(x, paeth4(a, b, c)); break;
+                    }
+                    reinterpret_cast<uint32_t *>(sbuf)[k] = v;
+                }
+                __syncthreads();
+                // windows(2) over this segment's bytes, plus the pair straddling the previous segment
+                for (int i = tid; i < slen; i += PNG_THREADS) {
+                    uint32_t key;
+                    if (i + 1 < slen) key = ((uint32_t)sbuf[i] << 8) | sbuf[i + 1];
+                    else continue;
+                    const uint32_t bit = 1u << (key & 31);
+                    if (!(atomicOr(&bitmap[key >> 5], bit) & bit)) ++cnt;
+                }
+                if (seg > 0 && tid == 0) {
+                    const uint32_t key = (bg_last << 8) | sbuf[0];
+                    const uint32_t bit = 1u << (key & 31);
+                    if (!(atomicOr(&bitmap[key >> 5], bit) & bit)) ++cnt;
+                }
+                __syncthreads();
+                if (tid == 0) bg_last = sbuf[slen - 1];
+            }
+            uint32_t v = cnt;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0) bg_cnt[tid >> 5] = v;
+            __syncthreads();
+            unsigned long long score = 0;
+            for (int w = 0; w < PNG_THREADS / 32; ++w) score += bg_cnt[w];
+            if (score < best_score) { best_score = score; best = f; }
+            __syncthreads();
+        }
+        filter = best;
+    }
+
+    for (int pass = (need_scores && filter >= 5) ? 0 : 1; pass < 2; ++pass) {
         unsigned long long sc[5] = {0, 0, 0, 0, 0};
         for (int seg = 0; seg < nseg; ++seg) {
             const size_t s0 = (size_t)seg * segcap;
             const int slen = (int)min((size_t)segcap, rb - s0);
-            const bool restage = !(nseg == 1 && pass == 1 && need_scores);
+            const bool restage = !(nseg == 1 && pass == 1 && need_scores && P.strategy != PIXO_B200_FILTER_BIGRAMS) ||
+                                 (nseg > 1);
             if (restage) {
                 __syncthreads();
                 // 16-byte front halo: the bpp bytes left of the segment (zeros at row start)
@@ -299,6 +375,273 @@ __global__ void __launch_bounds__(PNG_THREADS) k_png_filter(const PngParams P)
     }
 }
 
+// =========================================================================================
+// K4 (band kernel): a CTA walks a band of consecutive rows with a 3-deep ring of row buffers —
+// previous / current / next — so every raw byte is read from HBM exactly once and the next row
+// streams in (cp.async, 16-byte) under the current row's arithmetic.  Lane l of warp w owns
+// words w*C + 32*i + l of the row, so shared-memory and global accesses are fully coalesced.
+//   scores   : |i8(x - pred)| = 128 - | |x - pred| - 128 |  per byte, hence per word
+//              score = 512 - SAD(|x - pred|, 0x80808080): two native VABSDIFF4 per candidate
+//   paeth    : branch-free byte-SIMD predictor (see paeth_pred4)
+//   output   : winner re-derived, shifted to the row's byte phase in the output stream with one
+//              funnel shift against the neighbouring lane's word, aligned 32-bit stores
+//   adler    : per-thread sums folded with the row's distance to the end of the image; one block
+//              reduction per band
+// Used for every strategy except the sticky small-image AdaptiveFast case and rows too long for
+// three shared-memory row buffers, which stay on the row kernel above.
+// =========================================================================================
+#ifndef PNG_BAND_MIN_BLOCKS
+#define PNG_BAND_MIN_BLOCKS 4
+#endif
+#ifndef PNG_BAND_ROWS
+#define PNG_BAND_ROWS 16
+#endif
+constexpr int BAND_ROWS = PNG_BAND_ROWS;
+
+__device__ __forceinline__ uint32_t sel4(uint32_t mask, uint32_t x, uint32_t y)
+{
+    return (x & mask) | (y & ~mask);
+}
+
+// fallback_paeth_predictor (src/simd/fallback.rs:143-159) for four byte lanes at once.
+// With pa=|b-c|, pb=|a-c|, dab=|a-b|:  c lies within [min(a,b), max(a,b)]  <=>  max(pa,pb) <= dab,
+// in which case pc = |pa-pb|, otherwise pc = pa+pb >= max(pa,pb).  The reference's ladder
+// (a if pa<=pb && pa<=pc, else b if pb<=pc, else c) therefore reduces to: take the nearer of a/b
+// (a on ties) unless c is within the range and that nearer distance exceeds |pa-pb|, then c.
+__device__ __forceinline__ uint32_t paeth_pred4(uint32_t a, uint32_t b, uint32_t c)
+{
+    const uint32_t pa = __vabsdiffu4(b, c), pb = __vabsdiffu4(a, c), dab = __vabsdiffu4(a, b);
+    const uint32_t m1 = __vcmpleu4(pa, pb);          // 0xFF where pa <= pb
+    const uint32_t cand = sel4(m1, a, b);
+    const uint32_t mn = sel4(m1, pa, pb), mx = sel4(m1, pb, pa);
+    const uint32_t adiff = __vabsdiffu4(pa, pb);
+    const uint32_t within = __vcmpleu4(mx, dab);
+    const uint32_t keep = __vcmpleu4(mn, adiff);     // nearer endpoint still beats c
+    return sel4(within & ~keep, c, cand);
+}
+
+struct BandParams {
+    const uint8_t *data;
+    size_t in_stride;
+    uint8_t *out;
+    size_t out_stride;
+    uint32_t height, row_bytes, bpp, strategy;
+    unsigned long long *acc;   // per-image {A, B} (may be null)
+    uint32_t *counter;         // per-image band completion counter
+    uint32_t *adler_out;
+    uint32_t nbands;
+    uint32_t async16;          // rows are 16-byte aligned: cp.async path
+};
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(const BandParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint32_t red[5][PNG_THREADS / 32];
+    __shared__ unsigned long long red64[3][PNG_THREADS / 32];
+    __shared__ int s_filter;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t img = blockIdx.y;
+    const uint32_t rb = P.row_bytes;
+    const uint32_t pitch = 16 + ((rb + 15) & ~15u) + 16;   // [16 B zero halo][row][slack]
+    uint8_t *bufs[3] = {smem, smem + pitch, smem + 2 * pitch};
+    const uint8_t *image = P.data + (size_t)img * P.in_stride;
+    const uint8_t *lo_b = image, *hi_b = image + (size_t)P.height * rb;
+    const uint32_t r0 = blockIdx.x * BAND_ROWS;
+    const uint32_t r1 = min(P.height, r0 + BAND_ROWS);
+    const uint32_t n_out = rb + 1;
+    const uint32_t nw = (rb + 3) >> 2;
+    const uint32_t ashift = (4 - P.bpp) * 8;
+    // each warp owns a contiguous chunk of output words (a multiple of 32)
+    const uint32_t nj = (rb + 3 + 3) / 4 + 1;                       // output words incl. phase slack
+    const uint32_t chunk = (((nj + 7) / 8) + 31) & ~31u;
+    const uint32_t j_lo = warp * chunk, j_hi = min(nj, j_lo + chunk);
+
+    auto load_row = [&](uint32_t r, uint8_t *buf, bool async) {
+        const uint8_t *src = image + (size_t)r * rb;
+        if (P.async16) {
+            const uint32_t nv = rb >> 4;
+            for (uint32_t k = tid; k < nv; k += PNG_THREADS) cp_async16(buf + 16 + 16 * k, src + 16 * (size_t)k);
+            for (uint32_t i = (nv << 4) + tid; i < rb; i += PNG_THREADS) buf[16 + i] = src[i];
+        } else {
+            stage_bytes(buf + 16, src, (int)rb, lo_b, hi_b, tid);
+        }
+        (void)async;
+    };
+    // halos are zero for the whole band ("left" of the first pixel is 0)
+    if (tid < 12) reinterpret_cast<uint32_t *>(bufs[tid >> 2])[tid & 3] = 0;
+    // previous row of the band's first row (zeros above row 0), then the first row
+    if (r0 == 0) {
+        for (uint32_t i = tid; i < (pitch - 16) / 4; i += PNG_THREADS)
+            reinterpret_cast<uint32_t *>(bufs[(r0 + 2) % 3] + 16)[i] = 0;
+    } else {
+        load_row(r0 - 1, bufs[(r0 + 2) % 3], false);
+    }
+    load_row(r0, bufs[r0 % 3], false);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    unsigned long long accA = 0, accBpos = 0, accBneg = 0;
+    const unsigned long long Ntot = (unsigned long long)P.height * n_out;
+
+    for (uint32_t r = r0; r < r1; ++r) {
+        if (r + 1 < r1) load_row(r + 1, bufs[(r + 1) % 3], true);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the newest group
+        __syncthreads();
+        const uint32_t *c32 = reinterpret_cast<const uint32_t *>(bufs[r % 3]) + 4;
+        const uint32_t *p32 = reinterpret_cast<const uint32_t *>(bufs[(r + 2) % 3]) + 4;
+
+        auto operands = [&](uint32_t k, uint32_t &x, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &mask) {
+            x = c32[k]; b = p32[k];
+            a = __funnelshift_r(c32[(int)k - 1], x, ashift);
+            c = __funnelshift_r(p32[(int)k - 1], b, ashift);
+            const int valid = (int)rb - 4 * (int)k;
+            mask = valid >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - valid)));
+        };
+
+        int filter = (int)P.strategy;
+        if (filter >= 5) {
+            uint32_t T[5] = {0, 0, 0, 0, 0};
+            const bool fast = P.strategy == PIXO_B200_FILTER_ADAPTIVE_FAST;
+            for (uint32_t k = tid; k < nw; k += PNG_THREADS) {
+                uint32_t x, a, b, c, mask;
+                operands(k, x, a, b, c, mask);
+                T[1] += __vsadu4(__vabsdiffu4(x, a) & mask, 0x80808080u);
+                T[2] += __vsadu4(__vabsdiffu4(x, b) & mask, 0x80808080u);
+                T[4] += __vsadu4(__vabsdiffu4(x, paeth_pred4(a, b, c)) & mask, 0x80808080u);
+                if (!fast) {
+                    T[0] += __vsadu4(x & mask, 0x80808080u);
+                    T[3] += __vsadu4(__vabsdiffu4(x, __vhaddu4(a, b)) & mask, 0x80808080u);
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                uint32_t v = T[f];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) red[f][warp] = v;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long s[5];
+                for (int f = 0; f < 5; ++f) {
+                    unsigned long long t = 0;
+                    for (int w = 0; w < PNG_THREADS / 32; ++w) t += red[f][w];
+                    s[f] = 512ull * nw - t;   // score_filter: sum |i8|
+                }
+                int best;
+                if (fast) {   // adaptive_filter_fast, src/png/filter.rs:474-527
+                    const unsigned long long early = (unsigned long long)rb / 8 + 1;
+                    best = 1;
+                    unsigned long long bs = s[1];
+                    if (bs > early) {
+                        if (s[2] < bs) { bs = s[2]; best = 2; }
+                        if (bs > early && s[4] < bs) best = 4;
+                    }
+                } else {      // adaptive_filter, src/png/filter.rs:302-393
+                    const unsigned long long early = (unsigned long long)rb / 4 + 1;
+                    best = 0;
+                    unsigned long long bs = s[0];
+                    bool done = bs <= early;
+                    for (int f = 1; f < 5 && !done; ++f)
+                        if (s[f] < bs) {
+                            bs = s[f]; best = f;
+                            if (f < 4 && (bs == 0 || bs <= early)) done = true;
+                        }
+                }
+                s_filter = best;
+            }
+            __syncthreads();
+            filter = s_filter;
+        }
+
+        // ---- emit the winner ----
+        auto filtered = [&](uint32_t k) -> uint32_t {
+            if (k >= nw) return 0u;
+            uint32_t x, a, b, c, mask;
+            operands(k, x, a, b, c, mask);
+            uint32_t pred;
+            switch (filter) {
+            case 0: pred = 0; break;
+            case 1: pred = a; break;
+            case 2: pred = b; break;
+            case 3: pred = __vhaddu4(a, b); break;
+            default: pred = paeth_pred4(a, b, c); break;
+            }
+            return __vsub4(x, pred) & mask;
+        };
+        uint8_t *orow = P.out + (size_t)img * P.out_stride + (size_t)r * n_out;
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(orow + 1) & 3);
+        uint32_t *gal = reinterpret_cast<uint32_t *>(orow + 1 - sh);   // aligned; word j = bytes 4j-sh..
+        uint32_t S1 = 0, S2 = 0, S3 = 0;
+        uint32_t carry = j_lo ? filtered(j_lo - 1) : 0u;   // f[j-1] for this warp's first word
+        for (uint32_t j0 = j_lo; j0 < j_hi; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const uint32_t f = filtered(j);
+            if (j < nw) {
+                const uint32_t s4 = __dp4a(f, 0x01010101u, 0u);
+                S1 += s4; S2 += j * s4; S3 += __dp4a(f, 0x03020100u, 0u);
+            }
+            uint32_t fm1 = __shfl_up_sync(0xffffffffu, f, 1);
+            if (lane == 0) fm1 = carry;
+            carry = __shfl_sync(0xffffffffu, f, 31);
+            if (j < j_hi) {
+                const uint32_t word = __funnelshift_l(fm1, f, 8 * sh);
+                const int i0 = 4 * (int)j - (int)sh;            // first filtered-byte index in this word
+                if (i0 >= 0 && i0 + 3 < (int)rb) {
+                    gal[j] = word;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (i0 + t >= 0 && i0 + t < (int)rb) reinterpret_cast<uint8_t *>(gal + j)[t] = (uint8_t)(word >> (8 * t));
+                }
+            }
+        }
+        if (tid == 0) orow[0] = (uint8_t)filter;
+        if (P.acc) {
+            // distance-to-end weights: byte i of the row's filtered data weighs Wr - i, the type byte Wr + 1
+            const unsigned long long Wr = (Ntot - (unsigned long long)r * n_out - 1) % ADLER_MOD;
+            accA += S1;
+            accBpos += Wr * S1;
+            accBneg += 4ull * S2 + S3;
+            if (tid == 0) { accA += (unsigned)filter; accBpos += ((Wr + 1) % ADLER_MOD) * (unsigned)filter; }
+        }
+        __syncthreads();   // all reads of this row's buffers are done before the ring advances
+    }
+
+    if (P.acc) {
+        unsigned long long v[3] = {accA, accBpos, accBneg};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            v[q] = warp_sum(v[q]);
+            if (lane == 0) red64[q][warp] = v[q];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long A = 0, Bp = 0, Bn = 0;
+            for (int w = 0; w < PNG_THREADS / 32; ++w) { A += red64[0][w]; Bp += red64[1][w]; Bn += red64[2][w]; }
+            const unsigned long long Bm = (Bp % ADLER_MOD + ADLER_MOD - Bn % ADLER_MOD) % ADLER_MOD;
+            atomicAdd(&P.acc[2 * img], A % ADLER_MOD);
+            atomicAdd(&P.acc[2 * img + 1], Bm);
+            __threadfence();
+            const uint32_t done = atomicAdd(&P.counter[img], 1u) + 1;
+            if (done == P.nbands) {
+                __threadfence();
+                const unsigned long long At = atomicAdd(&P.acc[2 * img], 0ull);
+                const unsigned long long Bt = atomicAdd(&P.acc[2 * img + 1], 0ull);
+                const uint32_t s1 = (uint32_t)((1 + At) % ADLER_MOD);
+                const uint32_t s2 = (uint32_t)((Ntot % ADLER_MOD + Bt) % ADLER_MOD);
+                P.adler_out[img] = (s2 << 16) | s1;
+            }
+        }
+    }
+}
+
 // Standalone Adler-32 (K5): grid-stride over 16-byte vectors; per-thread A and end-weighted B.
 __global__ void __launch_bounds__(256)
 k_adler32(const uint8_t *__restrict__ data, size_t len, unsigned long long *acc,
@@ -360,26 +703,28 @@ int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_strid
                       uint32_t bpp, uint32_t strategy, uint8_t *d_out, size_t out_stride,
                       uint32_t *d_adler)
 {
-    if (strategy == PIXO_B200_FILTER_BIGRAMS)
-        return set_error(ctx, PIXO_B200_ERR_UNSUPPORTED,
-                         "FilterStrategy::Bigrams is not on the GPU path yet");
     if (row_bytes >= (1ull << 32) - 16)
         return set_error(ctx, PIXO_B200_ERR_IMAGE_TOO_LARGE, "row_bytes too large");
     // apply_filters_with_row_bytes pre-rules, src/png/filter.rs:72-86
     const size_t area = (size_t)width * (size_t)height;
     uint32_t strat = strategy;
-    if (area <= 4096 && (strat == PIXO_B200_FILTER_ADAPTIVE || strat == PIXO_B200_FILTER_ADAPTIVE_FAST))
+    if (area <= 4096 && (strat == PIXO_B200_FILTER_ADAPTIVE || strat == PIXO_B200_FILTER_ADAPTIVE_FAST ||
+                         strat == PIXO_B200_FILTER_BIGRAMS))
         strat = PIXO_B200_FILTER_SUB;
     // default-feature build: AdaptiveFast takes the sequential (sticky) loop when height <= 32
     const bool sticky = strat == PIXO_B200_FILTER_ADAPTIVE_FAST && height <= 32;
 
+    const size_t band_pitch = 16 + ((row_bytes + 15) & ~(size_t)15) + 16;
+    const size_t band_smem = 3 * band_pitch;
+    const bool use_band = !sticky && strat != PIXO_B200_FILTER_BIGRAMS && band_smem <= 200 * 1024 &&
+                          row_bytes < (1u << 18);
     const size_t segcap = row_bytes + 15 < (size_t)SEG_BYTES ? ((row_bytes + 15) & ~(size_t)15) : (size_t)SEG_BYTES;
-    const size_t smem = 2 * (16 + segcap) + segcap + 32;
+    const size_t smem = 2 * (16 + segcap) + segcap + 32 + 8192;   // + bigram "seen" bitmap
     static bool attr_set_dev[64];  // function attributes are per device
     bool &attr_set = attr_set_dev[ctx->device & 63];
     if (!attr_set) {
         PIXO_CUDA(ctx, cudaFuncSetAttribute(k_png_filter, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(2 * (16 + SEG_BYTES) + SEG_BYTES + 32)));
+                                            (int)(2 * (16 + SEG_BYTES) + SEG_BYTES + 32 + 8192)));
         attr_set = true;
     }
     // misc scratch: per image {accA, accB} u64, counter u32, decided u8
@@ -390,6 +735,31 @@ int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_strid
     auto *decided = reinterpret_cast<uint8_t *>(counter + n_images);
     PIXO_CUDA(ctx, cudaMemsetAsync(ctx->d_misc.ptr, 0, (size_t)n_images * per + 64, ctx->stream));
 
+    if (use_band) {
+        static bool band_attr[64];
+        if (!band_attr[ctx->device & 63]) {
+            PIXO_CUDA(ctx, cudaFuncSetAttribute(k_png_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            band_attr[ctx->device & 63] = true;
+        }
+        const uint32_t nbands = (height + BAND_ROWS - 1) / BAND_ROWS;
+        for (uint32_t i0 = 0; i0 < n_images; i0 += 65535) {
+            const uint32_t nb = n_images - i0 < 65535 ? n_images - i0 : 65535;
+            BandParams B;
+            B.data = d_data + (size_t)i0 * in_stride; B.in_stride = in_stride;
+            B.out = d_out + (size_t)i0 * out_stride; B.out_stride = out_stride;
+            B.height = height; B.row_bytes = (uint32_t)row_bytes; B.bpp = bpp; B.strategy = strat;
+            B.acc = d_adler ? acc + 2 * (size_t)i0 : nullptr;
+            B.counter = counter + i0;
+            B.adler_out = d_adler ? d_adler + i0 : nullptr;
+            B.nbands = nbands;
+            B.async16 = (row_bytes % 16 == 0 && in_stride % 16 == 0 &&
+                         (reinterpret_cast<uintptr_t>(d_data) & 15) == 0) ? 1u : 0u;
+            k_png_band<<<dim3(nbands, nb), PNG_THREADS, band_smem, ctx->stream>>>(B);
+            ctx->launches++;
+            PIXO_CUDA(ctx, cudaGetLastError());
+        }
+        return 0;
+    }
     for (uint32_t i0 = 0; i0 < n_images; i0 += 65535) {
         const uint32_t nb = n_images - i0 < 65535 ? n_images - i0 : 65535;
         PngParams P;

@@ -109,7 +109,7 @@ def test_gpu_reproduces_pixo_jpeg_bytes(gpu_ctx, c):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("c", [c for c in MANIFEST["png"] if c["preset"] != 2], ids=lambda c: c["file"])
+@pytest.mark.parametrize("c", MANIFEST["png"], ids=lambda c: c["file"])
 def test_gpu_reproduces_pixo_png_filter_stream(gpu_ctx, c):
     """pixo-wasm always runs the sequential loop; the product implements the default-feature
     (rayon) semantics, which coincide for Adaptive everywhere and for AdaptiveFast when

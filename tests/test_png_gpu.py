@@ -11,7 +11,8 @@ from pixo_b200.png import FilterStrategy, PngOptions
 pytestmark = pytest.mark.gpu
 
 STRATS = [FilterStrategy.NoFilter, FilterStrategy.Sub, FilterStrategy.Up, FilterStrategy.Average,
-          FilterStrategy.Paeth, FilterStrategy.MinSum, FilterStrategy.Adaptive, FilterStrategy.AdaptiveFast]
+          FilterStrategy.Paeth, FilterStrategy.MinSum, FilterStrategy.Adaptive, FilterStrategy.AdaptiveFast,
+          FilterStrategy.Bigrams]
 
 
 def _smooth(w, h, bpp, seed):
@@ -69,7 +70,7 @@ def test_long_rows_span_segments(po, gpu_ctx):
     # rows longer than the 32 KiB staging segment
     w, h, bpp = 30000, 40, 4
     img = _smooth(w, h, bpp, 5)
-    for st in (FilterStrategy.Adaptive, FilterStrategy.Paeth, FilterStrategy.AdaptiveFast):
+    for st in (FilterStrategy.Adaptive, FilterStrategy.Paeth, FilterStrategy.AdaptiveFast, FilterStrategy.Bigrams):
         got, ad = png.apply_filters(img, w, h, bpp, PngOptions(w, h, ColorType.Rgba, st), with_adler=True, ctx=gpu_ctx)
         ref = po.apply_filters(img, w, h, bpp, int(st))
         assert np.array_equal(got, ref)
@@ -89,12 +90,8 @@ def test_adler32_known_answers_and_sizes(po, gpu_ctx):
     assert png.adler32(d, ctx=gpu_ctx) == zlib.adler32(d.tobytes())
 
 
-def test_unsupported_and_invalid(gpu_ctx):
-    E = pixo_b200._lib
+def test_invalid_arguments(gpu_ctx):
     img = np.zeros(70 * 70 * 4, np.uint8)
-    with pytest.raises(pixo_b200.PixoError) as e:
-        png.apply_filters(img, 70, 70, 4, PngOptions(70, 70, ColorType.Rgba, FilterStrategy.Bigrams), ctx=gpu_ctx)
-    assert e.value.code == E.ERR_UNSUPPORTED
     with pytest.raises(pixo_b200.PixoError):
         png.apply_filters(img, 70, 70, 5, PngOptions(70, 70), ctx=gpu_ctx)
     with pytest.raises(pixo_b200.PixoError):
