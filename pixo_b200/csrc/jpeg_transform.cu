@@ -277,30 +277,27 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *_
             C[2 * i + 1][j] = pk(a1, b1);
         }
     }
-    // column pass on column pairs; post-scale packed (it feeds only multiplies / fma addends)
+    // column pass on column pairs, quantising each pair of columns as soon as it is transformed.
+    // The eight table entries of a column pair are fetched BEFORE its butterflies so the
+    // shared-memory latency is covered by the transform (ncu: the quantiser was where the warp
+    // waited on short-scoreboard stalls).
+    uint32_t W[32];
+    const f2 half2 = K2(0.5f), magic2 = K2(12582912.0f);  // 1.5 * 2^23
+    uint32_t kSign, kOne;  // in registers so copysign(1.0, q) is ONE lop3: (q & sign) | one
+    asm("mov.b32 %0, 0x80000000;" : "=r"(kSign));
+    asm("mov.b32 %0, 0x3F800000;" : "=r"(kOne));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+        float4 T[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) T[r] = *reinterpret_cast<const float4 *>(&tab[r * 4 + j]);
         const f2 in[8] = {C[0][j], C[1][j], C[2][j], C[3][j], C[4][j], C[5][j], C[6][j], C[7][j]};
         f2 o[8];
         aan_1d_x2_core(in, o, zero2);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) C[r][j] = mul2(o[r], K2(SK[r]));
-    }
-
-    uint32_t W[32];
-    const f2 half2 = K2(0.5f), magic2 = K2(12582912.0f);  // 1.5 * 2^23
-    uint32_t kSign, kOne, kHalf;  // in registers so copysign(c, q) is ONE lop3: (q & sign) | c
-    asm("mov.b32 %0, 0x80000000;" : "=r"(kSign));
-    asm("mov.b32 %0, 0x3F800000;" : "=r"(kOne));
-    asm("mov.b32 %0, 0x3F000000;" : "=r"(kHalf));
-    (void)kOne; (void)kHalf;
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 t = *reinterpret_cast<const float4 *>(&tab[r * 4 + j]);
-            const f2 nd = pk(t.x, t.y), rc = pk(t.z, t.w);
-            const f2 x = C[r][j];
+        for (int r = 0; r < 8; ++r) {
+            const f2 nd = pk(T[r].x, T[r].y), rc = pk(T[r].z, T[r].w);
+            const f2 x = mul2(o[r], K2(SK[r]));   // post-scale: feeds only a multiply / fma addend
             const f2 q0 = mul2(x, rc);
             const f2 e = fma2(q0, nd, x);
             const f2 q = fma2(e, rc, q0);
@@ -309,14 +306,15 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *_
             uint32_t sl, sh;
             asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(sl) : "r"(ql), "r"(kSign), "r"(kOne));
             asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(sh) : "r"(qh), "r"(kSign), "r"(kOne));
-            const f2 s = pk(__uint_as_float(sl), __uint_as_float(sh));
+            const f2 sg = pk(__uint_as_float(sl), __uint_as_float(sh));
             const f2 w = add2_rz(q, half2);
-            const f2 tt = fma2_rm(w, s, magic2);
+            const f2 tt = fma2_rm(w, sg, magic2);
             uint32_t tl, th, neg;
             upk_u(tt, tl, th);
             asm("prmt.b32 %0, %1, %2, %3;" : "=r"(neg) : "r"(ql), "r"(qh), "r"(0xFFBBu));
             W[r * 4 + j] = __byte_perm(tl, th, 0x5410) ^ neg;
         }
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         uint32_t w[4];
@@ -883,6 +881,65 @@ k_jpeg_hist(const int16_t *__restrict__ ycoef, size_t y_stride, const int16_t *_
         if (sh[i]) atomicAdd(&hist[(size_t)img * kHistWords + i], (unsigned long long)sh[i]);
 }
 
+#ifdef PIXO_UBENCH
+// Development microbenchmark (variant builds only): the block pipeline in isolation.
+//   mode 0: DCT + quant + stage (dct_quant_store_x2) on register data, no colour work
+//   mode 1: Y fill (ycc_row8 from a shared-memory tile) only
+//   mode 2: both, back to back (one Y job without global traffic)
+template <int MODE>
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_ubench(int iters, float zlo, float zhi, uint32_t *sink)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    K1Smem &S = *reinterpret_cast<K1Smem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    K1WarpSmem &WS = S.w[warp];
+    for (int i = tid; i < (int)sizeof(K1Smem) / 4; i += K1_THREADS) reinterpret_cast<uint32_t *>(smem_raw)[i] = i * 2654435761u;
+    __syncthreads();
+    for (int w = tid; w < 64; w += K1_THREADS) {
+        QPair e; e.nd_lo = -(float)(3 + w % 7); e.nd_hi = -(float)(2 + w % 5); e.r_lo = -1.0f / e.nd_lo; e.r_hi = -1.0f / e.nd_hi;
+        (w >= 32 ? S.q.chr : S.q.lum)[w & 31] = e;
+    }
+    __syncthreads();
+    const f2 zero2 = pk(zlo, zhi);
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        f2 R[4][8];
+        const int by = lane >> 4, l16 = lane & 15, par = l16 >> 3, k8 = l16 & 7;
+        const int mj = (k8 >> 1) * 2 + par, bx = k8 & 1;
+        if (MODE != 0) {
+            const uint8_t *base = WS.tile[it & 1] + (by * 8) * K1_HB + (mj * 2 + bx) * 24;
+            uint4 *cdst = reinterpret_cast<uint4 *>(WS.csum) + mj * 16;
+#pragma unroll
+            for (int rp = 0; rp < 4; ++rp) {
+                float y0[8], y1[8];
+                uint32_t h0[4], h1[4];
+                { const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2) * K1_HB); const uint2 a = p[0], b = p[1], c = p[2];
+                  const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y}; ycc_row8(wds, y0, h0); }
+                { const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2 + 1) * K1_HB); const uint2 a = p[0], b = p[1], c = p[2];
+                  const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y}; ycc_row8(wds, y1, h1); }
+#pragma unroll
+                for (int x = 0; x < 8; ++x) R[rp][x] = sub2(pk(y0[x], y1[x]), K2(8388736.0f));
+                cdst[((by * 4 + rp) * 2 + bx) ^ (mj & 7)] = make_uint4(h0[0] + h1[0], h0[1] + h1[1], h0[2] + h1[2], h0[3] + h1[3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int x = 0; x < 8; ++x) R[i][x] = pk((float)((it + i * 8 + x + lane) & 255) - 128.0f, (float)((it * 3 + x + lane) & 255) - 128.0f);
+        }
+        if (MODE != 1) {
+            const int slot = mj * 4 + by * 2 + bx;
+            dct_quant_store_x2<false>(R, S.q.lum, reinterpret_cast<uint4 *>(WS.csum) + 256 * 0 + slot * 8, ((slot >> 3) << 1) | (slot & 1), zero2);
+            __syncwarp();
+            acc += WS.csum[(lane * 33 + it) & 1023];
+        } else {
+            uint32_t lo, hi; upk_u(R[it & 3][lane & 7], lo, hi); acc += lo ^ hi;
+        }
+    }
+    if (acc == 0x12345678u) sink[tid] = acc;
+}
+#endif
+
 void make_quant_tab(const float *lum_q, const float *chr_q, QuantTab *qt)
 {
     for (int i = 0; i < 64; ++i) {
@@ -970,6 +1027,29 @@ int launch_k1(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint32
 }
 
 }  // namespace
+
+#ifdef PIXO_UBENCH
+extern "C" int pixo_b200_ubench(pixo_b200_ctx *ctx, int mode, int iters, float *ms_out)
+{
+    const size_t smem = sizeof(K1Smem);
+    uint32_t *sink = nullptr;
+    cudaMalloc(&sink, 4096);
+    auto run = [&](int it) {
+        const int grid = ctx->sm_count * K1_MIN_BLOCKS;
+        if (mode == 0) { cudaFuncSetAttribute(k_ubench<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_ubench<0><<<grid, K1_THREADS, smem, ctx->stream>>>(it, 0.f, 0.f, sink); }
+        if (mode == 1) { cudaFuncSetAttribute(k_ubench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_ubench<1><<<grid, K1_THREADS, smem, ctx->stream>>>(it, 0.f, 0.f, sink); }
+        if (mode == 2) { cudaFuncSetAttribute(k_ubench<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_ubench<2><<<grid, K1_THREADS, smem, ctx->stream>>>(it, 0.f, 0.f, sink); }
+    };
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    run(iters);
+    cudaStreamSynchronize(ctx->stream);
+    cudaEventRecord(e0, ctx->stream); run(iters); cudaEventRecord(e1, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaEventElapsedTime(ms_out, e0, e1);
+    cudaFree(sink);
+    return (int)cudaGetLastError();
+}
+#endif
 
 int launch_jpeg_transform(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pixel_stride,
                           uint32_t n_images, uint32_t w, uint32_t h, uint32_t color_type,
