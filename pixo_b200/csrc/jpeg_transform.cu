@@ -105,6 +105,44 @@ __device__ __forceinline__ void load_tile(uint8_t *__restrict__ smem,
     const int lin = (int)inside_px * BPP;
     const uint8_t *img_lo = img;
     const uint8_t *img_hi = img + pitch * h;
+    // Unaligned pitch, tile fully inside the image in x: every row is TB bytes at an arbitrary
+    // byte phase.  Fetch eight rows' worth of aligned word pairs back to back (one exposed
+    // memory latency per batch instead of one per row), then funnel-shift into place.
+    if (x0 + TILE_PX <= w) {
+        constexpr int NW = TB / 4;                 // words per tile row
+        constexpr int WPL = (NW + NT - 1) / NT;    // words per thread per row
+        const uint32_t y_last = min(y0 + (uint32_t)ROWS - 1, h - 1);
+        const uint8_t *first = col0 + min(y0, h - 1) * pitch - 3;
+        const uint8_t *last = col0 + y_last * pitch + TB + 8;
+        if (first >= img_lo && last <= img_hi) {
+#pragma unroll
+            for (int rb = 0; rb < ROWS; rb += 8) {
+                uint32_t lo[8][WPL], hi[8][WPL];
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const uint32_t sy = min(y0 + (uint32_t)(rb + rr), h - 1);
+                    const uint8_t *src = col0 + sy * pitch;
+                    const uint32_t *a0 = reinterpret_cast<const uint32_t *>(src - (reinterpret_cast<uintptr_t>(src) & 3));
+#pragma unroll
+                    for (int i = 0; i < WPL; ++i) {
+                        const int k = tid + i * NT;
+                        if (k < NW) { lo[rr][i] = __ldg(a0 + k); hi[rr][i] = __ldg(a0 + k + 1); }
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const uint32_t sy = min(y0 + (uint32_t)(rb + rr), h - 1);
+                    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(col0 + sy * pitch) & 3) * 8;
+#pragma unroll
+                    for (int i = 0; i < WPL; ++i) {
+                        const int k = tid + i * NT;
+                        if (k < NW) reinterpret_cast<uint32_t *>(smem + (rb + rr) * TB)[k] = __funnelshift_r(lo[rr][i], hi[rr][i], sh);
+                    }
+                }
+            }
+            return;
+        }
+    }
     for (int r = 0; r < ROWS; ++r) {
         const uint32_t sy = min(y0 + (uint32_t)r, h - 1);
         const uint8_t *src = col0 + sy * pitch;
@@ -488,8 +526,10 @@ __device__ __forceinline__ void ycc_row8(const uint32_t (&w)[6], float (&yv)[8],
 }
 
 // Warp-cooperative version of load_tile: ROWS x (TILE_PX*3) bytes with edge replication.
+// (kept out of line: it only runs for edge units and unaligned images, and inlining it twice
+// into the persistent loop costs instruction-cache room the TMA path needs)
 template <int ROWS, int TILE_PX>
-__device__ __forceinline__ void warp_load_tile_rgb(uint8_t *__restrict__ smem,
+__device__ __noinline__ void warp_load_tile_rgb(uint8_t *__restrict__ smem,
                                                    const uint8_t *__restrict__ img, uint32_t w,
                                                    uint32_t h, uint32_t x0, uint32_t y0, int lane)
 {
