@@ -388,14 +388,15 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
     const size_t cbb = align_up(g.nc * 64 * sizeof(int16_t), 256);
     const size_t coef_each = yb + 2 * cbb;
     const size_t in_stride = align_up(len_each, 256);
-    const uint64_t raw_cap = align_up(len_each / 2 + 65536, 4096);
-    const uint64_t scan_cap = align_up(raw_cap + raw_cap / 8, 256);
+    // device-side scan capacity per frame; a JPEG that needs more (pathological noise at very high
+    // quality) is finished by the host coder from the same coefficients
+    const uint64_t scan_cap = align_up((len_each / 2 + 65536) / 8 * 9, 256);
     const bool gpu_entropy = restart_interval == 0;
 
     uint32_t G = n_images < 16 ? n_images : 16;
     const size_t budget = (size_t)3 << 30;
     auto group_bytes = [&](uint32_t k) {
-        return 2 * (size_t)k * in_stride + (size_t)k * coef_each + entropy_scratch_bytes(k, g, raw_cap) +
+        return 2 * (size_t)k * in_stride + (size_t)k * coef_each + entropy_scratch_bytes(k, g) +
                2 * (size_t)k * scan_cap;
     };
     while (G > 1 && group_bytes(G) > budget) --G;
@@ -404,7 +405,7 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
     PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
     PIXO_TRY(ensure_dev(ctx, ctx->d_in, 2 * (size_t)G * in_stride));
     PIXO_TRY(ensure_dev(ctx, ctx->d_coef, (size_t)G * coef_each));
-    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(G, g, raw_cap)));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(G, g)));
     PIXO_TRY(ensure_dev(ctx, ctx->d_out, 2 * (size_t)G * scan_cap));
     PIXO_TRY(ensure_dev(ctx, ctx->d_misc, (size_t)G * kHistWords * sizeof(uint64_t) + 256));
     PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, (size_t)G * (kHistWords * sizeof(uint64_t) + 32) + 256));
@@ -451,13 +452,14 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
         const size_t cstride = coef_each / 2;
         PIXO_TRY(launch_jpeg_transform(ctx, d_in + (size_t)slot * G * in_stride, in_stride, cnt, g.width,
                                        g.height, g.color_type, g.subsampling, lum, chr, dy, cstride,
-                                       g.has_chroma ? dcb : nullptr, g.has_chroma ? dcr : nullptr, cstride, 0));
+                                       g.has_chroma ? dcb : nullptr, g.has_chroma ? dcr : nullptr, cstride,
+                                       PIXO_B200_COEF_ZIGZAG));  // the order every consumer below reads
         PIXO_CUDA(ctx, cudaEventRecord(ev_used[slot], ctx->stream));
         std::vector<HuffTables> tables(optimize ? cnt : 1);
         if (optimize) {
             auto *d_hist = reinterpret_cast<uint64_t *>(ctx->d_misc.ptr);
             PIXO_TRY(launch_jpeg_histogram(ctx, dy, cstride, dcb, dcr, cstride, cnt, g.ny, g.nc, g.y_per_mcu,
-                                           restart_interval, false, d_hist));
+                                           restart_interval, true, d_hist));
             PIXO_CUDA(ctx, cudaMemcpyAsync(h_hist, d_hist, (size_t)cnt * kHistWords * sizeof(uint64_t),
                                            cudaMemcpyDeviceToHost, ctx->stream));
             PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -474,16 +476,16 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
             uint32_t *d_ovf = nullptr;
             auto *ent = reinterpret_cast<uint8_t *>(ctx->d_ent.ptr);
             if (!optimize) {
-                PIXO_TRY(launch_jpeg_entropy(ctx, dy, cstride, dcb, dcr, cstride, cnt, g, tables[0], ent, raw_cap,
+                PIXO_TRY(launch_jpeg_entropy(ctx, dy, cstride, dcb, dcr, cstride, cnt, g, tables[0], ent,
                                              scan, scan_cap, &d_len, &d_ovf));
                 PIXO_CUDA(ctx, cudaMemcpyAsync(h_len, d_len, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
                 PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf, d_ovf, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
             } else {
-                const size_t per = entropy_scratch_bytes(1, g, raw_cap);
+                const size_t per = entropy_scratch_bytes(1, g);
                 for (uint32_t k = 0; k < cnt; ++k) {  // per-image tables: one pass per image
                     PIXO_TRY(launch_jpeg_entropy(ctx, dy + (size_t)k * cstride, cstride, dcb + (size_t)k * cstride,
                                                  dcr + (size_t)k * cstride, cstride, 1, g, tables[k],
-                                                 ent + (size_t)k * per, raw_cap, scan + (size_t)k * scan_cap,
+                                                 ent + (size_t)k * per, scan + (size_t)k * scan_cap,
                                                  scan_cap, &d_len, &d_ovf));
                     PIXO_CUDA(ctx, cudaMemcpyAsync(h_len + k, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
                     PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf + k, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -529,7 +531,7 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
                 const size_t body = entropy_encode_scan(reinterpret_cast<int16_t *>(hc),
                                                         reinterpret_cast<int16_t *>(hc + yb),
                                                         reinterpret_cast<int16_t *>(hc + yb + cbb), g,
-                                                        tables[optimize ? k : 0], restart_interval, false,
+                                                        tables[optimize ? k : 0], restart_interval, true,
                                                         o + hdr[k], out_cap_each - hdr[k] - 2, ctx->host_threads);
                 if (body == (size_t)-1)
                     return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small", out_cap_each);
@@ -597,28 +599,25 @@ int pixo_b200_jpeg_encode_dev(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_
     const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
     float lum[64], chr[64];
     quant_tables((int)quality, nullptr, nullptr, lum, chr);
-    const size_t bpp = color_type == PIXO_B200_GRAY ? 1 : 3;
-    const size_t len_each = (size_t)width * height * bpp;
     const size_t yb = align_up(g.ny * 64 * sizeof(int16_t), 256);
     const size_t cbb = align_up(g.nc * 64 * sizeof(int16_t), 256);
     const size_t coef_each = yb + 2 * cbb;
-    const uint64_t raw_cap = align_up(len_each / 2 + 65536, 4096);
     PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
     PIXO_TRY(ensure_dev(ctx, ctx->d_coef, (size_t)n_images * coef_each));
-    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(n_images, g, raw_cap)));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(n_images, g)));
     auto *d_coef = reinterpret_cast<uint8_t *>(ctx->d_coef.ptr);
     auto *dy = reinterpret_cast<int16_t *>(d_coef);
     auto *dcb = reinterpret_cast<int16_t *>(d_coef + yb);
     auto *dcr = reinterpret_cast<int16_t *>(d_coef + yb + cbb);
     PIXO_TRY(launch_jpeg_transform(ctx, d_pixels, pixel_stride, n_images, width, height, color_type, subsampling,
                                    lum, chr, dy, coef_each / 2, g.has_chroma ? dcb : nullptr,
-                                   g.has_chroma ? dcr : nullptr, coef_each / 2, 0));
+                                   g.has_chroma ? dcr : nullptr, coef_each / 2, PIXO_B200_COEF_ZIGZAG));
     HuffTables t;
     huff_standard(t);
     uint64_t *len_src = nullptr;
     uint32_t *ovf_src = nullptr;
     PIXO_TRY(launch_jpeg_entropy(ctx, dy, coef_each / 2, dcb, dcr, coef_each / 2, n_images, g, t,
-                                 reinterpret_cast<uint8_t *>(ctx->d_ent.ptr), raw_cap, d_scan, scan_cap_each,
+                                 reinterpret_cast<uint8_t *>(ctx->d_ent.ptr), d_scan, scan_cap_each,
                                  &len_src, &ovf_src));
     PIXO_CUDA(ctx, cudaMemcpyAsync(d_scan_len, len_src, (size_t)n_images * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     PIXO_CUDA(ctx, cudaMemcpyAsync(d_overflow, ovf_src, (size_t)n_images * 4, cudaMemcpyDeviceToDevice, ctx->stream));

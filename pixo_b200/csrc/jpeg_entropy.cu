@@ -7,474 +7,510 @@
 //   BitWriterMsb            src/bits.rs:195-290 (MSB-first, 0xFF -> 0xFF00 stuffing, 1-padding)
 //   encode_scan             src/jpeg/mod.rs:1408-1563 (scan order: Y..,Cb,Cr per MCU)
 //
-// The DC predictor of a block is the previous block of the same component in the coefficient
-// array, so every block's code length is independent:
-//   1. k_huff_len    one thread per block: bits of its code                        (u32/block)
-//   2. k_scan_local / k_scan_top   exclusive scan of those lengths in scan order   (bit offsets)
-//   3. k_huff_emit   one thread per block: writes its bits at its offset into a zeroed raw
-//                    buffer (big-endian words; the two boundary words by atomicOr)
-//   4. k_ff_count / k_ff_top / k_stuff   pad the last byte with 1s, count 0xFF bytes per chunk,
-//                    scan, and copy with 0x00 inserted after every 0xFF
-// Restart intervals stay on the host coder (jpeg_host.cpp): they need per-interval padding.
+// One kernel, one pass over the coefficients (k_huff).  The DC predictor of a block is the
+// previous block of the same component in the coefficient array, so every block's code is
+// independent of the others; only its POSITION in the stream is not.  A CTA takes a chunk of 128
+// consecutive blocks (scan order) of one image:
+//   1. each thread codes its block once into a private shared-memory slot (coefficients arrive
+//      in zig-zag order; a 64-bit non-zero mask drives the symbol loop, so the loop runs once per
+//      non-zero coefficient and there is a single, small copy of the symbol code);
+//   2. the block bit lengths are scanned in the CTA; the chunk total enters a decoupled
+//      look-back chain (one status word per chunk: bit count + the chunk's last 7 bits), which
+//      yields the chunk's bit offset in the image's stream and the partial byte it inherits;
+//   3. the slots are funnel-shifted into a shared window aligned to the stream's 32-bit words;
+//   4. the chunk owns every byte whose last bit it wrote.  It counts its 0xFF bytes, a second
+//      look-back chain turns those counts into the number of stuffed zeros before the chunk, and
+//      the window is copied out with the 0x00s inserted, 16 bytes per store.
+// Nothing but the final scan bytes is written to global memory.  Restart intervals stay on the
+// host coder (jpeg_host.cpp): they need per-interval padding.
 #include "common.cuh"
 #include "jpeg_host.hpp"
 
 namespace pixo {
 namespace {
 
-__host__ __device__ constexpr int zz2(int i)
-{
-    constexpr int t[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
-                           12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
-                           35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
-                           58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-    return t[i];
-}
-
+// Huffman tables as the symbol loop wants them: one word per symbol with the amplitude field
+// already opened up,  entry = ((code << cat) << 5) | (len + cat),  cat = symbol & 15 (AC) or the
+// DC category.  16 + 11 + 5 = 32 bits at most.
 struct HuffDev {
-    uint16_t dc_code[2][12];
-    uint16_t ac_code[2][256];
-    uint8_t dc_len[2][12];
-    uint8_t ac_len[2][256];
+    uint32_t dc[2][12];
+    uint32_t ac[2][256];
 };
 
 struct EntParams {
-    const int16_t *y, *cb, *cr;
+    const int16_t *y, *cb, *cr;    // zig-zag ordered blocks
     size_t y_stride, c_stride;     // int16 elements between images
     uint32_t bpm;                  // blocks per MCU in scan order: 6 (4:2:0), 3 (4:4:4), 1 (gray)
     uint32_t y_per_mcu;            // 4, 1, 1
     uint64_t nblocks;              // per image, scan order
-    uint32_t *blk_bits;            // [n][nblocks_padded] lengths, then in-chunk exclusive offsets
-    uint64_t blk_pitch;
-    uint32_t *chunk_tot;           // [n][nchunks]
-    uint64_t *chunk_base;          // [n][nchunks]
-    uint32_t nchunks;
-    uint64_t *total_bits;          // [n]
-    uint8_t *raw;                  // [n][raw_cap]
-    uint64_t raw_cap;
-    uint32_t *ff_tot;              // [n][ff_chunks]
-    uint64_t *ff_base;             // [n][ff_chunks]
-    uint32_t ff_chunks;
+    uint32_t nchunks;              // per image
+    unsigned long long *st_bits;   // [n][nchunks] look-back chain 1: stream bits
+    unsigned long long *st_ff;     // [n][nchunks] look-back chain 2: 0xFF bytes
+    uint32_t *ticket;              // chunk dispenser (launch order == dependency order)
     uint8_t *out;                  // [n][out_cap]
     uint64_t out_cap;
     uint64_t *out_len;             // [n] final byte count
-    uint32_t *overflow;            // [n] set when a capacity was exceeded
+    uint32_t *overflow;            // [n] set when out_cap was exceeded (or the chain faulted)
 };
 
-constexpr int SCAN_CH = 2048;      // blocks per scan chunk (256 threads x 8)
-constexpr int FF_CH = 4096;        // raw bytes per stuffing chunk (128 threads x 32)
+constexpr int EB = 128;            // blocks per chunk == threads per CTA
+constexpr int SLOT_W = 24;         // words of a block's code kept in shared memory (768 bits)
+constexpr int MAX_W = 54;          // worst case: 27 + 63 * 26 = 1665 bits
+constexpr int WIN_W = 1024;        // stream words assembled per round
+constexpr int WIN_B = WIN_W * 4;
+constexpr int SBUF_B = 2 * WIN_B + 32;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
-__device__ __forceinline__ int cat16(int v)
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_PFX = 2ull << 62;
+constexpr unsigned long long ST_VAL = (1ull << 55) - 1;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p)
 {
-    const int a = v < 0 ? -v : v;
-    return 32 - __clz(a);
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long pack_status(unsigned long long flag, uint32_t tail,
+                                                          unsigned long long value)
+{
+    return flag | ((unsigned long long)(tail & 0x7F) << 55) | (value & ST_VAL);
 }
 
-// locate block `s` (scan order) : pointer to its 64 coefficients, its table (0 lum / 1 chroma)
-// and the DC of its predecessor in the same component (0 at the start of the scan)
-__device__ __forceinline__ const int16_t *locate(const EntParams &P, uint32_t img, uint64_t s,
-                                                 int &tbl, int &prev_dc)
+// Exclusive prefix over chunks [0, chunk) of one image (whole warp; decoupled look-back, 32
+// predecessors per step).  tail_in = the 7-bit tail published by chunk-1.
+__device__ unsigned long long look_back(const unsigned long long *st, int chunk, int lane,
+                                        uint32_t *tail_in, bool *fault)
 {
-    const uint64_t m = s / P.bpm;
-    const uint32_t k = (uint32_t)(s - m * P.bpm);
-    const int16_t *arr;
-    uint64_t idx;
-    if (k < P.y_per_mcu) { arr = P.y + (size_t)img * P.y_stride; idx = m * P.y_per_mcu + k; tbl = 0; }
-    else if (k == P.y_per_mcu) { arr = P.cb + (size_t)img * P.c_stride; idx = m; tbl = 1; }
-    else { arr = P.cr + (size_t)img * P.c_stride; idx = m; tbl = 1; }
-    prev_dc = idx ? arr[(idx - 1) * 64] : 0;
-    return arr + idx * 64;
-}
-
-struct BitSink {
-    uint32_t *words;
-    uint64_t widx, wcap;
-    uint64_t acc;
-    int filled;
-    bool shared_first;
-    __device__ __forceinline__ void put(uint32_t code, int len)
-    {
-        if (len == 0) return;
-        acc |= (uint64_t)code << (64 - filled - len);
-        filled += len;
-        if (filled >= 32) {
-            const uint32_t w = __byte_perm((uint32_t)(acc >> 32), 0, 0x0123);  // big-endian bytes
-            if (widx < wcap) {
-                if (shared_first) atomicOr(&words[widx], w); else words[widx] = w;
-            }
-            shared_first = false;
-            ++widx;
-            acc <<= 32;
-            filled -= 32;
+    unsigned long long excl = 0;
+    uint32_t tl = 0, spins = 0;
+    bool first = true;
+    int base = chunk - 1;
+    while (base >= 0) {
+        const int idx = base - lane;
+        const unsigned long long v = idx >= 0 ? ld_status(st + idx) : ST_PFX;
+        const uint32_t flag = (uint32_t)(v >> 62);
+        if (__any_sync(0xffffffffu, flag == 0)) {
+            if (++spins > SPIN_LIMIT) { *fault = true; break; }
+            __nanosleep(40);
+            continue;
         }
-    }
-    __device__ __forceinline__ void finish()
-    {
-        if (filled > 0 && widx < wcap)
-            atomicOr(&words[widx], __byte_perm((uint32_t)(acc >> 32), 0, 0x0123));
-    }
-};
-
-// Symbolise one block held in 32 packed words (natural order) — encode_block's walk.
-template <bool EMIT>
-__device__ __forceinline__ uint32_t walk_block(const uint32_t (&w)[32], int prev_dc, int tbl,
-                                               const HuffDev &T, BitSink *sink)
-{
-    uint32_t bits = 0;
-    {
-        const int dc = (int)(int16_t)(w[0] & 0xFFFF);
-        const int diff = (int)(int16_t)(dc - prev_dc);
-        const int cat = cat16(diff);
-        const int len = T.dc_len[tbl][cat];
-        bits += len + cat;
-        if (EMIT) {
-            const uint32_t amp = (uint32_t)(diff < 0 ? diff - 1 : diff) & ((1u << cat) - 1u);
-            sink->put(((uint32_t)T.dc_code[tbl][cat] << cat) | amp, len + cat);
-        }
-    }
-    int run = 0;
+        const uint32_t pm = __ballot_sync(0xffffffffu, flag == 2);
+        const int stop = pm ? __ffs(pm) - 1 : 31;
+        unsigned long long val = lane <= stop ? (v & ST_VAL) : 0ull;
 #pragma unroll
-    for (int i = 1; i < 64; ++i) {
-        const int nat = zz2(i);
-        const uint32_t word = w[nat >> 1];
-        const int c = (int)(int16_t)((nat & 1) ? (word >> 16) : (word & 0xFFFF));
-        if (c == 0) {
-            ++run;
-        } else {
-            while (run >= 16) {
-                bits += T.ac_len[tbl][0xF0];
-                if (EMIT) sink->put(T.ac_code[tbl][0xF0], T.ac_len[tbl][0xF0]);
-                run -= 16;
-            }
-            const int cat = cat16(c);
-            const int rs = (run << 4) | cat;
-            const int len = T.ac_len[tbl][rs];
-            bits += len + cat;
-            if (EMIT) {
-                const uint32_t amp = (uint32_t)(c < 0 ? c - 1 : c) & ((1u << cat) - 1u);
-                sink->put(((uint32_t)T.ac_code[tbl][rs] << cat) | amp, len + cat);
-            }
-            run = 0;
-        }
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        excl += val;
+        if (first) { tl = __shfl_sync(0xffffffffu, (uint32_t)(v >> 55) & 0x7Fu, 0); first = false; }
+        if (pm) break;
+        base -= 32;
     }
-    if (run > 0) {
-        bits += T.ac_len[tbl][0];
-        if (EMIT) sink->put(T.ac_code[tbl][0], T.ac_len[tbl][0]);
-    }
-    return bits;
+    *tail_in = tl;
+    return excl;
 }
 
-__device__ __forceinline__ void load_block(const int16_t *p, uint32_t (&w)[32])
+// bits 0..15 -> even positions, bits 16..31 -> odd positions (outer perfect shuffle)
+__device__ __forceinline__ uint32_t interleave16(uint32_t x)
 {
-    const uint4 *src = reinterpret_cast<const uint4 *>(p);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint4 t = __ldg(src + k);
-        w[k * 4] = t.x; w[k * 4 + 1] = t.y; w[k * 4 + 2] = t.z; w[k * 4 + 3] = t.w;
-    }
+    uint32_t t;
+    t = (x ^ (x >> 8)) & 0x0000FF00u; x ^= t ^ (t << 8);
+    t = (x ^ (x >> 4)) & 0x00F000F0u; x ^= t ^ (t << 4);
+    t = (x ^ (x >> 2)) & 0x0C0C0C0Cu; x ^= t ^ (t << 2);
+    t = (x ^ (x >> 1)) & 0x22222222u; x ^= t ^ (t << 1);
+    return x;
 }
 
-__global__ void __launch_bounds__(128)
-k_huff_len(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
+// 0x80 in every byte of w that equals 0xFF
+__device__ __forceinline__ uint32_t ff_bytes(uint32_t w)
 {
-    __shared__ HuffDev T;
-    for (int i = threadIdx.x; i < (int)(sizeof(HuffDev) / 4); i += blockDim.x)
-        reinterpret_cast<uint32_t *>(&T)[i] = reinterpret_cast<const uint32_t *>(&Tp)[i];
-    __syncthreads();
-    const uint32_t img = blockIdx.y;
-    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.nblocks) return;
-    int tbl, prev;
-    const int16_t *blk = locate(P, img, s, tbl, prev);
-    uint32_t w[32];
-    load_block(blk, w);
-    P.blk_bits[(size_t)img * P.blk_pitch + s] = walk_block<false>(w, prev, tbl, T, nullptr);
+    return ((w & 0x7F7F7F7Fu) + 0x01010101u) & w & 0x80808080u;
 }
 
-// exclusive scan of SCAN_CH values per CTA (in place) + chunk totals
-__global__ void __launch_bounds__(256) k_scan_local(const __grid_constant__ EntParams P)
+// CTA-wide exclusive scan of one u32 per thread (EB threads); *total = sum.  Two barriers.
+__device__ __forceinline__ uint32_t cta_scan(uint32_t x, uint32_t *s_ws, uint32_t *total)
 {
-    __shared__ uint32_t wsum[8];
-    const uint32_t img = blockIdx.y, chunk = blockIdx.x;
-    uint32_t *v = P.blk_bits + (size_t)img * P.blk_pitch + (size_t)chunk * SCAN_CH;
-    const uint64_t base = (uint64_t)chunk * SCAN_CH;
     const int t = threadIdx.x;
-    uint32_t x[8], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint64_t i = base + (uint64_t)t * 8 + k;
-        x[k] = i < P.nblocks ? v[t * 8 + k] : 0u;
-        sum += x[k];
-    }
-    uint32_t inc = sum;
+    uint32_t inc = x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
         if ((t & 31) >= o) inc += n;
     }
-    if ((t & 31) == 31) wsum[t >> 5] = inc;
     __syncthreads();
-    uint32_t wbase = 0;
-    for (int k = 0; k < (t >> 5); ++k) wbase += wsum[k];
-    uint32_t run = wbase + inc - sum;
+    if ((t & 31) == 31) s_ws[t >> 5] = inc;
+    __syncthreads();
+    uint32_t wb = 0, tot = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint64_t i = base + (uint64_t)t * 8 + k;
-        if (i < P.nblocks) v[t * 8 + k] = run;
-        run += x[k];
+    for (int k = 0; k < EB / 32; ++k) {
+        const uint32_t v = s_ws[k];
+        if (k < (t >> 5)) wb += v;
+        tot += v;
     }
-    if (t == 255) P.chunk_tot[(size_t)img * P.nchunks + chunk] = wbase + inc;
+    *total = tot;
+    return wb + inc - x;
 }
 
-// one CTA per image: exclusive scan of a u32 array of `n` totals into u64 bases + grand total
-__device__ void scan_top(const uint32_t *tot, uint64_t *base, uint32_t n, unsigned long long *grand)
-{
-    __shared__ unsigned long long wsum[8];
-    __shared__ unsigned long long carry;
-    const int t = threadIdx.x;
-    if (t == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t i0 = 0; i0 < n; i0 += 256) {
-        const uint32_t i = i0 + t;
-        const unsigned long long x = i < n ? tot[i] : 0ull;
-        unsigned long long inc = x;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long m = __shfl_up_sync(0xffffffffu, inc, o);
-            if ((t & 31) >= o) inc += m;
-        }
-        if ((t & 31) == 31) wsum[t >> 5] = inc;
-        __syncthreads();
-        unsigned long long wb = 0;
-        for (int k = 0; k < (t >> 5); ++k) wb += wsum[k];
-        if (i < n) base[i] = carry + wb + inc - x;
-        __syncthreads();
-        if (t == 255) carry += wb + inc;
-        __syncthreads();
-    }
-    if (t == 0) *grand = carry;
-}
-
-__global__ void __launch_bounds__(256) k_scan_top(const __grid_constant__ EntParams P)
-{
-    const uint32_t img = blockIdx.x;
-    scan_top(P.chunk_tot + (size_t)img * P.nchunks, P.chunk_base + (size_t)img * P.nchunks, P.nchunks,
-             reinterpret_cast<unsigned long long *>(P.total_bits + img));
-    __syncthreads();
-    if (threadIdx.x == 0 && (P.total_bits[img] + 7) / 8 > P.raw_cap) P.overflow[img] = 1;
-}
-
-__global__ void __launch_bounds__(128)
-k_huff_emit(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
+__global__ void __launch_bounds__(EB, 7)
+k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
 {
     __shared__ HuffDev T;
-    for (int i = threadIdx.x; i < (int)(sizeof(HuffDev) / 4); i += blockDim.x)
+    __shared__ uint32_t slot[SLOT_W * EB];
+    __shared__ __align__(16) uint32_t work[32 * EB];  // coefficient stage, then window + stuffed bytes
+    __shared__ uint32_t s_ws[EB / 32];
+    __shared__ uint32_t s_tl[EB];
+    __shared__ unsigned long long s_pfx, s_ffx;
+    __shared__ uint32_t s_id, s_tailin, s_fault;
+    static_assert(WIN_B + SBUF_B <= (int)sizeof(work), "window + stuffed bytes must fit the stage");
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) { s_id = atomicAdd(P.ticket, 1u); s_fault = 0; }
+    for (int i = t; i < (int)(sizeof(HuffDev) / 4); i += EB)
         reinterpret_cast<uint32_t *>(&T)[i] = reinterpret_cast<const uint32_t *>(&Tp)[i];
     __syncthreads();
-    const uint32_t img = blockIdx.y;
-    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.nblocks) return;
-    int tbl, prev;
-    const int16_t *blk = locate(P, img, s, tbl, prev);
-    uint32_t w[32];
-    load_block(blk, w);
-    const uint64_t off = P.chunk_base[(size_t)img * P.nchunks + s / SCAN_CH] +
-                         P.blk_bits[(size_t)img * P.blk_pitch + s];
-    BitSink sink;
-    sink.words = reinterpret_cast<uint32_t *>(P.raw + (size_t)img * P.raw_cap);
-    sink.wcap = P.raw_cap / 4;
-    sink.widx = off >> 5;
-    sink.filled = (int)(off & 31);
-    sink.acc = 0;
-    sink.shared_first = sink.filled != 0;
-    walk_block<true>(w, prev, tbl, T, &sink);
-    sink.finish();
-}
+    const uint32_t img = s_id / P.nchunks, chunk = s_id % P.nchunks;
+    const bool last_chunk = chunk == P.nchunks - 1;
+    const uint64_t s = (uint64_t)chunk * EB + t;
+    const bool valid = s < P.nblocks;
+    const int nv = (int)min((uint64_t)EB, P.nblocks - (uint64_t)chunk * EB);
 
-// ---- 0xFF stuffing ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_ff_count(const __grid_constant__ EntParams P)
-{
-    __shared__ uint32_t wsum[4];
-    const uint32_t img = blockIdx.y, chunk = blockIdx.x;
-    const uint64_t bits = P.total_bits[img];
-    const uint64_t nbytes = (bits + 7) / 8;
-    uint8_t *raw = P.raw + (size_t)img * P.raw_cap;
-    const uint64_t b0 = (uint64_t)chunk * FF_CH + (uint64_t)threadIdx.x * 32;
-    uint32_t cnt = 0;
-    if (b0 < nbytes && nbytes <= P.raw_cap) {
-        // BitWriterMsb::flush: pad the final partial byte with 1s (src/bits.rs:261-272)
-        if (nbytes - 1 >= b0 && nbytes - 1 < b0 + 32 && (bits & 7))
-            raw[nbytes - 1] |= (uint8_t)((1u << (8 - (bits & 7))) - 1u);
-        const uint4 a = *reinterpret_cast<const uint4 *>(raw + b0);
-        const uint4 b = *reinterpret_cast<const uint4 *>(raw + b0 + 16);
-        const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    // ---- 1. code the block into its slot ---------------------------------------------------
+    uint32_t spill[MAX_W - SLOT_W];  // words beyond SLOT_W (pathological blocks): local memory
+    uint32_t L = 0, tail7 = 0;
+    int nwt = 0;
+    if (valid) {
+        const uint64_t m = s / P.bpm;
+        const uint32_t k = (uint32_t)(s - m * P.bpm);
+        const int16_t *arr;
+        uint64_t idx;
+        int tbl;
+        if (k < P.y_per_mcu) { arr = P.y + (size_t)img * P.y_stride; idx = m * P.y_per_mcu + k; tbl = 0; }
+        else if (k == P.y_per_mcu) { arr = P.cb + (size_t)img * P.c_stride; idx = m; tbl = 1; }
+        else { arr = P.cr + (size_t)img * P.c_stride; idx = m; tbl = 1; }
+        const int prev_dc = idx ? arr[(idx - 1) * 64] : 0;
+        const uint4 *src = reinterpret_cast<const uint4 *>(arr + idx * 64);
+        uint32_t e0 = 0, e1 = 0;
+        int dc;
+        {
+            uint32_t w[32];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint64_t wb = b0 + 4 * k;
+            for (int q = 0; q < 8; ++q) {
+                const uint4 v = __ldg(src + q);
+                w[q * 4] = v.x; w[q * 4 + 1] = v.y; w[q * 4 + 2] = v.z; w[q * 4 + 3] = v.w;
+            }
+            dc = (int)(int16_t)(w[0] & 0xFFFF);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (wb + j < nbytes && ((wv[k] >> (8 * j)) & 0xFF) == 0xFF) ++cnt;
+            for (int j = 0; j < 32; ++j) work[j * EB + t] = w[j];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                e0 |= __vminu2(w[j], 0x00010001u) << j;
+                e1 |= __vminu2(w[16 + j], 0x00010001u) << j;
+            }
+        }
+        const uint32_t M0 = interleave16(e0), M1 = interleave16(e1);  // bit i = coefficient i != 0
+
+        uint32_t acc = 0, lastw = 0;
+        int filled = 0, nw = 0;
+        auto put = [&](uint32_t v, int n) {
+            const int total = filled + n;  // 1..58
+            const unsigned long long V = (unsigned long long)v << (64 - total);
+            const uint32_t hi = acc | (uint32_t)(V >> 32), lo = (uint32_t)V;
+            if (total >= 32) {
+                if (nw < SLOT_W) slot[nw * EB + t] = hi; else spill[nw - SLOT_W] = hi;
+                lastw = hi; ++nw; acc = lo; filled = total - 32;
+            } else {
+                acc = hi; filled = total;
+            }
+        };
+        {   // DC difference
+            const int diff = (int)(int16_t)(dc - prev_dc);
+            const uint32_t a = (uint32_t)abs(diff);
+            const int cat = 32 - __clz(a);
+            const uint32_t e = T.dc[tbl][cat];
+            const uint32_t amp = a ^ (((1u << cat) - 1u) & (uint32_t)(diff >> 31));
+            put((e >> 5) | amp, (int)(e & 31));
+        }
+        const uint32_t *tab = T.ac[tbl];
+        const uint32_t zrl = tab[0xF0], eob = tab[0x00];
+        const char *stage = reinterpret_cast<const char *>(work) + t * 4;
+        int prevpos = 0;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            uint32_t mb = __brev(half ? M1 : (M0 & ~1u));
+            const int basepos = half * 32;
+            while (mb) {
+                const int p = __clz(mb);
+                mb &= ~(0x80000000u >> p);
+                const int pos = basepos + p;
+                int run = pos - prevpos - 1;
+                prevpos = pos;
+                const int c = *reinterpret_cast<const int16_t *>(stage + (pos >> 1) * (EB * 4) + (pos & 1) * 2);
+                while (run >= 16) { put(zrl >> 5, (int)(zrl & 31)); run -= 16; }
+                const uint32_t a = (uint32_t)abs(c);
+                const int cat = 32 - __clz(a);
+                const uint32_t e = tab[(run << 4) | cat];
+                const uint32_t amp = a ^ (((1u << cat) - 1u) & (uint32_t)(c >> 31));
+                put((e >> 5) | amp, (int)(e & 31));
+            }
+        }
+        if (prevpos != 63) put(eob >> 5, (int)(eob & 31));
+        L = (uint32_t)nw * 32u + (uint32_t)filled;
+        tail7 = __funnelshift_rc(acc, lastw, 32 - filled) & 0x7Fu;
+        nwt = nw;
+        if (filled) {
+            if (nw < SLOT_W) slot[nw * EB + t] = acc; else spill[nw - SLOT_W] = acc;
+            nwt = nw + 1;
         }
     }
-    uint32_t v = cnt;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) P.ff_tot[(size_t)img * P.ff_chunks + chunk] = wsum[0] + wsum[1] + wsum[2] + wsum[3];
-}
+    s_tl[t] = (L << 7) | tail7;
 
-__global__ void __launch_bounds__(256) k_ff_top(const __grid_constant__ EntParams P)
-{
-    const uint32_t img = blockIdx.x;
-    __shared__ unsigned long long total_ff;
-    scan_top(P.ff_tot + (size_t)img * P.ff_chunks, P.ff_base + (size_t)img * P.ff_chunks, P.ff_chunks, &total_ff);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint64_t nbytes = (P.total_bits[img] + 7) / 8;
-        const uint64_t len = nbytes + total_ff;
-        P.out_len[img] = len;
-        if (len > P.out_cap) P.overflow[img] = 1;
-    }
-}
-
-__global__ void __launch_bounds__(128) k_stuff(const __grid_constant__ EntParams P)
-{
-    __shared__ uint32_t wsum[4];
-    const uint32_t img = blockIdx.y, chunk = blockIdx.x;
-    const uint64_t nbytes = (P.total_bits[img] + 7) / 8;
-    if (P.overflow[img]) return;
-    const uint8_t *raw = P.raw + (size_t)img * P.raw_cap;
-    uint8_t *out = P.out + (size_t)img * P.out_cap;
-    const int t = threadIdx.x;
-    const uint64_t b0 = (uint64_t)chunk * FF_CH + (uint64_t)t * 32;
-    uint32_t wv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t cnt = 0;
-    int nvalid = 0;
-    if (b0 < nbytes) {
-        nvalid = (int)min((uint64_t)32, nbytes - b0);
-        const uint4 a = *reinterpret_cast<const uint4 *>(raw + b0);
-        const uint4 b = *reinterpret_cast<const uint4 *>(raw + b0 + 16);
-        wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w; wv[4] = b.x; wv[5] = b.y; wv[6] = b.z; wv[7] = b.w;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (4 * k + j < nvalid && ((wv[k] >> (8 * j)) & 0xFF) == 0xFF) ++cnt;
-    }
-    uint32_t inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-        if ((t & 31) >= o) inc += n;
-    }
-    if ((t & 31) == 31) wsum[t >> 5] = inc;
-    __syncthreads();
-    uint32_t wb = 0;
-    for (int k = 0; k < (t >> 5); ++k) wb += wsum[k];
-    uint64_t o = b0 + P.ff_base[(size_t)img * P.ff_chunks + chunk] + wb + inc - cnt;
-    if (cnt == 0 && nvalid == 32 && (o & 3) == 0) {
-        uint32_t *o32 = reinterpret_cast<uint32_t *>(out + o);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o32[k] = wv[k];
-        return;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (4 * k + j < nvalid) {
-                const uint8_t byte = (uint8_t)(wv[k] >> (8 * j));
-                out[o++] = byte;
-                if (byte == 0xFF) out[o++] = 0x00;
+    // ---- 2. offsets: CTA scan + look-back chain 1 --------------------------------------------
+    uint32_t Lc;
+    const uint32_t o_t = cta_scan(L, s_ws, &Lc);  // barriers inside also publish s_tl / the stage is dead
+    unsigned long long *st1 = P.st_bits + (size_t)img * P.nchunks;
+    unsigned long long *st2 = P.st_ff + (size_t)img * P.nchunks;
+    if (warp == 0) {
+        uint32_t ctail = 0;
+        if (lane == 0) {  // the chunk's last 7 bits (a block has >= 2 bits: at most 4 steps)
+            int got = 0;
+            for (int k = nv - 1; k >= 0 && got < 7; --k) {
+                const uint32_t x = s_tl[k];
+                const int take = min((int)(x >> 7), 7 - got);
+                ctail |= (x & ((1u << take) - 1u)) << got;
+                got += take;
             }
+            st_status(st1 + chunk, pack_status(chunk == 0 ? ST_PFX : ST_AGG, ctail, Lc));
+        }
+        uint32_t tin = 0;
+        unsigned long long excl = 0;
+        if (chunk) {
+            bool fault = false;
+            excl = look_back(st1, (int)chunk, lane, &tin, &fault);
+            if (lane == 0) {
+                st_status(st1 + chunk, pack_status(ST_PFX, ctail, excl + Lc));
+                if (fault) s_fault = 1;
+            }
+        }
+        if (lane == 0) { s_pfx = excl; s_tailin = tin; }
+    }
+    __syncthreads();
+    const unsigned long long Pc = s_pfx;
+    const uint32_t q0 = (uint32_t)Pc & 31u;           // bit offset of the chunk inside window word 0
+    const uint32_t endbit = q0 + Lc;                  // window bit index one past the chunk
+    const uint32_t padc = last_chunk ? ((8u - (endbit & 7u)) & 7u) : 0u;   // 1-padding (bits.rs:261-272)
+    const uint32_t ob0 = q0 >> 3;                     // owned window bytes [ob0, ob1)
+    const uint32_t ob1 = (endbit >> 3) + (padc ? 1u : 0u);
+    const int nrounds = max(1, (int)((ob1 + WIN_B - 1) / WIN_B));
+    uint32_t *obuf = work;
+    uint8_t *sbuf = reinterpret_cast<uint8_t *>(work) + WIN_B;
+    uint8_t *outp = P.out + (size_t)img * P.out_cap;
+
+    // per-thread constants of the funnel-shifted copy
+    const uint32_t D = q0 + o_t;
+    const int d0 = (int)(D >> 5), sh = (int)(D & 31u);
+    const int nd = L ? (int)((sh + L + 31u) >> 5) : 0;   // destination words
+
+    uint32_t Ftot = 0, Fdone = 0;
+    unsigned long long gbase = 0;
+    const int iters = nrounds == 1 ? 1 : 2 * nrounds;  // >1 round: a counting sweep, then the emitting sweep
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        const int r = it < nrounds ? it : it - nrounds;
+        const bool emit = nrounds == 1 || it >= nrounds;
+        // ---- 3. assemble window r ----------------------------------------------------------
+        for (int i = t; i < WIN_W / 4; i += EB) reinterpret_cast<uint4 *>(obuf)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        {
+            const int wlo = r * WIN_W;
+            const int kb = max(0, wlo - d0), ke = min(nd, wlo + WIN_W - d0);
+            uint32_t prev = 0;
+            if (kb > 0 && kb <= nwt) prev = (kb - 1) < SLOT_W ? slot[(kb - 1) * EB + t] : spill[kb - 1 - SLOT_W];
+            for (int k = kb; k < ke; ++k) {
+                uint32_t cur = 0;
+                if (k < nwt) cur = k < SLOT_W ? slot[k * EB + t] : spill[k - SLOT_W];
+                const uint32_t v = __funnelshift_r(cur, prev, sh);
+                uint32_t *dst = obuf + (d0 + k - wlo);
+                if (k == 0 || k == nd - 1) atomicOr(dst, v); else *dst = v;
+                prev = cur;
+            }
+            if (t == 0) {
+                const uint32_t q = q0 & 7u;  // inherited bits of the straddling first byte
+                if (r == 0 && q) atomicOr(&obuf[0], (s_tailin & ((1u << q) - 1u)) << (32u - q0));
+                const int pw = (int)(endbit >> 5) - wlo;
+                if (padc && pw >= 0 && pw < WIN_W)
+                    atomicOr(&obuf[pw], ((1u << padc) - 1u) << (32u - (endbit & 31u) - padc));
+            }
+        }
+        __syncthreads();
+        // ---- 4a. count the 0xFF bytes this thread's 32 window bytes hold -------------------------
+        const int wb0 = r * WIN_B;
+        const int a = max((int)ob0 - wb0, 0), b = min((int)ob1 - wb0, WIN_B);
+        const int lo = max(32 * t, a), hi = min(32 * t + 32, b);
+        uint32_t cnt = 0;
+        if (hi > lo) {
+            for (int j = (lo >> 2) - 8 * t; j < 8 && 32 * t + 4 * j < hi; ++j) {
+                const int wbyte = 32 * t + 4 * j;
+                uint32_t f = ff_bytes(obuf[8 * t + j]);
+                if (wbyte < lo || wbyte + 4 > hi) {
+                    uint32_t keep = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (wbyte + i >= lo && wbyte + i < hi) keep |= 0x80000000u >> (8 * i);
+                    f &= keep;
+                }
+                cnt += __popc(f);
+            }
+        }
+        uint32_t Fr;
+        const uint32_t ffb = cta_scan(cnt, s_ws, &Fr);
+        if (!emit) { Ftot += Fr; }
+        if (it == (nrounds == 1 ? 0 : nrounds - 1)) {
+            // ---- look-back chain 2: stuffed zeros before this chunk ------------------------------
+            if (nrounds == 1) Ftot = Fr;
+            if (warp == 0) {
+                if (lane == 0) st_status(st2 + chunk, pack_status(chunk == 0 ? ST_PFX : ST_AGG, 0, Ftot));
+                unsigned long long fx = 0;
+                if (chunk) {
+                    bool fault = false;
+                    uint32_t dummy;
+                    fx = look_back(st2, (int)chunk, lane, &dummy, &fault);
+                    if (lane == 0) {
+                        st_status(st2 + chunk, pack_status(ST_PFX, 0, fx + Ftot));
+                        if (fault) s_fault = 1;
+                    }
+                }
+                if (lane == 0) s_ffx = fx;
+            }
+            __syncthreads();
+            gbase = (Pc >> 3) + s_ffx;  // output index of the first owned byte
+        }
+        if (!emit) continue;
+        // ---- 4b. stuffed bytes of this window -> sbuf -> global ------------------------------------
+        const unsigned long long G = gbase + (r == 0 ? 0u : (uint32_t)(wb0 - (int)ob0)) + Fdone;
+        const uint32_t nr = (uint32_t)max(b - a, 0) + Fr;
+        const uint32_t shb = (uint32_t)((reinterpret_cast<uintptr_t>(outp) + G) & 15u);
+        if (hi > lo) {
+            uint32_t dst = shb + (uint32_t)(lo - a) + ffb;
+            for (int j = (lo >> 2) - 8 * t; j < 8 && 32 * t + 4 * j < hi; ++j) {
+                const int wbyte = 32 * t + 4 * j;
+                const uint32_t w = obuf[8 * t + j];
+                if (wbyte >= lo && wbyte + 4 <= hi && ff_bytes(w) == 0 && (dst & 3u) == 0) {
+                    *reinterpret_cast<uint32_t *>(sbuf + dst) = __byte_perm(w, 0, 0x0123);
+                    dst += 4;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (wbyte + i >= lo && wbyte + i < hi) {
+                            const uint32_t byte = (w >> (24 - 8 * i)) & 0xFFu;
+                            sbuf[dst++] = (uint8_t)byte;
+                            if (byte == 0xFFu) sbuf[dst++] = 0;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (G + nr <= P.out_cap) {
+            uint8_t *gdst = outp + G - shb;  // 16-byte aligned
+            const uint32_t end = shb + nr;
+            for (uint32_t c16 = t; c16 * 16 < end; c16 += EB) {
+                const uint32_t lo_b = c16 * 16, hi_b = lo_b + 16;
+                if (lo_b >= shb && hi_b <= end) {
+                    *reinterpret_cast<uint4 *>(gdst + lo_b) = *reinterpret_cast<const uint4 *>(sbuf + lo_b);
+                } else {
+                    for (uint32_t i = max(lo_b, shb); i < min(hi_b, end); ++i) gdst[i] = sbuf[i];
+                }
+            }
+        } else if (t == 0) {
+            P.overflow[img] = 1;
+        }
+        Fdone += Fr;
+        // (the next round's first barrier separates these sbuf reads from its sbuf writes)
+    }
+    if (t == 0) {
+        if (s_fault) P.overflow[img] = 1;
+        if (last_chunk) {
+            const unsigned long long total = ((Pc >> 5) << 2) + ob1 + s_ffx + Ftot;
+            P.out_len[img] = total;
+            if (total > P.out_cap) P.overflow[img] = 1;
+        }
+    }
 }
 
 }  // namespace
 
 // Device scratch layout for n images (all sizes in bytes, 256-aligned)
 struct EntropyPlan {
-    size_t blk_pitch, nchunks, ff_chunks;
-    size_t off_blk, off_ctot, off_cbase, off_tbits, off_fftot, off_ffbase, off_outlen, off_ovf, off_raw, total;
+    size_t nchunks;
+    size_t off_st1, off_st2, off_ticket, off_ovf, zero_bytes, off_outlen, total;
 };
 
 static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
 
-static EntropyPlan plan_entropy(uint32_t n, uint64_t nblocks, uint64_t raw_cap)
+static EntropyPlan plan_entropy(uint32_t n, uint64_t nblocks)
 {
     EntropyPlan p;
-    p.nchunks = (size_t)((nblocks + SCAN_CH - 1) / SCAN_CH);
-    p.blk_pitch = p.nchunks * SCAN_CH;
-    p.ff_chunks = (size_t)((raw_cap + FF_CH - 1) / FF_CH);
+    p.nchunks = (size_t)((nblocks + EB - 1) / EB);
     size_t o = 0;
-    p.off_blk = o; o += a256((size_t)n * p.blk_pitch * 4);
-    p.off_ctot = o; o += a256((size_t)n * p.nchunks * 4);
-    p.off_cbase = o; o += a256((size_t)n * p.nchunks * 8);
-    p.off_tbits = o; o += a256((size_t)n * 8);
-    p.off_fftot = o; o += a256((size_t)n * p.ff_chunks * 4);
-    p.off_ffbase = o; o += a256((size_t)n * p.ff_chunks * 8);
-    p.off_outlen = o; o += a256((size_t)n * 8);
+    p.off_st1 = o; o += a256((size_t)n * p.nchunks * 8);
+    p.off_st2 = o; o += a256((size_t)n * p.nchunks * 8);
+    p.off_ticket = o; o += 256;
     p.off_ovf = o; o += a256((size_t)n * 4);
-    p.off_raw = o; o += (size_t)n * raw_cap;
+    p.zero_bytes = o;  // everything up to here is cleared per launch
+    p.off_outlen = o; o += a256((size_t)n * 8);
     p.total = o;
     return p;
 }
 
-size_t entropy_scratch_bytes(uint32_t n, const FrameGeometry &g, uint64_t raw_cap)
+size_t entropy_scratch_bytes(uint32_t n, const FrameGeometry &g)
 {
-    return plan_entropy(n, g.ny + 2 * g.nc, raw_cap).total;
+    return plan_entropy(n, g.ny + 2 * g.nc).total;
 }
 
-// Enqueue the whole entropy stage for n images on ctx->stream.  d_scratch: entropy_scratch_bytes.
-// d_out: n * out_cap bytes of scan data; *d_out_len / *d_overflow point into the scratch.
+// Enqueue the entropy stage for n images (zig-zag ordered coefficients) on ctx->stream.
+// d_scratch: entropy_scratch_bytes.  d_out: n * out_cap bytes of scan data; *d_out_len /
+// *d_overflow point into the scratch.
 int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride, const int16_t *d_cb,
                         const int16_t *d_cr, size_t c_stride, uint32_t n, const FrameGeometry &g,
-                        const HuffTables &t, uint8_t *d_scratch, uint64_t raw_cap, uint8_t *d_out,
-                        uint64_t out_cap, uint64_t **d_out_len, uint32_t **d_overflow)
+                        const HuffTables &t, uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap,
+                        uint64_t **d_out_len, uint32_t **d_overflow)
 {
     const uint64_t nblocks = g.ny + 2 * g.nc;
-    const EntropyPlan pl = plan_entropy(n, nblocks, raw_cap);
+    const EntropyPlan pl = plan_entropy(n, nblocks);
+    if ((uint64_t)n * pl.nchunks > 0x7FFFFFFFull)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "entropy stage: too many blocks per call");
     EntParams P;
     P.y = d_y; P.cb = d_cb; P.cr = d_cr; P.y_stride = y_stride; P.c_stride = c_stride;
     P.bpm = g.y_per_mcu + (g.has_chroma ? 2 : 0);
     P.y_per_mcu = g.y_per_mcu;
     P.nblocks = nblocks;
-    P.blk_bits = reinterpret_cast<uint32_t *>(d_scratch + pl.off_blk);
-    P.blk_pitch = pl.blk_pitch;
-    P.chunk_tot = reinterpret_cast<uint32_t *>(d_scratch + pl.off_ctot);
-    P.chunk_base = reinterpret_cast<uint64_t *>(d_scratch + pl.off_cbase);
     P.nchunks = (uint32_t)pl.nchunks;
-    P.total_bits = reinterpret_cast<uint64_t *>(d_scratch + pl.off_tbits);
-    P.raw = d_scratch + pl.off_raw;
-    P.raw_cap = raw_cap;
-    P.ff_tot = reinterpret_cast<uint32_t *>(d_scratch + pl.off_fftot);
-    P.ff_base = reinterpret_cast<uint64_t *>(d_scratch + pl.off_ffbase);
-    P.ff_chunks = (uint32_t)pl.ff_chunks;
-    P.out = d_out; P.out_cap = out_cap;
-    P.out_len = reinterpret_cast<uint64_t *>(d_scratch + pl.off_outlen);
+    P.st_bits = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_st1);
+    P.st_ff = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_st2);
+    P.ticket = reinterpret_cast<uint32_t *>(d_scratch + pl.off_ticket);
     P.overflow = reinterpret_cast<uint32_t *>(d_scratch + pl.off_ovf);
+    P.out_len = reinterpret_cast<uint64_t *>(d_scratch + pl.off_outlen);
+    P.out = d_out; P.out_cap = out_cap;
     *d_out_len = P.out_len;
     *d_overflow = P.overflow;
 
     HuffDev T;
     memset(&T, 0, sizeof T);
     for (int k = 0; k < 2; ++k) {
-        for (int i = 0; i < 12; ++i) { T.dc_code[k][i] = t.code[k][i]; T.dc_len[k][i] = t.len[k][i]; }
-        for (int i = 0; i < 256; ++i) { T.ac_code[k][i] = t.code[2 + k][i]; T.ac_len[k][i] = t.len[2 + k][i]; }
+        for (int cat = 0; cat < 12; ++cat)
+            if (t.len[k][cat]) T.dc[k][cat] = (((uint32_t)t.code[k][cat] << cat) << 5) | (uint32_t)(t.len[k][cat] + cat);
+        for (int rs = 0; rs < 256; ++rs) {
+            const int cat = rs & 15;
+            if (t.len[2 + k][rs] && cat <= 10)
+                T.ac[k][rs] = (((uint32_t)t.code[2 + k][rs] << cat) << 5) | (uint32_t)(t.len[2 + k][rs] + cat);
+        }
     }
-    if (n > 65535) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "entropy stage: too many images per call");
     cudaStream_t st = ctx->stream;
-    PIXO_CUDA(ctx, cudaMemsetAsync(P.overflow, 0, (size_t)n * 4, st));
-    PIXO_CUDA(ctx, cudaMemsetAsync(P.raw, 0, (size_t)n * raw_cap, st));
-    const unsigned gb = (unsigned)((nblocks + 127) / 128);
-    k_huff_len<<<dim3(gb, n), 128, 0, st>>>(P, T);
-    k_scan_local<<<dim3(P.nchunks, n), 256, 0, st>>>(P);
-    k_scan_top<<<n, 256, 0, st>>>(P);
-    k_huff_emit<<<dim3(gb, n), 128, 0, st>>>(P, T);
-    k_ff_count<<<dim3(P.ff_chunks, n), 128, 0, st>>>(P);
-    k_ff_top<<<n, 256, 0, st>>>(P);
-    k_stuff<<<dim3(P.ff_chunks, n), 128, 0, st>>>(P);
-    ctx->launches += 7;
+    PIXO_CUDA(ctx, cudaMemsetAsync(d_scratch, 0, pl.zero_bytes, st));
+    k_huff<<<(unsigned)((size_t)n * pl.nchunks), EB, 0, st>>>(P, T);
+    ctx->launches += 1;
     PIXO_CUDA(ctx, cudaGetLastError());
     return 0;
 }

@@ -161,3 +161,54 @@ def test_determinism_and_decoder_acceptance(po, gpu_ctx):
     sizes = [len(jpeg.encode(img, JpegOptions(w, h, ColorType.Rgb, q, Subsampling.S420), ctx=gpu_ctx))
              for q in (10, 50, 90)]
     assert sizes[0] < sizes[1] < sizes[2]   # tests/jpeg_conformance.rs:84
+
+
+def _scan_bytes(jpg: bytes) -> bytes:
+    """entropy-coded segment of a baseline file: after the SOS header, before EOI"""
+    i = 2
+    while True:
+        assert jpg[i] == 0xFF
+        ln = int.from_bytes(jpg[i + 2:i + 4], "big")
+        if jpg[i + 1] == 0xDA:
+            return jpg[i + 2 + ln:-2]
+        i += 2 + ln
+
+
+@pytest.mark.parametrize("w,h,ct,ss", [(640, 480, 2, 1), (333, 222, 2, 0), (257, 129, 0, 0)])
+def test_entropy_stage_dense_blocks(po, gpu_ctx, w, h, ct, ss):
+    """Noise at q 97-100: blocks longer than the 768-bit shared-memory slot (local-memory
+    words), chunks that need several assembly windows, frequent 0xFF bytes; optimised tables."""
+    img = po.gen_noise(w, h, 3 if ct == 2 else 1, 7)
+    for q in (100, 97):
+        for opt in (False, True):
+            o = JpegOptions(w, h, ColorType(ct), q, Subsampling(ss), None, opt)
+            assert jpeg.encode(img, o, ctx=gpu_ctx) == po.jpeg_encode(img, w, h, ct, q, ss, 0, opt), (q, opt)
+
+
+def test_encode_dev_device_resident(po, gpu_ctx):
+    """pixo_b200_jpeg_encode_dev: device RGB in, device scan bytes + lengths out; a capacity that
+    is too small is reported (needed size in the length) and nothing is written past it."""
+    import torch
+    from pixo_b200 import _lib
+    lib = _lib.load()
+    w, h, n = 1000, 600, 3
+    frames = np.stack([po.gen_noise(w, h, 3, 5), po.gen_gradient_rgb(w, h), po.gen_noise(w, h, 3, 6)])
+    stride = w * h * 3
+    d_px = torch.from_numpy(frames.reshape(n, -1)).cuda()
+    refs = [_scan_bytes(po.jpeg_encode(frames[k].reshape(-1), w, h, 2, 80, 1)) for k in range(n)]
+    for cap in (1 << 20, 4096):
+        d_scan = torch.full((n, cap + 256), 0xA5, dtype=torch.uint8, device="cuda")
+        d_len = torch.zeros(n, dtype=torch.int64, device="cuda")
+        d_ovf = torch.zeros(n, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        rc = lib.pixo_b200_jpeg_encode_dev(gpu_ctx.handle, d_px.data_ptr(), stride, n, w, h, 2, 80, 1,
+                                           d_scan.data_ptr(), cap + 256, d_len.data_ptr(), d_ovf.data_ptr())
+        _lib.check(gpu_ctx.handle, rc)
+        gpu_ctx.sync()
+        lens, ovf, scan = d_len.cpu().numpy(), d_ovf.cpu().numpy(), d_scan.cpu().numpy()
+        for k in range(n):
+            assert lens[k] == len(refs[k]), k
+            if len(refs[k]) <= cap + 256:
+                assert ovf[k] == 0 and scan[k, :lens[k]].tobytes() == refs[k]
+            else:
+                assert ovf[k] != 0
