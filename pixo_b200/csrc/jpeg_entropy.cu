@@ -29,9 +29,10 @@
 namespace pixo {
 namespace {
 
-// Huffman tables as the symbol loop wants them: one word per symbol with the amplitude field
-// already opened up,  entry = ((code << cat) << 5) | (len + cat),  cat = symbol & 15 (AC) or the
-// DC category.  16 + 11 + 5 = 32 bits at most.
+// Huffman tables as the symbol loop wants them: one word per symbol,
+//   entry = (code << (32 - len)) | (len + cat),   cat = symbol & 15 (AC) or the DC category
+// i.e. the code left-aligned in the upper half-word and the total field width (code + amplitude
+// bits) in the low five bits.
 struct HuffDev {
     uint32_t dc[2][12];
     uint32_t ac[2][256];
@@ -44,6 +45,7 @@ struct EntParams {
     uint32_t y_per_mcu;            // 4, 1, 1
     uint64_t nblocks;              // per image, scan order
     uint32_t nchunks;              // per image
+    uint32_t nimages;
     unsigned long long *st_bits;   // [n][nchunks] look-back chain 1: stream bits
     unsigned long long *st_ff;     // [n][nchunks] look-back chain 2: 0xFF bytes
     uint32_t *ticket;              // chunk dispenser (launch order == dependency order)
@@ -80,8 +82,8 @@ __device__ __forceinline__ unsigned long long pack_status(unsigned long long fla
     return flag | ((unsigned long long)(tail & 0x7F) << 55) | (value & ST_VAL);
 }
 
-// Exclusive prefix over chunks [0, chunk) of one image (whole warp; decoupled look-back, 32
-// predecessors per step).  tail_in = the 7-bit tail published by chunk-1.
+// Exclusive prefix over chunks [0, chunk) of one image (whole warp; decoupled look-back, 128
+// predecessors per step, four per lane).  tail_in = the 7-bit tail published by chunk-1.
 __device__ unsigned long long look_back(const unsigned long long *st, int chunk, int lane,
                                         uint32_t *tail_in, bool *fault)
 {
@@ -90,23 +92,36 @@ __device__ unsigned long long look_back(const unsigned long long *st, int chunk,
     bool first = true;
     int base = chunk - 1;
     while (base >= 0) {
-        const int idx = base - lane;
-        const unsigned long long v = idx >= 0 ? ld_status(st + idx) : ST_PFX;
-        const uint32_t flag = (uint32_t)(v >> 62);
-        if (__any_sync(0xffffffffu, flag == 0)) {
+        unsigned long long v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = base - lane - 32 * k;
+            v[k] = idx >= 0 ? ld_status(st + idx) : ST_PFX;
+        }
+        unsigned long long step = 0;
+        bool retry = false, done = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t flag = (uint32_t)(v[k] >> 62);
+            const uint32_t inv = __ballot_sync(0xffffffffu, flag == 0);
+            const uint32_t pm = __ballot_sync(0xffffffffu, flag == 2);
+            const int stop = pm ? __ffs(pm) - 1 : 31;           // nearest inclusive prefix, if any
+            if (inv & (0xffffffffu >> (31 - stop))) { retry = true; break; }
+            unsigned long long val = lane <= stop ? (v[k] & ST_VAL) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            step += val;
+            if (pm) { done = true; break; }
+        }
+        if (retry) {
             if (++spins > SPIN_LIMIT) { *fault = true; break; }
-            __nanosleep(40);
+            __nanosleep(20);
             continue;
         }
-        const uint32_t pm = __ballot_sync(0xffffffffu, flag == 2);
-        const int stop = pm ? __ffs(pm) - 1 : 31;
-        unsigned long long val = lane <= stop ? (v & ST_VAL) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-        excl += val;
-        if (first) { tl = __shfl_sync(0xffffffffu, (uint32_t)(v >> 55) & 0x7Fu, 0); first = false; }
-        if (pm) break;
-        base -= 32;
+        excl += step;
+        if (first) { tl = __shfl_sync(0xffffffffu, (uint32_t)(v[0] >> 55) & 0x7Fu, 0); first = false; }
+        if (done) break;
+        base -= 128;
     }
     *tail_in = tl;
     return excl;
@@ -127,6 +142,93 @@ __device__ __forceinline__ uint32_t interleave16(uint32_t x)
 __device__ __forceinline__ uint32_t ff_bytes(uint32_t w)
 {
     return ((w & 0x7F7F7F7Fu) + 0x01010101u) & w & 0x80808080u;
+}
+
+// ---- the symbol loop -------------------------------------------------------------------------
+__device__ __forceinline__ int lds_s16(uint32_t a)
+{
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v));
+}
+__device__ __forceinline__ uint32_t msb_index(uint32_t v)  // FLO: 31 - clz, v != 0
+{
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
+// Codes one block (encode_block, src/jpeg/huffman.rs:423-481) into 32-bit words
+//   word k -> shared [sa_slot + k * EB * 4] for k < SLOT_W; SPILL: later words -> spill[k - SLOT_W],
+//   !SPILL: later words are dropped (the caller sees the length and runs the SPILL variant).
+// Pending bits are kept left-aligned in `acc`; a symbol arrives left-aligned too (vl, n bits).
+// Returns the block's length in bits; *acc_out = the last, partial word (left-aligned).
+template <bool SPILL>
+__device__ __forceinline__ uint32_t code_block(uint32_t M0, uint32_t M1, int diff, const uint32_t *dctab,
+                                               uint32_t sa_ac, uint32_t sa_stage, uint32_t sa_slot,
+                                               uint32_t *spill, uint32_t *acc_out)
+{
+    uint32_t acc = 0, filled = 0;
+    uint32_t sp = sa_slot;
+    const uint32_t sp_end = sa_slot + SLOT_W * EB * 4;
+    auto put = [&](uint32_t vl, uint32_t n) {
+        const uint32_t hi = acc | (vl >> filled);
+        const uint32_t lo = __funnelshift_r(0u, vl, filled);  // vl << (32 - filled); 0 when filled == 0
+        const uint32_t total = filled + n;
+        if (total >= 32u) {
+            if (sp < sp_end) sts_u32(sp, hi);
+            else if (SPILL) spill[(sp - sp_end) / (EB * 4)] = hi;
+            sp += EB * 4;
+            acc = lo;
+        } else {
+            acc = hi;
+        }
+        filled = total & 31u;
+    };
+    {   // DC difference
+        const uint32_t a = (uint32_t)abs(diff);
+        const uint32_t cat = 32u - (uint32_t)__clz(a);
+        const uint32_t e = dctab[cat];
+        const uint32_t amp = a ^ (((1u << cat) - 1u) & (uint32_t)(diff >> 31));
+        const uint32_t n = e & 31u;
+        put((e & 0xFFFF0000u) | (n ? amp << (32u - n) : 0u), n);
+    }
+    const uint32_t zrl = lds_u32(sa_ac + 0xF0 * 4), eob = lds_u32(sa_ac);
+    uint32_t nprev = ~0u;  // -(previous position) - 1
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        uint32_t mb = __brev(half ? M1 : (M0 & ~1u));  // scan order == descending bit index
+        const uint32_t top = half * 32 + 31;
+        while (mb) {
+            const uint32_t f = msb_index(mb);
+            mb &= ~(1u << f);
+            const uint32_t pos = top - f;
+            uint32_t run = pos + nprev;
+            nprev = ~pos;
+            // coefficient pos sits at stage word pos >> 1, half-word pos & 1
+            const int c = lds_s16(sa_stage + pos * (EB * 2) - (pos & 1u) * (EB * 2 - 2));
+            while (run >= 16u) { put(zrl & 0xFFFF0000u, zrl & 31u); run -= 16u; }
+            const uint32_t a = (uint32_t)abs(c);
+            const uint32_t fl = msb_index(a);  // cat - 1
+            const uint32_t e = lds_u32(sa_ac + 4u + run * 64u + fl * 4u);
+            const uint32_t amp = a ^ (~(0xFFFFFFFEu << fl) & (uint32_t)(c >> 31));
+            const uint32_t n = e & 31u;
+            put((e & 0xFFFF0000u) | (amp << (32u - n)), n);
+        }
+    }
+    if (nprev != ~63u) put(eob & 0xFFFF0000u, eob & 31u);
+    *acc_out = acc;
+    return ((sp - sa_slot) / (EB * 4)) * 32u + filled;
 }
 
 // CTA-wide exclusive scan of one u32 per thread (EB threads); *total = sum.  Two barriers.
@@ -170,7 +272,8 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
     for (int i = t; i < (int)(sizeof(HuffDev) / 4); i += EB)
         reinterpret_cast<uint32_t *>(&T)[i] = reinterpret_cast<const uint32_t *>(&Tp)[i];
     __syncthreads();
-    const uint32_t img = s_id / P.nchunks, chunk = s_id % P.nchunks;
+    // chunk-major dispensing: the n images' chains advance side by side
+    const uint32_t chunk = s_id / P.nimages, img = s_id % P.nimages;
     const bool last_chunk = chunk == P.nchunks - 1;
     const uint64_t s = (uint64_t)chunk * EB + t;
     const bool valid = s < P.nblocks;
@@ -209,60 +312,25 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
                 e1 |= __vminu2(w[16 + j], 0x00010001u) << j;
             }
         }
+        asm volatile("" ::: "memory");  // the stage is read back through ld.shared below
         const uint32_t M0 = interleave16(e0), M1 = interleave16(e1);  // bit i = coefficient i != 0
-
-        uint32_t acc = 0, lastw = 0;
-        int filled = 0, nw = 0;
-        auto put = [&](uint32_t v, int n) {
-            const int total = filled + n;  // 1..58
-            const unsigned long long V = (unsigned long long)v << (64 - total);
-            const uint32_t hi = acc | (uint32_t)(V >> 32), lo = (uint32_t)V;
-            if (total >= 32) {
-                if (nw < SLOT_W) slot[nw * EB + t] = hi; else spill[nw - SLOT_W] = hi;
-                lastw = hi; ++nw; acc = lo; filled = total - 32;
-            } else {
-                acc = hi; filled = total;
-            }
-        };
-        {   // DC difference
-            const int diff = (int)(int16_t)(dc - prev_dc);
-            const uint32_t a = (uint32_t)abs(diff);
-            const int cat = 32 - __clz(a);
-            const uint32_t e = T.dc[tbl][cat];
-            const uint32_t amp = a ^ (((1u << cat) - 1u) & (uint32_t)(diff >> 31));
-            put((e >> 5) | amp, (int)(e & 31));
-        }
-        const uint32_t *tab = T.ac[tbl];
-        const uint32_t zrl = tab[0xF0], eob = tab[0x00];
-        const char *stage = reinterpret_cast<const char *>(work) + t * 4;
-        int prevpos = 0;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            uint32_t mb = __brev(half ? M1 : (M0 & ~1u));
-            const int basepos = half * 32;
-            while (mb) {
-                const int p = __clz(mb);
-                mb &= ~(0x80000000u >> p);
-                const int pos = basepos + p;
-                int run = pos - prevpos - 1;
-                prevpos = pos;
-                const int c = *reinterpret_cast<const int16_t *>(stage + (pos >> 1) * (EB * 4) + (pos & 1) * 2);
-                while (run >= 16) { put(zrl >> 5, (int)(zrl & 31)); run -= 16; }
-                const uint32_t a = (uint32_t)abs(c);
-                const int cat = 32 - __clz(a);
-                const uint32_t e = tab[(run << 4) | cat];
-                const uint32_t amp = a ^ (((1u << cat) - 1u) & (uint32_t)(c >> 31));
-                put((e >> 5) | amp, (int)(e & 31));
-            }
-        }
-        if (prevpos != 63) put(eob >> 5, (int)(eob & 31));
-        L = (uint32_t)nw * 32u + (uint32_t)filled;
-        tail7 = __funnelshift_rc(acc, lastw, 32 - filled) & 0x7Fu;
+        const int diff = (int)(int16_t)(dc - prev_dc);
+        const uint32_t sa_stage = (uint32_t)__cvta_generic_to_shared(work) + 4u * t;
+        const uint32_t sa_slot = (uint32_t)__cvta_generic_to_shared(slot) + 4u * t;
+        const uint32_t sa_ac = (uint32_t)__cvta_generic_to_shared(&T.ac[tbl][0]);
+        uint32_t acc;
+        L = code_block<false>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill, &acc);
+        if (L > SLOT_W * 32u)  // rare: run again, now keeping the words past the slot in local memory
+            L = code_block<true>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill, &acc);
+        asm volatile("" ::: "memory");  // slot words were written through st.shared
+        const int nw = (int)(L >> 5), filled = (int)(L & 31u);
         nwt = nw;
         if (filled) {
             if (nw < SLOT_W) slot[nw * EB + t] = acc; else spill[nw - SLOT_W] = acc;
             nwt = nw + 1;
         }
+        const uint32_t lastw = nw == 0 ? 0u : (nw - 1 < SLOT_W ? slot[(nw - 1) * EB + t] : spill[nw - 1 - SLOT_W]);
+        tail7 = __funnelshift_rc(acc, lastw, 32 - filled) & 0x7Fu;
     }
     s_tl[t] = (L << 7) | tail7;
 
@@ -487,6 +555,7 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
     P.y_per_mcu = g.y_per_mcu;
     P.nblocks = nblocks;
     P.nchunks = (uint32_t)pl.nchunks;
+    P.nimages = n;
     P.st_bits = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_st1);
     P.st_ff = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_st2);
     P.ticket = reinterpret_cast<uint32_t *>(d_scratch + pl.off_ticket);
@@ -500,11 +569,12 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
     memset(&T, 0, sizeof T);
     for (int k = 0; k < 2; ++k) {
         for (int cat = 0; cat < 12; ++cat)
-            if (t.len[k][cat]) T.dc[k][cat] = (((uint32_t)t.code[k][cat] << cat) << 5) | (uint32_t)(t.len[k][cat] + cat);
+            if (t.len[k][cat])
+                T.dc[k][cat] = ((uint32_t)t.code[k][cat] << (32 - t.len[k][cat])) | (uint32_t)(t.len[k][cat] + cat);
         for (int rs = 0; rs < 256; ++rs) {
             const int cat = rs & 15;
             if (t.len[2 + k][rs] && cat <= 10)
-                T.ac[k][rs] = (((uint32_t)t.code[2 + k][rs] << cat) << 5) | (uint32_t)(t.len[2 + k][rs] + cat);
+                T.ac[k][rs] = ((uint32_t)t.code[2 + k][rs] << (32 - t.len[2 + k][rs])) | (uint32_t)(t.len[2 + k][rs] + cat);
         }
     }
     cudaStream_t st = ctx->stream;

@@ -23,6 +23,20 @@ if which == "jpeg420":
         _lib.check(ctx.handle, lib.pixo_b200_jpeg_coefficients_dev(
             ctx.handle, px.data_ptr(), H * W * 3, n, W, H, 2, 1, lq.ctypes.data_as(_lib.f32p),
             cq.ctypes.data_as(_lib.f32p), y.data_ptr(), ny * 64, cb.data_ptr(), cr.data_ptr(), nc * 64, 0, None))
+elif which == "encode":   # whole device path on the bench's frame mix (gradient / LCG noise)
+    from pixo_b200 import synthetic
+    g = synthetic.gradient_rgb(W, H).reshape(H, W * 3)
+    fr = np.stack([np.roll(g, k, axis=0).reshape(-1) if k % 2 == 0 else synthetic.noise(W, H, 3, 42 + k).reshape(-1)
+                   for k in range(n)])
+    px = torch.from_numpy(fr).cuda()
+    cap = (H * W * 3 // 2 + 65536 + 8192) // 256 * 256
+    scan = torch.empty((n, cap), dtype=torch.uint8, device="cuda")
+    sl = torch.zeros(n, dtype=torch.int64, device="cuda"); so = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for _ in range(reps):
+        _lib.check(ctx.handle, lib.pixo_b200_jpeg_encode_dev(ctx.handle, px.data_ptr(), H * W * 3, n, W, H, 2, 80, 1,
+                                                             scan.data_ptr(), cap, sl.data_ptr(), so.data_ptr()))
+    torch.cuda.synchronize()
+    print("scan bytes", sl.cpu().numpy().tolist(), "overflow", int(so.sum()))
 elif which == "png":
     rb = W * 4
     px = torch.randint(0, 256, (n, H * rb), dtype=torch.uint8, device="cuda")
