@@ -9,20 +9,22 @@
 //
 // One kernel, one pass over the coefficients (k_huff).  The DC predictor of a block is the
 // previous block of the same component in the coefficient array, so every block's code is
-// independent of the others; only its POSITION in the stream is not.  A CTA takes a chunk of 128
-// consecutive blocks (scan order) of one image:
-//   1. each thread codes its block once into a private shared-memory slot (coefficients arrive
-//      in zig-zag order; a 64-bit non-zero mask drives the symbol loop, so the loop runs once per
+// independent of the others; only its POSITION in the stream is not.  The kernel is persistent
+// and every warp works alone (warp-level synchronisation only): it draws a chunk of 32
+// consecutive blocks (scan order) of one image from a ticket counter, then
+//   1. each lane codes its block once into a private shared-memory slot (coefficients arrive in
+//      zig-zag order; a 64-bit non-zero mask drives the symbol loop, so the loop runs once per
 //      non-zero coefficient and there is a single, small copy of the symbol code);
-//   2. the block bit lengths are scanned in the CTA; the chunk total enters a decoupled
+//   2. the block bit lengths are scanned in the warp; the chunk total enters a decoupled
 //      look-back chain (one status word per chunk: bit count + the chunk's last 7 bits), which
 //      yields the chunk's bit offset in the image's stream and the partial byte it inherits;
 //   3. the slots are funnel-shifted into a shared window aligned to the stream's 32-bit words;
 //   4. the chunk owns every byte whose last bit it wrote.  It counts its 0xFF bytes, a second
 //      look-back chain turns those counts into the number of stuffed zeros before the chunk, and
 //      the window is copied out with the 0x00s inserted, 16 bytes per store.
-// Nothing but the final scan bytes is written to global memory.  Restart intervals stay on the
-// host coder (jpeg_host.cpp): they need per-interval padding.
+// Tickets are dispensed chunk-major across the images of a batch, so their chains advance side
+// by side.  Nothing but the final scan bytes is written to global memory.  Restart intervals
+// stay on the host coder (jpeg_host.cpp): they need per-interval padding.
 #include "common.cuh"
 #include "jpeg_host.hpp"
 
@@ -43,7 +45,7 @@ struct EntParams {
     size_t y_stride, c_stride;     // int16 elements between images
     uint32_t bpm;                  // blocks per MCU in scan order: 6 (4:2:0), 3 (4:4:4), 1 (gray)
     uint32_t y_per_mcu;            // 4, 1, 1
-    uint64_t nblocks;              // per image, scan order
+    uint32_t nblocks;              // per image, scan order
     uint32_t nchunks;              // per image
     uint32_t nimages;
     unsigned long long *st_bits;   // [n][nchunks] look-back chain 1: stream bits
@@ -55,10 +57,12 @@ struct EntParams {
     uint32_t *overflow;            // [n] set when out_cap was exceeded (or the chain faulted)
 };
 
-constexpr int EB = 128;            // blocks per chunk == threads per CTA
+constexpr int CB = 32;             // blocks per chunk == one warp
+constexpr int HUFF_WARPS = 4;      // warps per CTA (they only share the tables)
+constexpr int HUFF_CTAS_PER_SM = 7;
 constexpr int SLOT_W = 24;         // words of a block's code kept in shared memory (768 bits)
 constexpr int MAX_W = 54;          // worst case: 27 + 63 * 26 = 1665 bits
-constexpr int WIN_W = 1024;        // stream words assembled per round
+constexpr int WIN_W = 256;         // stream words assembled per round (32 bytes per lane)
 constexpr int WIN_B = WIN_W * 4;
 constexpr int SBUF_B = 2 * WIN_B + 32;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
@@ -169,7 +173,7 @@ __device__ __forceinline__ uint32_t msb_index(uint32_t v)  // FLO: 31 - clz, v !
 }
 
 // Codes one block (encode_block, src/jpeg/huffman.rs:423-481) into 32-bit words
-//   word k -> shared [sa_slot + k * EB * 4] for k < SLOT_W; SPILL: later words -> spill[k - SLOT_W],
+//   word k -> shared [sa_slot + k * CB * 4] for k < SLOT_W; SPILL: later words -> spill[k - SLOT_W],
 //   !SPILL: later words are dropped (the caller sees the length and runs the SPILL variant).
 // Pending bits are kept left-aligned in `acc`; a symbol arrives left-aligned too (vl, n bits).
 // Returns the block's length in bits; *acc_out = the last, partial word (left-aligned).
@@ -180,15 +184,15 @@ __device__ __forceinline__ uint32_t code_block(uint32_t M0, uint32_t M1, int dif
 {
     uint32_t acc = 0, filled = 0;
     uint32_t sp = sa_slot;
-    const uint32_t sp_end = sa_slot + SLOT_W * EB * 4;
+    const uint32_t sp_end = sa_slot + SLOT_W * CB * 4;
     auto put = [&](uint32_t vl, uint32_t n) {
         const uint32_t hi = acc | (vl >> filled);
         const uint32_t lo = __funnelshift_r(0u, vl, filled);  // vl << (32 - filled); 0 when filled == 0
         const uint32_t total = filled + n;
         if (total >= 32u) {
             if (sp < sp_end) sts_u32(sp, hi);
-            else if (SPILL) spill[(sp - sp_end) / (EB * 4)] = hi;
-            sp += EB * 4;
+            else if (SPILL) spill[(sp - sp_end) / (CB * 4)] = hi;
+            sp += CB * 4;
             acc = lo;
         } else {
             acc = hi;
@@ -216,7 +220,7 @@ __device__ __forceinline__ uint32_t code_block(uint32_t M0, uint32_t M1, int dif
             uint32_t run = pos + nprev;
             nprev = ~pos;
             // coefficient pos sits at stage word pos >> 1, half-word pos & 1
-            const int c = lds_s16(sa_stage + pos * (EB * 2) - (pos & 1u) * (EB * 2 - 2));
+            const int c = lds_s16(sa_stage + pos * (CB * 2) - (pos & 1u) * (CB * 2 - 2));
             while (run >= 16u) { put(zrl & 0xFFFF0000u, zrl & 31u); run -= 16u; }
             const uint32_t a = (uint32_t)abs(c);
             const uint32_t fl = msb_index(a);  // cat - 1
@@ -228,282 +232,292 @@ __device__ __forceinline__ uint32_t code_block(uint32_t M0, uint32_t M1, int dif
     }
     if (nprev != ~63u) put(eob & 0xFFFF0000u, eob & 31u);
     *acc_out = acc;
-    return ((sp - sa_slot) / (EB * 4)) * 32u + filled;
+    return ((sp - sa_slot) / (CB * 4)) * 32u + filled;
 }
 
-// CTA-wide exclusive scan of one u32 per thread (EB threads); *total = sum.  Two barriers.
-__device__ __forceinline__ uint32_t cta_scan(uint32_t x, uint32_t *s_ws, uint32_t *total)
+// warp-wide exclusive scan; *total = sum over the warp
+__device__ __forceinline__ uint32_t warp_scan(uint32_t x, int lane, uint32_t *total)
 {
-    const int t = threadIdx.x;
     uint32_t inc = x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-        if ((t & 31) >= o) inc += n;
+        if (lane >= o) inc += n;
     }
-    __syncthreads();
-    if ((t & 31) == 31) s_ws[t >> 5] = inc;
-    __syncthreads();
-    uint32_t wb = 0, tot = 0;
-#pragma unroll
-    for (int k = 0; k < EB / 32; ++k) {
-        const uint32_t v = s_ws[k];
-        if (k < (t >> 5)) wb += v;
-        tot += v;
-    }
-    *total = tot;
-    return wb + inc - x;
+    *total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - x;
 }
 
-__global__ void __launch_bounds__(EB, 7)
+// Shared memory of one warp.  The coefficient stage is dead once the blocks are coded; the
+// stream window and the stuffed bytes reuse it.
+struct WarpMem {
+    uint32_t slot[SLOT_W * CB];
+    union {
+        uint32_t stage[32 * CB];
+        struct {
+            uint32_t obuf[WIN_W];
+            uint8_t sbuf[SBUF_B];
+        } w;
+    };
+    uint32_t tl[CB];
+};
+
+// Persistent kernel; every WARP works on its own: it draws a chunk of 32 blocks from the ticket
+// counter, codes it and emits its bytes with warp-level synchronisation only.
+__global__ void __launch_bounds__(32 * HUFF_WARPS, HUFF_CTAS_PER_SM)
 k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
 {
     __shared__ HuffDev T;
-    __shared__ uint32_t slot[SLOT_W * EB];
-    __shared__ __align__(16) uint32_t work[32 * EB];  // coefficient stage, then window + stuffed bytes
-    __shared__ uint32_t s_ws[EB / 32];
-    __shared__ uint32_t s_tl[EB];
-    __shared__ unsigned long long s_pfx, s_ffx;
-    __shared__ uint32_t s_id, s_tailin, s_fault;
-    static_assert(WIN_B + SBUF_B <= (int)sizeof(work), "window + stuffed bytes must fit the stage");
+    __shared__ __align__(16) WarpMem wmem[HUFF_WARPS];
+    static_assert(sizeof(((WarpMem *)0)->w) <= sizeof(((WarpMem *)0)->stage), "window + stuffed bytes must fit the stage");
 
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t == 0) { s_id = atomicAdd(P.ticket, 1u); s_fault = 0; }
-    for (int i = t; i < (int)(sizeof(HuffDev) / 4); i += EB)
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (int)(sizeof(HuffDev) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t *>(&T)[i] = reinterpret_cast<const uint32_t *>(&Tp)[i];
     __syncthreads();
-    // chunk-major dispensing: the n images' chains advance side by side
-    const uint32_t chunk = s_id / P.nimages, img = s_id % P.nimages;
-    const bool last_chunk = chunk == P.nchunks - 1;
-    const uint64_t s = (uint64_t)chunk * EB + t;
-    const bool valid = s < P.nblocks;
-    const int nv = (int)min((uint64_t)EB, P.nblocks - (uint64_t)chunk * EB);
-
-    // ---- 1. code the block into its slot ---------------------------------------------------
+    WarpMem &M = wmem[threadIdx.x >> 5];
+    uint32_t *const slot = M.slot;
+    uint32_t *const obuf = M.w.obuf;
+    uint8_t *const sbuf = M.w.sbuf;
+    const uint32_t sa_stage = (uint32_t)__cvta_generic_to_shared(M.stage) + 4u * lane;
+    const uint32_t sa_slot = (uint32_t)__cvta_generic_to_shared(M.slot) + 4u * lane;
+    const uint32_t total_chunks = P.nchunks * P.nimages;
     uint32_t spill[MAX_W - SLOT_W];  // words beyond SLOT_W (pathological blocks): local memory
-    uint32_t L = 0, tail7 = 0;
-    int nwt = 0;
-    if (valid) {
-        const uint64_t m = s / P.bpm;
-        const uint32_t k = (uint32_t)(s - m * P.bpm);
-        const int16_t *arr;
-        uint64_t idx;
-        int tbl;
-        if (k < P.y_per_mcu) { arr = P.y + (size_t)img * P.y_stride; idx = m * P.y_per_mcu + k; tbl = 0; }
-        else if (k == P.y_per_mcu) { arr = P.cb + (size_t)img * P.c_stride; idx = m; tbl = 1; }
-        else { arr = P.cr + (size_t)img * P.c_stride; idx = m; tbl = 1; }
-        const int prev_dc = idx ? arr[(idx - 1) * 64] : 0;
-        const uint4 *src = reinterpret_cast<const uint4 *>(arr + idx * 64);
-        uint32_t e0 = 0, e1 = 0;
-        int dc;
-        {
-            uint32_t w[32];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const uint4 v = __ldg(src + q);
-                w[q * 4] = v.x; w[q * 4 + 1] = v.y; w[q * 4 + 2] = v.z; w[q * 4 + 3] = v.w;
-            }
-            dc = (int)(int16_t)(w[0] & 0xFFFF);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) work[j * EB + t] = w[j];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                e0 |= __vminu2(w[j], 0x00010001u) << j;
-                e1 |= __vminu2(w[16 + j], 0x00010001u) << j;
-            }
-        }
-        asm volatile("" ::: "memory");  // the stage is read back through ld.shared below
-        const uint32_t M0 = interleave16(e0), M1 = interleave16(e1);  // bit i = coefficient i != 0
-        const int diff = (int)(int16_t)(dc - prev_dc);
-        const uint32_t sa_stage = (uint32_t)__cvta_generic_to_shared(work) + 4u * t;
-        const uint32_t sa_slot = (uint32_t)__cvta_generic_to_shared(slot) + 4u * t;
-        const uint32_t sa_ac = (uint32_t)__cvta_generic_to_shared(&T.ac[tbl][0]);
-        uint32_t acc;
-        L = code_block<false>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill, &acc);
-        if (L > SLOT_W * 32u)  // rare: run again, now keeping the words past the slot in local memory
-            L = code_block<true>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill, &acc);
-        asm volatile("" ::: "memory");  // slot words were written through st.shared
-        const int nw = (int)(L >> 5), filled = (int)(L & 31u);
-        nwt = nw;
-        if (filled) {
-            if (nw < SLOT_W) slot[nw * EB + t] = acc; else spill[nw - SLOT_W] = acc;
-            nwt = nw + 1;
-        }
-        const uint32_t lastw = nw == 0 ? 0u : (nw - 1 < SLOT_W ? slot[(nw - 1) * EB + t] : spill[nw - 1 - SLOT_W]);
-        tail7 = __funnelshift_rc(acc, lastw, 32 - filled) & 0x7Fu;
-    }
-    s_tl[t] = (L << 7) | tail7;
 
-    // ---- 2. offsets: CTA scan + look-back chain 1 --------------------------------------------
-    uint32_t Lc;
-    const uint32_t o_t = cta_scan(L, s_ws, &Lc);  // barriers inside also publish s_tl / the stage is dead
-    unsigned long long *st1 = P.st_bits + (size_t)img * P.nchunks;
-    unsigned long long *st2 = P.st_ff + (size_t)img * P.nchunks;
-    if (warp == 0) {
+    for (;;) {
+        uint32_t id = 0;
+        if (lane == 0) id = atomicAdd(P.ticket, 1u);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= total_chunks) break;
+        // chunk-major dispensing: the n images' chains advance side by side
+        const uint32_t chunk = id / P.nimages, img = id - chunk * P.nimages;
+        const bool last_chunk = chunk == P.nchunks - 1;
+        const uint32_t s = chunk * CB + lane;
+        const bool valid = s < P.nblocks;
+        const int nv = (int)min((uint32_t)CB, P.nblocks - chunk * CB);
+
+        // ---- 1. code the block into its slot -----------------------------------------------
+        uint32_t L = 0, tail7 = 0;
+        int nwt = 0;
+        if (valid) {
+            const uint32_t m = s / P.bpm;
+            const uint32_t k = s - m * P.bpm;
+            const int16_t *arr;
+            size_t idx;
+            int tbl;
+            if (k < P.y_per_mcu) { arr = P.y + (size_t)img * P.y_stride; idx = (size_t)m * P.y_per_mcu + k; tbl = 0; }
+            else if (k == P.y_per_mcu) { arr = P.cb + (size_t)img * P.c_stride; idx = m; tbl = 1; }
+            else { arr = P.cr + (size_t)img * P.c_stride; idx = m; tbl = 1; }
+            const int prev_dc = idx ? arr[(idx - 1) * 64] : 0;
+            const uint4 *src = reinterpret_cast<const uint4 *>(arr + idx * 64);
+            uint32_t e0 = 0, e1 = 0;
+            int dc;
+            {
+                uint32_t w[32];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint4 v = __ldg(src + q);
+                    w[q * 4] = v.x; w[q * 4 + 1] = v.y; w[q * 4 + 2] = v.z; w[q * 4 + 3] = v.w;
+                }
+                dc = (int)(int16_t)(w[0] & 0xFFFF);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) M.stage[j * CB + lane] = w[j];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    e0 |= __vminu2(w[j], 0x00010001u) << j;
+                    e1 |= __vminu2(w[16 + j], 0x00010001u) << j;
+                }
+            }
+            asm volatile("" ::: "memory");  // the stage is read back through ld.shared below
+            const uint32_t M0 = interleave16(e0), M1 = interleave16(e1);  // bit i = coefficient i != 0
+            const int diff = (int)(int16_t)(dc - prev_dc);
+            const uint32_t sa_ac = (uint32_t)__cvta_generic_to_shared(&T.ac[tbl][0]);
+            uint32_t acc;
+            L = code_block<false>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill, &acc);
+            if (L > SLOT_W * 32u)  // rare: run again, now keeping the words past the slot in local memory
+                L = code_block<true>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill, &acc);
+            asm volatile("" ::: "memory");  // slot words were written through st.shared
+            const int nw = (int)(L >> 5), filled = (int)(L & 31u);
+            nwt = nw;
+            if (filled) {
+                if (nw < SLOT_W) slot[nw * CB + lane] = acc; else spill[nw - SLOT_W] = acc;
+                nwt = nw + 1;
+            }
+            const uint32_t lastw = nw == 0 ? 0u : (nw - 1 < SLOT_W ? slot[(nw - 1) * CB + lane] : spill[nw - 1 - SLOT_W]);
+            tail7 = __funnelshift_rc(acc, lastw, 32 - filled) & 0x7Fu;
+        }
+        M.tl[lane] = (L << 7) | tail7;
+        __syncwarp();  // every lane is done with the stage; tl[] visible
+
+        // ---- 2. offsets: warp scan + look-back chain 1 -----------------------------------------
+        uint32_t Lc;
+        const uint32_t o_t = warp_scan(L, lane, &Lc);
+        unsigned long long *st1 = P.st_bits + (size_t)img * P.nchunks;
+        unsigned long long *st2 = P.st_ff + (size_t)img * P.nchunks;
+        bool fault = false;
         uint32_t ctail = 0;
         if (lane == 0) {  // the chunk's last 7 bits (a block has >= 2 bits: at most 4 steps)
             int got = 0;
             for (int k = nv - 1; k >= 0 && got < 7; --k) {
-                const uint32_t x = s_tl[k];
+                const uint32_t x = M.tl[k];
                 const int take = min((int)(x >> 7), 7 - got);
                 ctail |= (x & ((1u << take) - 1u)) << got;
                 got += take;
             }
             st_status(st1 + chunk, pack_status(chunk == 0 ? ST_PFX : ST_AGG, ctail, Lc));
         }
-        uint32_t tin = 0;
-        unsigned long long excl = 0;
+        uint32_t tailin = 0;
+        unsigned long long Pc = 0;
         if (chunk) {
-            bool fault = false;
-            excl = look_back(st1, (int)chunk, lane, &tin, &fault);
-            if (lane == 0) {
-                st_status(st1 + chunk, pack_status(ST_PFX, ctail, excl + Lc));
-                if (fault) s_fault = 1;
-            }
+            Pc = look_back(st1, (int)chunk, lane, &tailin, &fault);
+            if (lane == 0) st_status(st1 + chunk, pack_status(ST_PFX, ctail, Pc + Lc));
         }
-        if (lane == 0) { s_pfx = excl; s_tailin = tin; }
-    }
-    __syncthreads();
-    const unsigned long long Pc = s_pfx;
-    const uint32_t q0 = (uint32_t)Pc & 31u;           // bit offset of the chunk inside window word 0
-    const uint32_t endbit = q0 + Lc;                  // window bit index one past the chunk
-    const uint32_t padc = last_chunk ? ((8u - (endbit & 7u)) & 7u) : 0u;   // 1-padding (bits.rs:261-272)
-    const uint32_t ob0 = q0 >> 3;                     // owned window bytes [ob0, ob1)
-    const uint32_t ob1 = (endbit >> 3) + (padc ? 1u : 0u);
-    const int nrounds = max(1, (int)((ob1 + WIN_B - 1) / WIN_B));
-    uint32_t *obuf = work;
-    uint8_t *sbuf = reinterpret_cast<uint8_t *>(work) + WIN_B;
-    uint8_t *outp = P.out + (size_t)img * P.out_cap;
+        const uint32_t q0 = (uint32_t)Pc & 31u;           // bit offset of the chunk inside window word 0
+        const uint32_t endbit = q0 + Lc;                  // window bit index one past the chunk
+        const uint32_t padc = last_chunk ? ((8u - (endbit & 7u)) & 7u) : 0u;   // 1-padding (bits.rs:261-272)
+        const uint32_t ob0 = q0 >> 3;                     // owned window bytes [ob0, ob1)
+        const uint32_t ob1 = (endbit >> 3) + (padc ? 1u : 0u);
+        const int nrounds = max(1, (int)((ob1 + WIN_B - 1) / WIN_B));
+        uint8_t *outp = P.out + (size_t)img * P.out_cap;
 
-    // per-thread constants of the funnel-shifted copy
-    const uint32_t D = q0 + o_t;
-    const int d0 = (int)(D >> 5), sh = (int)(D & 31u);
-    const int nd = L ? (int)((sh + L + 31u) >> 5) : 0;   // destination words
+        // per-lane constants of the funnel-shifted copy
+        const uint32_t D = q0 + o_t;
+        const int d0 = (int)(D >> 5), sh = (int)(D & 31u);
+        const int nd = L ? (int)((sh + L + 31u) >> 5) : 0;   // destination words
 
-    uint32_t Ftot = 0, Fdone = 0;
-    unsigned long long gbase = 0;
-    const int iters = nrounds == 1 ? 1 : 2 * nrounds;  // >1 round: a counting sweep, then the emitting sweep
+        uint32_t Ftot = 0, Fdone = 0;
+        unsigned long long gbase = 0, ffx = 0;
+        const int iters = nrounds == 1 ? 1 : 2 * nrounds;  // >1 round: a counting sweep, then the emitting sweep
 #pragma unroll 1
-    for (int it = 0; it < iters; ++it) {
-        const int r = it < nrounds ? it : it - nrounds;
-        const bool emit = nrounds == 1 || it >= nrounds;
-        // ---- 3. assemble window r ----------------------------------------------------------
-        for (int i = t; i < WIN_W / 4; i += EB) reinterpret_cast<uint4 *>(obuf)[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        {
-            const int wlo = r * WIN_W;
-            const int kb = max(0, wlo - d0), ke = min(nd, wlo + WIN_W - d0);
-            uint32_t prev = 0;
-            if (kb > 0 && kb <= nwt) prev = (kb - 1) < SLOT_W ? slot[(kb - 1) * EB + t] : spill[kb - 1 - SLOT_W];
-            for (int k = kb; k < ke; ++k) {
-                uint32_t cur = 0;
-                if (k < nwt) cur = k < SLOT_W ? slot[k * EB + t] : spill[k - SLOT_W];
-                const uint32_t v = __funnelshift_r(cur, prev, sh);
-                uint32_t *dst = obuf + (d0 + k - wlo);
-                if (k == 0 || k == nd - 1) atomicOr(dst, v); else *dst = v;
-                prev = cur;
-            }
-            if (t == 0) {
-                const uint32_t q = q0 & 7u;  // inherited bits of the straddling first byte
-                if (r == 0 && q) atomicOr(&obuf[0], (s_tailin & ((1u << q) - 1u)) << (32u - q0));
-                const int pw = (int)(endbit >> 5) - wlo;
-                if (padc && pw >= 0 && pw < WIN_W)
-                    atomicOr(&obuf[pw], ((1u << padc) - 1u) << (32u - (endbit & 31u) - padc));
-            }
-        }
-        __syncthreads();
-        // ---- 4a. count the 0xFF bytes this thread's 32 window bytes hold -------------------------
-        const int wb0 = r * WIN_B;
-        const int a = max((int)ob0 - wb0, 0), b = min((int)ob1 - wb0, WIN_B);
-        const int lo = max(32 * t, a), hi = min(32 * t + 32, b);
-        uint32_t cnt = 0;
-        if (hi > lo) {
-            for (int j = (lo >> 2) - 8 * t; j < 8 && 32 * t + 4 * j < hi; ++j) {
-                const int wbyte = 32 * t + 4 * j;
-                uint32_t f = ff_bytes(obuf[8 * t + j]);
-                if (wbyte < lo || wbyte + 4 > hi) {
-                    uint32_t keep = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (wbyte + i >= lo && wbyte + i < hi) keep |= 0x80000000u >> (8 * i);
-                    f &= keep;
-                }
-                cnt += __popc(f);
-            }
-        }
-        uint32_t Fr;
-        const uint32_t ffb = cta_scan(cnt, s_ws, &Fr);
-        if (!emit) { Ftot += Fr; }
-        if (it == (nrounds == 1 ? 0 : nrounds - 1)) {
-            // ---- look-back chain 2: stuffed zeros before this chunk ------------------------------
-            if (nrounds == 1) Ftot = Fr;
-            if (warp == 0) {
-                if (lane == 0) st_status(st2 + chunk, pack_status(chunk == 0 ? ST_PFX : ST_AGG, 0, Ftot));
-                unsigned long long fx = 0;
-                if (chunk) {
-                    bool fault = false;
-                    uint32_t dummy;
-                    fx = look_back(st2, (int)chunk, lane, &dummy, &fault);
-                    if (lane == 0) {
-                        st_status(st2 + chunk, pack_status(ST_PFX, 0, fx + Ftot));
-                        if (fault) s_fault = 1;
+        for (int it = 0; it < iters; ++it) {
+            const int r = it < nrounds ? it : it - nrounds;
+            const bool emit = nrounds == 1 || it >= nrounds;
+            // ---- 3. assemble window r ----------------------------------------------------------
+            for (int i = lane; i < WIN_W / 4; i += 32) reinterpret_cast<uint4 *>(obuf)[i] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            {
+                const int wlo = r * WIN_W;
+                const int kb = max(0, wlo - d0), ke = min(nd, wlo + WIN_W - d0);
+                uint32_t prev = 0;
+                if (nwt <= SLOT_W) {  // the usual case: every word is in the slot
+                    if (kb > 0 && kb <= nwt) prev = slot[(kb - 1) * CB + lane];
+                    for (int k = kb; k < ke; ++k) {
+                        const uint32_t cur = k < nwt ? slot[k * CB + lane] : 0u;
+                        const uint32_t v = __funnelshift_r(cur, prev, sh);
+                        uint32_t *dst = obuf + (d0 + k - wlo);
+                        if (k == 0 || k == nd - 1) atomicOr(dst, v); else *dst = v;
+                        prev = cur;
+                    }
+                } else {
+                    if (kb > 0 && kb <= nwt) prev = (kb - 1) < SLOT_W ? slot[(kb - 1) * CB + lane] : spill[kb - 1 - SLOT_W];
+                    for (int k = kb; k < ke; ++k) {
+                        uint32_t cur = 0;
+                        if (k < nwt) cur = k < SLOT_W ? slot[k * CB + lane] : spill[k - SLOT_W];
+                        const uint32_t v = __funnelshift_r(cur, prev, sh);
+                        uint32_t *dst = obuf + (d0 + k - wlo);
+                        if (k == 0 || k == nd - 1) atomicOr(dst, v); else *dst = v;
+                        prev = cur;
                     }
                 }
-                if (lane == 0) s_ffx = fx;
+                if (lane == 0) {
+                    const uint32_t q = q0 & 7u;  // inherited bits of the straddling first byte
+                    if (r == 0 && q) atomicOr(&obuf[0], (tailin & ((1u << q) - 1u)) << (32u - q0));
+                    const int pw = (int)(endbit >> 5) - wlo;
+                    if (padc && pw >= 0 && pw < WIN_W)
+                        atomicOr(&obuf[pw], ((1u << padc) - 1u) << (32u - (endbit & 31u) - padc));
+                }
             }
-            __syncthreads();
-            gbase = (Pc >> 3) + s_ffx;  // output index of the first owned byte
-        }
-        if (!emit) continue;
-        // ---- 4b. stuffed bytes of this window -> sbuf -> global ------------------------------------
-        const unsigned long long G = gbase + (r == 0 ? 0u : (uint32_t)(wb0 - (int)ob0)) + Fdone;
-        const uint32_t nr = (uint32_t)max(b - a, 0) + Fr;
-        const uint32_t shb = (uint32_t)((reinterpret_cast<uintptr_t>(outp) + G) & 15u);
-        if (hi > lo) {
-            uint32_t dst = shb + (uint32_t)(lo - a) + ffb;
-            for (int j = (lo >> 2) - 8 * t; j < 8 && 32 * t + 4 * j < hi; ++j) {
-                const int wbyte = 32 * t + 4 * j;
-                const uint32_t w = obuf[8 * t + j];
-                if (wbyte >= lo && wbyte + 4 <= hi && ff_bytes(w) == 0 && (dst & 3u) == 0) {
-                    *reinterpret_cast<uint32_t *>(sbuf + dst) = __byte_perm(w, 0, 0x0123);
-                    dst += 4;
-                } else {
+            __syncwarp();
+            // ---- 4a. count the 0xFF bytes in this lane's 32 window bytes ---------------------------
+            const int wb0 = r * WIN_B;
+            const int a = max((int)ob0 - wb0, 0), b = min((int)ob1 - wb0, WIN_B);
+            const int lo = max(32 * lane, a), hi = min(32 * lane + 32, b);
+            uint32_t cnt = 0;
+            if (hi > lo) {
+                for (int j = (lo >> 2) - 8 * lane; j < 8 && 32 * lane + 4 * j < hi; ++j) {
+                    const int wbyte = 32 * lane + 4 * j;
+                    uint32_t f = ff_bytes(obuf[8 * lane + j]);
+                    if (wbyte < lo || wbyte + 4 > hi) {
+                        uint32_t keep = 0;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (wbyte + i >= lo && wbyte + i < hi) {
-                            const uint32_t byte = (w >> (24 - 8 * i)) & 0xFFu;
-                            sbuf[dst++] = (uint8_t)byte;
-                            if (byte == 0xFFu) sbuf[dst++] = 0;
+                        for (int i = 0; i < 4; ++i)
+                            if (wbyte + i >= lo && wbyte + i < hi) keep |= 0x80000000u >> (8 * i);
+                        f &= keep;
+                    }
+                    cnt += __popc(f);
+                }
+            }
+            uint32_t Fr;
+            const uint32_t ffb = warp_scan(cnt, lane, &Fr);
+            if (!emit) Ftot += Fr;
+            if (it == (nrounds == 1 ? 0 : nrounds - 1)) {
+                // ---- look-back chain 2: stuffed zeros before this chunk ------------------------------
+                if (nrounds == 1) Ftot = Fr;
+                if (lane == 0) st_status(st2 + chunk, pack_status(chunk == 0 ? ST_PFX : ST_AGG, 0, Ftot));
+                if (chunk) {
+                    uint32_t dummy;
+                    ffx = look_back(st2, (int)chunk, lane, &dummy, &fault);
+                    if (lane == 0) st_status(st2 + chunk, pack_status(ST_PFX, 0, ffx + Ftot));
+                }
+                gbase = (Pc >> 3) + ffx;  // output index of the first owned byte
+            }
+            if (!emit) continue;
+            // ---- 4b. stuffed bytes of this window -> sbuf -> global ------------------------------------
+            const unsigned long long G = gbase + (r == 0 ? 0u : (uint32_t)(wb0 - (int)ob0)) + Fdone;
+            const uint32_t nr = (uint32_t)max(b - a, 0) + Fr;
+            const uint32_t shb = (uint32_t)((reinterpret_cast<uintptr_t>(outp) + G) & 15u);
+            if (hi > lo) {
+                uint32_t dst = shb + (uint32_t)(lo - a) + ffb;
+                for (int j = (lo >> 2) - 8 * lane; j < 8 && 32 * lane + 4 * j < hi; ++j) {
+                    const int wbyte = 32 * lane + 4 * j;
+                    const uint32_t w = obuf[8 * lane + j];
+                    if (wbyte >= lo && wbyte + 4 <= hi && ff_bytes(w) == 0) {
+                        if ((dst & 3u) == 0) {
+                            *reinterpret_cast<uint32_t *>(sbuf + dst) = __byte_perm(w, 0, 0x0123);
+                        } else {
+                            sbuf[dst] = (uint8_t)(w >> 24); sbuf[dst + 1] = (uint8_t)(w >> 16);
+                            sbuf[dst + 2] = (uint8_t)(w >> 8); sbuf[dst + 3] = (uint8_t)w;
+                        }
+                        dst += 4;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (wbyte + i >= lo && wbyte + i < hi) {
+                                const uint32_t byte = (w >> (24 - 8 * i)) & 0xFFu;
+                                sbuf[dst++] = (uint8_t)byte;
+                                if (byte == 0xFFu) sbuf[dst++] = 0;
+                            }
                         }
                     }
                 }
             }
-        }
-        __syncthreads();
-        if (G + nr <= P.out_cap) {
-            uint8_t *gdst = outp + G - shb;  // 16-byte aligned
-            const uint32_t end = shb + nr;
-            for (uint32_t c16 = t; c16 * 16 < end; c16 += EB) {
-                const uint32_t lo_b = c16 * 16, hi_b = lo_b + 16;
-                if (lo_b >= shb && hi_b <= end) {
-                    *reinterpret_cast<uint4 *>(gdst + lo_b) = *reinterpret_cast<const uint4 *>(sbuf + lo_b);
-                } else {
-                    for (uint32_t i = max(lo_b, shb); i < min(hi_b, end); ++i) gdst[i] = sbuf[i];
+            __syncwarp();
+            if (G + nr <= P.out_cap) {
+                uint8_t *gdst = outp + G - shb;  // 16-byte aligned
+                const uint32_t end = shb + nr;
+                for (uint32_t c16 = lane; c16 * 16 < end; c16 += 32) {
+                    const uint32_t lo_b = c16 * 16, hi_b = lo_b + 16;
+                    if (lo_b >= shb && hi_b <= end) {
+                        *reinterpret_cast<uint4 *>(gdst + lo_b) = *reinterpret_cast<const uint4 *>(sbuf + lo_b);
+                    } else {
+                        for (uint32_t i = max(lo_b, shb); i < min(hi_b, end); ++i) gdst[i] = sbuf[i];
+                    }
                 }
+            } else if (lane == 0) {
+                P.overflow[img] = 1;
             }
-        } else if (t == 0) {
-            P.overflow[img] = 1;
+            Fdone += Fr;
+            __syncwarp();  // sbuf / obuf are rewritten by the next round (or the next chunk's stage)
         }
-        Fdone += Fr;
-        // (the next round's first barrier separates these sbuf reads from its sbuf writes)
-    }
-    if (t == 0) {
-        if (s_fault) P.overflow[img] = 1;
-        if (last_chunk) {
-            const unsigned long long total = ((Pc >> 5) << 2) + ob1 + s_ffx + Ftot;
-            P.out_len[img] = total;
-            if (total > P.out_cap) P.overflow[img] = 1;
+        if (lane == 0) {
+            if (fault) P.overflow[img] = 1;
+            if (last_chunk) {
+                const unsigned long long total = ((Pc >> 5) << 2) + ob1 + ffx + Ftot;
+                P.out_len[img] = total;
+                if (total > P.out_cap) P.overflow[img] = 1;
+            }
         }
+        __syncwarp();
     }
 }
 
@@ -520,7 +534,7 @@ static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
 static EntropyPlan plan_entropy(uint32_t n, uint64_t nblocks)
 {
     EntropyPlan p;
-    p.nchunks = (size_t)((nblocks + EB - 1) / EB);
+    p.nchunks = (size_t)((nblocks + CB - 1) / CB);
     size_t o = 0;
     p.off_st1 = o; o += a256((size_t)n * p.nchunks * 8);
     p.off_st2 = o; o += a256((size_t)n * p.nchunks * 8);
@@ -547,13 +561,13 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
 {
     const uint64_t nblocks = g.ny + 2 * g.nc;
     const EntropyPlan pl = plan_entropy(n, nblocks);
-    if ((uint64_t)n * pl.nchunks > 0x7FFFFFFFull)
+    if (nblocks > 0xFFFFFFFFull || (uint64_t)n * pl.nchunks > 0x7FFFFFFFull)
         return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "entropy stage: too many blocks per call");
     EntParams P;
     P.y = d_y; P.cb = d_cb; P.cr = d_cr; P.y_stride = y_stride; P.c_stride = c_stride;
     P.bpm = g.y_per_mcu + (g.has_chroma ? 2 : 0);
     P.y_per_mcu = g.y_per_mcu;
-    P.nblocks = nblocks;
+    P.nblocks = (uint32_t)nblocks;
     P.nchunks = (uint32_t)pl.nchunks;
     P.nimages = n;
     P.st_bits = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_st1);
@@ -579,7 +593,9 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
     }
     cudaStream_t st = ctx->stream;
     PIXO_CUDA(ctx, cudaMemsetAsync(d_scratch, 0, pl.zero_bytes, st));
-    k_huff<<<(unsigned)((size_t)n * pl.nchunks), EB, 0, st>>>(P, T);
+    const size_t want = ((size_t)n * pl.nchunks + HUFF_WARPS - 1) / HUFF_WARPS;
+    const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)ctx->sm_count * HUFF_CTAS_PER_SM);
+    k_huff<<<grid, 32 * HUFF_WARPS, 0, st>>>(P, T);
     ctx->launches += 1;
     PIXO_CUDA(ctx, cudaGetLastError());
     return 0;
