@@ -95,13 +95,20 @@ __device__ unsigned long long look_back(const unsigned long long *st, int chunk,
     uint32_t tl = 0, spins = 0;
     bool first = true;
     int base = chunk - 1;
+    // Chunks finish roughly in ticket order: wait (one lane, sleeping) until the nearest
+    // predecessor has published, then the wide scan below almost never has to retry.
+    if (lane == 0) {
+        while ((ld_status(st + base) >> 62) == 0) {
+            if (++spins > SPIN_LIMIT) break;
+            __nanosleep(100);
+        }
+    }
+    __syncwarp();
     while (base >= 0) {
         unsigned long long v[4];
+        const unsigned long long *p = st + (base - lane);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int idx = base - lane - 32 * k;
-            v[k] = idx >= 0 ? ld_status(st + idx) : ST_PFX;
-        }
+        for (int k = 0; k < 4; ++k) v[k] = base - lane - 32 * k >= 0 ? ld_status(p - 32 * k) : ST_PFX;
         unsigned long long step = 0;
         bool retry = false, done = false;
 #pragma unroll
@@ -284,7 +291,18 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
     const uint32_t total_chunks = P.nchunks * P.nimages;
     uint32_t spill[MAX_W - SLOT_W];  // words beyond SLOT_W (pathological blocks): local memory
 
+    // block `s` (scan order) of image `img`: its component array, index in it, table (0 lum / 1 chroma)
+    auto locate = [&](uint32_t img, uint32_t s, const int16_t *&arr, size_t &idx, int &tbl) {
+        const uint32_t m = s / P.bpm;
+        const uint32_t k = s - m * P.bpm;
+        if (k < P.y_per_mcu) { arr = P.y + (size_t)img * P.y_stride; idx = (size_t)m * P.y_per_mcu + k; tbl = 0; }
+        else if (k == P.y_per_mcu) { arr = P.cb + (size_t)img * P.c_stride; idx = m; tbl = 1; }
+        else { arr = P.cr + (size_t)img * P.c_stride; idx = m; tbl = 1; }
+    };
+
     for (;;) {
+        // (drawing the ticket a chunk ahead would hide the atomic's latency, but it delays that
+        // chunk's status by a whole chunk time and every successor waits on it: 3x slower)
         uint32_t id = 0;
         if (lane == 0) id = atomicAdd(P.ticket, 1u);
         id = __shfl_sync(0xffffffffu, id, 0);
@@ -300,14 +318,10 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         uint32_t L = 0, tail7 = 0;
         int nwt = 0;
         if (valid) {
-            const uint32_t m = s / P.bpm;
-            const uint32_t k = s - m * P.bpm;
             const int16_t *arr;
             size_t idx;
             int tbl;
-            if (k < P.y_per_mcu) { arr = P.y + (size_t)img * P.y_stride; idx = (size_t)m * P.y_per_mcu + k; tbl = 0; }
-            else if (k == P.y_per_mcu) { arr = P.cb + (size_t)img * P.c_stride; idx = m; tbl = 1; }
-            else { arr = P.cr + (size_t)img * P.c_stride; idx = m; tbl = 1; }
+            locate(img, s, arr, idx, tbl);
             const int prev_dc = idx ? arr[(idx - 1) * 64] : 0;
             const uint4 *src = reinterpret_cast<const uint4 *>(arr + idx * 64);
             uint32_t e0 = 0, e1 = 0;
@@ -495,14 +509,14 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             if (G + nr <= P.out_cap) {
                 uint8_t *gdst = outp + G - shb;  // 16-byte aligned
                 const uint32_t end = shb + nr;
-                for (uint32_t c16 = lane; c16 * 16 < end; c16 += 32) {
-                    const uint32_t lo_b = c16 * 16, hi_b = lo_b + 16;
-                    if (lo_b >= shb && hi_b <= end) {
-                        *reinterpret_cast<uint4 *>(gdst + lo_b) = *reinterpret_cast<const uint4 *>(sbuf + lo_b);
-                    } else {
-                        for (uint32_t i = max(lo_b, shb); i < min(hi_b, end); ++i) gdst[i] = sbuf[i];
-                    }
-                }
+                const uint32_t full_lo = (shb + 15u) >> 4, full_hi = end >> 4;  // whole 16-byte pieces
+                for (uint32_t c16 = full_lo + lane; c16 < full_hi; c16 += 32)
+                    *reinterpret_cast<uint4 *>(gdst + c16 * 16) = *reinterpret_cast<const uint4 *>(sbuf + c16 * 16);
+                // ragged head (lanes 0-15) and tail (lanes 16-31), one byte per lane
+                const uint32_t hb = (uint32_t)lane < 16u ? shb + lane : max(full_hi, full_lo) * 16u + (lane - 16u);
+                const bool in_head = (uint32_t)lane < 16u && hb < min(full_lo * 16u, end);
+                const bool in_tail = lane >= 16 && full_hi >= full_lo && hb < end;
+                if (in_head || in_tail) gdst[hb] = sbuf[hb];
             } else if (lane == 0) {
                 P.overflow[img] = 1;
             }
