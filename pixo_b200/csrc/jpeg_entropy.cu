@@ -58,13 +58,14 @@ struct EntParams {
 };
 
 constexpr int CB = 32;             // blocks per chunk == one warp
+static_assert(CB * 4 == 128, "the slot word stride is spelled out in code_block's PTX");
 constexpr int HUFF_WARPS = 4;      // warps per CTA (they only share the tables)
-constexpr int HUFF_CTAS_PER_SM = 7;
-constexpr int SLOT_W = 24;         // words of a block's code kept in shared memory (768 bits)
+constexpr int HUFF_CTAS_PER_SM = 6;
+constexpr int SLOT_W = 16;         // words of a block's code kept in shared memory (512 bits)
 constexpr int MAX_W = 54;          // worst case: 27 + 63 * 26 = 1665 bits
 constexpr int WIN_W = 256;         // stream words assembled per round (32 bytes per lane)
 constexpr int WIN_B = WIN_W * 4;
-constexpr int SBUF_B = 2 * WIN_B + 32;
+constexpr int SBUF_B = 2 * WIN_B + 48;    // stuffed bytes of a window + alignment slack + the head pad
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_PFX = 2ull << 62;
@@ -116,13 +117,11 @@ __device__ unsigned long long look_back(const unsigned long long *st, int chunk,
             const uint32_t flag = (uint32_t)(v[k] >> 62);
             const uint32_t inv = __ballot_sync(0xffffffffu, flag == 0);
             const uint32_t pm = __ballot_sync(0xffffffffu, flag == 2);
-            const int stop = pm ? __ffs(pm) - 1 : 31;           // nearest inclusive prefix, if any
-            if (inv & (0xffffffffu >> (31 - stop))) { retry = true; break; }
-            unsigned long long val = lane <= stop ? (v[k] & ST_VAL) : 0ull;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-            step += val;
-            if (pm) { done = true; break; }
+            const int stop = pm ? __ffs(pm) - 1 : 32;           // nearest inclusive prefix, if any
+            if (inv & ((2u << min(stop, 31)) - 1u)) { retry = true; break; }
+            // aggregates are small (a chunk's bits / bytes): one 32-bit warp reduction
+            step += __reduce_add_sync(0xffffffffu, lane < stop ? (uint32_t)v[k] : 0u);
+            if (pm) { step += __shfl_sync(0xffffffffu, v[k], stop) & ST_VAL; done = true; break; }
         }
         if (retry) {
             if (++spins > SPIN_LIMIT) { *fault = true; break; }
@@ -193,6 +192,26 @@ __device__ __forceinline__ uint32_t code_block(uint32_t M0, uint32_t M1, int dif
     uint32_t sp = sa_slot;
     const uint32_t sp_end = sa_slot + SLOT_W * CB * 4;
     auto put = [&](uint32_t vl, uint32_t n) {
+        if (!SPILL) {  // branch-free: a full word is stored under a predicate
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p, q;\n\t"
+                ".reg .b32 t, hi, lo, tot;\n\t"
+                "shr.b32 t, %4, %1;\n\t"
+                "or.b32 hi, %0, t;\n\t"
+                "shf.r.wrap.b32 lo, 0, %4, %1;\n\t"   // vl << (32 - filled); 0 when filled == 0
+                "add.u32 tot, %1, %5;\n\t"
+                "setp.ge.u32 p, tot, 32;\n\t"
+                "setp.lt.and.u32 q, %2, %3, p;\n\t"
+                "@q st.shared.u32 [%2], hi;\n\t"
+                "@p add.u32 %2, %2, 128;\n\t"
+                "selp.b32 %0, lo, hi, p;\n\t"
+                "and.b32 %1, tot, 31;\n\t"
+                "}"
+                : "+r"(acc), "+r"(filled), "+r"(sp)
+                : "r"(sp_end), "r"(vl), "r"(n));
+            return;
+        }
         const uint32_t hi = acc | (vl >> filled);
         const uint32_t lo = __funnelshift_r(0u, vl, filled);  // vl << (32 - filled); 0 when filled == 0
         const uint32_t total = filled + n;
@@ -255,10 +274,11 @@ __device__ __forceinline__ uint32_t warp_scan(uint32_t x, int lane, uint32_t *to
     return inc - x;
 }
 
-// Shared memory of one warp.  The coefficient stage is dead once the blocks are coded; the
-// stream window and the stuffed bytes reuse it.
+// Shared memory of one warp.  Two chunks are in flight (see k_huff), each with its own slots.
+// The coefficient stage is dead once a chunk's blocks are coded; the stream window and the
+// stuffed bytes reuse it.
 struct WarpMem {
-    uint32_t slot[SLOT_W * CB];
+    uint32_t slot[2][SLOT_W * CB];
     union {
         uint32_t stage[32 * CB];
         struct {
@@ -269,8 +289,26 @@ struct WarpMem {
     uint32_t tl[CB];
 };
 
-// Persistent kernel; every WARP works on its own: it draws a chunk of 32 blocks from the ticket
-// counter, codes it and emits its bytes with warp-level synchronisation only.
+// What a warp remembers about a chunk between its phases (lane-private unless noted).
+struct ChunkState {
+    uint32_t chunk, img;   // uniform
+    uint32_t L, o_t;       // this lane's block: code length, bit offset inside the chunk
+    int nwt;               // words the block occupies
+    uint32_t Lc, ctail;    // uniform: chunk bits, its last 7 bits
+    int buf;               // slot / spill buffer
+    unsigned long long Pc; // uniform: bits before the chunk (after phase A)
+    uint32_t tailin;       // uniform: the 7 bits before the chunk
+    uint32_t Ftot;         // uniform: 0xFF bytes the chunk owns
+    bool fault;
+};
+
+// Persistent kernel; every WARP works on its own: it draws chunks of 32 blocks from the ticket
+// counter and takes each through three phases with warp-level synchronisation only,
+//   W  code the blocks into slots, publish the chunk's bit count              (chain 1)
+//   A  look back for the bit offset, assemble + count 0xFF, publish the count  (chain 2)
+//   B  look back for the stuffed-byte offset, assemble again, emit
+// software-pipelined as  A(j) W(j+1) B(j):  a look-back runs a phase after the value it depends
+// on was published by this warp's neighbours in the chain, so it seldom has to wait for them.
 __global__ void __launch_bounds__(32 * HUFF_WARPS, HUFF_CTAS_PER_SM)
 k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
 {
@@ -283,45 +321,33 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         reinterpret_cast<uint32_t *>(&T)[i] = reinterpret_cast<const uint32_t *>(&Tp)[i];
     __syncthreads();
     WarpMem &M = wmem[threadIdx.x >> 5];
-    uint32_t *const slot = M.slot;
     uint32_t *const obuf = M.w.obuf;
     uint8_t *const sbuf = M.w.sbuf;
     const uint32_t sa_stage = (uint32_t)__cvta_generic_to_shared(M.stage) + 4u * lane;
-    const uint32_t sa_slot = (uint32_t)__cvta_generic_to_shared(M.slot) + 4u * lane;
     const uint32_t total_chunks = P.nchunks * P.nimages;
-    uint32_t spill[MAX_W - SLOT_W];  // words beyond SLOT_W (pathological blocks): local memory
+    uint32_t spill[2][MAX_W - SLOT_W];  // words beyond SLOT_W (long blocks): local memory
 
-    // block `s` (scan order) of image `img`: its component array, index in it, table (0 lum / 1 chroma)
-    auto locate = [&](uint32_t img, uint32_t s, const int16_t *&arr, size_t &idx, int &tbl) {
-        const uint32_t m = s / P.bpm;
-        const uint32_t k = s - m * P.bpm;
-        if (k < P.y_per_mcu) { arr = P.y + (size_t)img * P.y_stride; idx = (size_t)m * P.y_per_mcu + k; tbl = 0; }
-        else if (k == P.y_per_mcu) { arr = P.cb + (size_t)img * P.c_stride; idx = m; tbl = 1; }
-        else { arr = P.cr + (size_t)img * P.c_stride; idx = m; tbl = 1; }
-    };
-
-    for (;;) {
-        // (drawing the ticket a chunk ahead would hide the atomic's latency, but it delays that
-        // chunk's status by a whole chunk time and every successor waits on it: 3x slower)
-        uint32_t id = 0;
-        if (lane == 0) id = atomicAdd(P.ticket, 1u);
-        id = __shfl_sync(0xffffffffu, id, 0);
-        if (id >= total_chunks) break;
+    // ---- W: code the lane's block of chunk `id` into slot buffer `buf`, publish the bit count ----
+    auto phase_w = [&](uint32_t id, int buf, ChunkState &C) {
         // chunk-major dispensing: the n images' chains advance side by side
-        const uint32_t chunk = id / P.nimages, img = id - chunk * P.nimages;
-        const bool last_chunk = chunk == P.nchunks - 1;
-        const uint32_t s = chunk * CB + lane;
-        const bool valid = s < P.nblocks;
-        const int nv = (int)min((uint32_t)CB, P.nblocks - chunk * CB);
-
-        // ---- 1. code the block into its slot -----------------------------------------------
+        C.chunk = id / P.nimages;
+        C.img = id - C.chunk * P.nimages;
+        C.buf = buf;
+        C.fault = false;
+        const uint32_t s = C.chunk * CB + lane;
+        const int nv = (int)min((uint32_t)CB, P.nblocks - C.chunk * CB);
+        uint32_t *const slot = M.slot[buf];
         uint32_t L = 0, tail7 = 0;
         int nwt = 0;
-        if (valid) {
+        if (s < P.nblocks) {
+            const uint32_t m = s / P.bpm;
+            const uint32_t k = s - m * P.bpm;
             const int16_t *arr;
             size_t idx;
             int tbl;
-            locate(img, s, arr, idx, tbl);
+            if (k < P.y_per_mcu) { arr = P.y + (size_t)C.img * P.y_stride; idx = (size_t)m * P.y_per_mcu + k; tbl = 0; }
+            else if (k == P.y_per_mcu) { arr = P.cb + (size_t)C.img * P.c_stride; idx = m; tbl = 1; }
+            else { arr = P.cr + (size_t)C.img * P.c_stride; idx = m; tbl = 1; }
             const int prev_dc = idx ? arr[(idx - 1) * 64] : 0;
             const uint4 *src = reinterpret_cast<const uint4 *>(arr + idx * 64);
             uint32_t e0 = 0, e1 = 0;
@@ -338,37 +364,34 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
                 for (int j = 0; j < 32; ++j) M.stage[j * CB + lane] = w[j];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    e0 |= __vminu2(w[j], 0x00010001u) << j;
-                    e1 |= __vminu2(w[16 + j], 0x00010001u) << j;
+                    e0 += __vminu2(w[j], 0x00010001u) * (1u << j);       // disjoint bits: + is |
+                    e1 += __vminu2(w[16 + j], 0x00010001u) * (1u << j);
                 }
             }
             asm volatile("" ::: "memory");  // the stage is read back through ld.shared below
             const uint32_t M0 = interleave16(e0), M1 = interleave16(e1);  // bit i = coefficient i != 0
             const int diff = (int)(int16_t)(dc - prev_dc);
             const uint32_t sa_ac = (uint32_t)__cvta_generic_to_shared(&T.ac[tbl][0]);
+            const uint32_t sa_slot = (uint32_t)__cvta_generic_to_shared(slot) + 4u * lane;
             uint32_t acc;
-            L = code_block<false>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill, &acc);
-            if (L > SLOT_W * 32u)  // rare: run again, now keeping the words past the slot in local memory
-                L = code_block<true>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill, &acc);
+            L = code_block<false>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill[buf], &acc);
+            if (L > SLOT_W * 32u)  // long block: run again, keeping the words past the slot in local memory
+                L = code_block<true>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill[buf], &acc);
             asm volatile("" ::: "memory");  // slot words were written through st.shared
             const int nw = (int)(L >> 5), filled = (int)(L & 31u);
             nwt = nw;
             if (filled) {
-                if (nw < SLOT_W) slot[nw * CB + lane] = acc; else spill[nw - SLOT_W] = acc;
+                if (nw < SLOT_W) slot[nw * CB + lane] = acc; else spill[buf][nw - SLOT_W] = acc;
                 nwt = nw + 1;
             }
-            const uint32_t lastw = nw == 0 ? 0u : (nw - 1 < SLOT_W ? slot[(nw - 1) * CB + lane] : spill[nw - 1 - SLOT_W]);
+            const uint32_t lastw = nw == 0 ? 0u : (nw - 1 < SLOT_W ? slot[(nw - 1) * CB + lane] : spill[buf][nw - 1 - SLOT_W]);
             tail7 = __funnelshift_rc(acc, lastw, 32 - filled) & 0x7Fu;
         }
         M.tl[lane] = (L << 7) | tail7;
         __syncwarp();  // every lane is done with the stage; tl[] visible
-
-        // ---- 2. offsets: warp scan + look-back chain 1 -----------------------------------------
-        uint32_t Lc;
-        const uint32_t o_t = warp_scan(L, lane, &Lc);
-        unsigned long long *st1 = P.st_bits + (size_t)img * P.nchunks;
-        unsigned long long *st2 = P.st_ff + (size_t)img * P.nchunks;
-        bool fault = false;
+        C.L = L;
+        C.nwt = nwt;
+        C.o_t = warp_scan(L, lane, &C.Lc);
         uint32_t ctail = 0;
         if (lane == 0) {  // the chunk's last 7 bits (a block has >= 2 bits: at most 4 steps)
             int got = 0;
@@ -378,35 +401,37 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
                 ctail |= (x & ((1u << take) - 1u)) << got;
                 got += take;
             }
-            st_status(st1 + chunk, pack_status(chunk == 0 ? ST_PFX : ST_AGG, ctail, Lc));
+            st_status(P.st_bits + (size_t)C.img * P.nchunks + C.chunk,
+                      pack_status(C.chunk == 0 ? ST_PFX : ST_AGG, ctail, C.Lc));
         }
-        uint32_t tailin = 0;
-        unsigned long long Pc = 0;
-        if (chunk) {
-            Pc = look_back(st1, (int)chunk, lane, &tailin, &fault);
-            if (lane == 0) st_status(st1 + chunk, pack_status(ST_PFX, ctail, Pc + Lc));
-        }
-        const uint32_t q0 = (uint32_t)Pc & 31u;           // bit offset of the chunk inside window word 0
-        const uint32_t endbit = q0 + Lc;                  // window bit index one past the chunk
+        C.ctail = __shfl_sync(0xffffffffu, ctail, 0);
+        C.Pc = 0;
+        C.tailin = 0;
+        C.Ftot = 0;
+        __syncwarp();
+    };
+
+    // ---- assemble the chunk's stream window by window; count its 0xFF bytes (EMIT: and write) ----
+    // gbase: output index of the chunk's first owned byte (EMIT only).  Returns the 0xFF count.
+    auto sweep = [&](const ChunkState &C, bool emit, unsigned long long gbase) -> uint32_t {
+        const uint32_t *const slot = M.slot[C.buf];
+        const uint32_t *const spl = spill[C.buf];
+        const bool last_chunk = C.chunk == P.nchunks - 1;
+        const uint32_t q0 = (uint32_t)C.Pc & 31u;         // bit offset of the chunk inside window word 0
+        const uint32_t endbit = q0 + C.Lc;                // window bit index one past the chunk
         const uint32_t padc = last_chunk ? ((8u - (endbit & 7u)) & 7u) : 0u;   // 1-padding (bits.rs:261-272)
         const uint32_t ob0 = q0 >> 3;                     // owned window bytes [ob0, ob1)
         const uint32_t ob1 = (endbit >> 3) + (padc ? 1u : 0u);
         const int nrounds = max(1, (int)((ob1 + WIN_B - 1) / WIN_B));
-        uint8_t *outp = P.out + (size_t)img * P.out_cap;
-
+        uint8_t *outp = P.out + (size_t)C.img * P.out_cap;
         // per-lane constants of the funnel-shifted copy
-        const uint32_t D = q0 + o_t;
+        const uint32_t D = q0 + C.o_t;
         const int d0 = (int)(D >> 5), sh = (int)(D & 31u);
-        const int nd = L ? (int)((sh + L + 31u) >> 5) : 0;   // destination words
-
-        uint32_t Ftot = 0, Fdone = 0;
-        unsigned long long gbase = 0, ffx = 0;
-        const int iters = nrounds == 1 ? 1 : 2 * nrounds;  // >1 round: a counting sweep, then the emitting sweep
+        const int nd = C.L ? (int)((sh + C.L + 31u) >> 5) : 0;   // destination words
+        const int nwt = C.nwt;
+        uint32_t Fsum = 0;
 #pragma unroll 1
-        for (int it = 0; it < iters; ++it) {
-            const int r = it < nrounds ? it : it - nrounds;
-            const bool emit = nrounds == 1 || it >= nrounds;
-            // ---- 3. assemble window r ----------------------------------------------------------
+        for (int r = 0; r < nrounds; ++r) {
             for (int i = lane; i < WIN_W / 4; i += 32) reinterpret_cast<uint4 *>(obuf)[i] = make_uint4(0, 0, 0, 0);
             __syncwarp();
             {
@@ -423,10 +448,10 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
                         prev = cur;
                     }
                 } else {
-                    if (kb > 0 && kb <= nwt) prev = (kb - 1) < SLOT_W ? slot[(kb - 1) * CB + lane] : spill[kb - 1 - SLOT_W];
+                    if (kb > 0 && kb <= nwt) prev = (kb - 1) < SLOT_W ? slot[(kb - 1) * CB + lane] : spl[kb - 1 - SLOT_W];
                     for (int k = kb; k < ke; ++k) {
                         uint32_t cur = 0;
-                        if (k < nwt) cur = k < SLOT_W ? slot[k * CB + lane] : spill[k - SLOT_W];
+                        if (k < nwt) cur = k < SLOT_W ? slot[k * CB + lane] : spl[k - SLOT_W];
                         const uint32_t v = __funnelshift_r(cur, prev, sh);
                         uint32_t *dst = obuf + (d0 + k - wlo);
                         if (k == 0 || k == nd - 1) atomicOr(dst, v); else *dst = v;
@@ -435,68 +460,53 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
                 }
                 if (lane == 0) {
                     const uint32_t q = q0 & 7u;  // inherited bits of the straddling first byte
-                    if (r == 0 && q) atomicOr(&obuf[0], (tailin & ((1u << q) - 1u)) << (32u - q0));
+                    if (r == 0 && q) atomicOr(&obuf[0], (C.tailin & ((1u << q) - 1u)) << (32u - q0));
                     const int pw = (int)(endbit >> 5) - wlo;
                     if (padc && pw >= 0 && pw < WIN_W)
                         atomicOr(&obuf[pw], ((1u << padc) - 1u) << (32u - (endbit & 31u) - padc));
                 }
             }
             __syncwarp();
-            // ---- 4a. count the 0xFF bytes in this lane's 32 window bytes ---------------------------
+            // Count the 0xFF bytes in this lane's 32 window bytes.  No bounds: a window byte the
+            // chunk does not own is either untouched (0) or the unfinished last byte, whose low
+            // bits are still 0 - never 0xFF.
             const int wb0 = r * WIN_B;
             const int a = max((int)ob0 - wb0, 0), b = min((int)ob1 - wb0, WIN_B);
-            const int lo = max(32 * lane, a), hi = min(32 * lane + 32, b);
-            uint32_t cnt = 0;
-            if (hi > lo) {
-                for (int j = (lo >> 2) - 8 * lane; j < 8 && 32 * lane + 4 * j < hi; ++j) {
-                    const int wbyte = 32 * lane + 4 * j;
-                    uint32_t f = ff_bytes(obuf[8 * lane + j]);
-                    if (wbyte < lo || wbyte + 4 > hi) {
-                        uint32_t keep = 0;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (wbyte + i >= lo && wbyte + i < hi) keep |= 0x80000000u >> (8 * i);
-                        f &= keep;
-                    }
-                    cnt += __popc(f);
-                }
+            uint32_t wv[8];
+            {
+                const uint4 x = reinterpret_cast<const uint4 *>(obuf)[2 * lane];
+                const uint4 y = reinterpret_cast<const uint4 *>(obuf)[2 * lane + 1];
+                wv[0] = x.x; wv[1] = x.y; wv[2] = x.z; wv[3] = x.w; wv[4] = y.x; wv[5] = y.y; wv[6] = y.z; wv[7] = y.w;
             }
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cnt += __popc(ff_bytes(wv[j]));
             uint32_t Fr;
             const uint32_t ffb = warp_scan(cnt, lane, &Fr);
-            if (!emit) Ftot += Fr;
-            if (it == (nrounds == 1 ? 0 : nrounds - 1)) {
-                // ---- look-back chain 2: stuffed zeros before this chunk ------------------------------
-                if (nrounds == 1) Ftot = Fr;
-                if (lane == 0) st_status(st2 + chunk, pack_status(chunk == 0 ? ST_PFX : ST_AGG, 0, Ftot));
-                if (chunk) {
-                    uint32_t dummy;
-                    ffx = look_back(st2, (int)chunk, lane, &dummy, &fault);
-                    if (lane == 0) st_status(st2 + chunk, pack_status(ST_PFX, 0, ffx + Ftot));
-                }
-                gbase = (Pc >> 3) + ffx;  // output index of the first owned byte
-            }
-            if (!emit) continue;
-            // ---- 4b. stuffed bytes of this window -> sbuf -> global ------------------------------------
-            const unsigned long long G = gbase + (r == 0 ? 0u : (uint32_t)(wb0 - (int)ob0)) + Fdone;
-            const uint32_t nr = (uint32_t)max(b - a, 0) + Fr;
-            const uint32_t shb = (uint32_t)((reinterpret_cast<uintptr_t>(outp) + G) & 15u);
-            if (hi > lo) {
-                uint32_t dst = shb + (uint32_t)(lo - a) + ffb;
-                for (int j = (lo >> 2) - 8 * lane; j < 8 && 32 * lane + 4 * j < hi; ++j) {
-                    const int wbyte = 32 * lane + 4 * j;
-                    const uint32_t w = obuf[8 * lane + j];
-                    if (wbyte >= lo && wbyte + 4 <= hi && ff_bytes(w) == 0) {
-                        if ((dst & 3u) == 0) {
-                            *reinterpret_cast<uint32_t *>(sbuf + dst) = __byte_perm(w, 0, 0x0123);
-                        } else {
-                            sbuf[dst] = (uint8_t)(w >> 24); sbuf[dst + 1] = (uint8_t)(w >> 16);
-                            sbuf[dst + 2] = (uint8_t)(w >> 8); sbuf[dst + 3] = (uint8_t)w;
-                        }
-                        dst += 4;
-                    } else {
+            if (emit) {
+                // stuffed bytes of this window -> sbuf -> global
+                const unsigned long long G = gbase + (r == 0 ? 0u : (uint32_t)(wb0 - (int)ob0)) + Fsum;
+                const uint32_t nr = (uint32_t)max(b - a, 0) + Fr;
+                const uint32_t shb = (uint32_t)((reinterpret_cast<uintptr_t>(outp) + G) & 15u);
+                // Every lane with owned bytes emits its whole 32-byte piece (bytes outside the owned
+                // range land outside the part of sbuf that is copied out); sbuf index 16 + shb is
+                // the chunk's first owned byte of this window.
+                if (32 * lane < b) {
+                    uint32_t dst = 16u + shb + (uint32_t)(32 * lane) - (uint32_t)a + ffb;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            if (wbyte + i >= lo && wbyte + i < hi) {
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t w = wv[j];
+                        if (ff_bytes(w) == 0) {
+                            if ((dst & 3u) == 0) {
+                                *reinterpret_cast<uint32_t *>(sbuf + dst) = __byte_perm(w, 0, 0x0123);
+                            } else {
+                                sbuf[dst] = (uint8_t)(w >> 24); sbuf[dst + 1] = (uint8_t)(w >> 16);
+                                sbuf[dst + 2] = (uint8_t)(w >> 8); sbuf[dst + 3] = (uint8_t)w;
+                            }
+                            dst += 4;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
                                 const uint32_t byte = (w >> (24 - 8 * i)) & 0xFFu;
                                 sbuf[dst++] = (uint8_t)byte;
                                 if (byte == 0xFFu) sbuf[dst++] = 0;
@@ -504,34 +514,73 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
                         }
                     }
                 }
+                __syncwarp();
+                if (G + nr <= P.out_cap) {
+                    uint8_t *gdst = outp + G - shb;  // 16-byte aligned
+                    const uint32_t end = shb + nr;
+                    const uint32_t full_lo = (shb + 15u) >> 4, full_hi = end >> 4;  // whole 16-byte pieces
+                    const uint8_t *sb = sbuf + 16;
+                    for (uint32_t c16 = full_lo + lane; c16 < full_hi; c16 += 32)
+                        *reinterpret_cast<uint4 *>(gdst + c16 * 16) = *reinterpret_cast<const uint4 *>(sb + c16 * 16);
+                    // ragged head (lanes 0-15) and tail (lanes 16-31), one byte per lane
+                    const uint32_t hb = (uint32_t)lane < 16u ? shb + lane : max(full_hi, full_lo) * 16u + (lane - 16u);
+                    const bool in_head = (uint32_t)lane < 16u && hb < min(full_lo * 16u, end);
+                    const bool in_tail = lane >= 16 && full_hi >= full_lo && hb < end;
+                    if (in_head || in_tail) gdst[hb] = sb[hb];
+                } else if (lane == 0) {
+                    P.overflow[C.img] = 1;
+                }
             }
-            __syncwarp();
-            if (G + nr <= P.out_cap) {
-                uint8_t *gdst = outp + G - shb;  // 16-byte aligned
-                const uint32_t end = shb + nr;
-                const uint32_t full_lo = (shb + 15u) >> 4, full_hi = end >> 4;  // whole 16-byte pieces
-                for (uint32_t c16 = full_lo + lane; c16 < full_hi; c16 += 32)
-                    *reinterpret_cast<uint4 *>(gdst + c16 * 16) = *reinterpret_cast<const uint4 *>(sbuf + c16 * 16);
-                // ragged head (lanes 0-15) and tail (lanes 16-31), one byte per lane
-                const uint32_t hb = (uint32_t)lane < 16u ? shb + lane : max(full_hi, full_lo) * 16u + (lane - 16u);
-                const bool in_head = (uint32_t)lane < 16u && hb < min(full_lo * 16u, end);
-                const bool in_tail = lane >= 16 && full_hi >= full_lo && hb < end;
-                if (in_head || in_tail) gdst[hb] = sbuf[hb];
-            } else if (lane == 0) {
-                P.overflow[img] = 1;
-            }
-            Fdone += Fr;
-            __syncwarp();  // sbuf / obuf are rewritten by the next round (or the next chunk's stage)
+            Fsum += Fr;
+            __syncwarp();  // obuf / sbuf are rewritten by the next round, or by the next chunk's stage
         }
-        if (lane == 0) {
-            if (fault) P.overflow[img] = 1;
-            if (last_chunk) {
-                const unsigned long long total = ((Pc >> 5) << 2) + ob1 + ffx + Ftot;
-                P.out_len[img] = total;
-                if (total > P.out_cap) P.overflow[img] = 1;
-            }
+        if (emit && lane == 0 && last_chunk) {
+            const unsigned long long total = gbase - (C.Pc >> 3) + (((C.Pc >> 5) << 2) + ob1) + Fsum;
+            P.out_len[C.img] = total;
+            if (total > P.out_cap) P.overflow[C.img] = 1;
         }
-        __syncwarp();
+        return Fsum;
+    };
+
+    // ---- A: bit offset from chain 1, then the chunk's 0xFF count into chain 2 ------------------------
+    auto phase_a = [&](ChunkState &C) {
+        unsigned long long *st1 = P.st_bits + (size_t)C.img * P.nchunks;
+        unsigned long long *st2 = P.st_ff + (size_t)C.img * P.nchunks;
+        if (C.chunk) {
+            C.Pc = look_back(st1, (int)C.chunk, lane, &C.tailin, &C.fault);
+            if (lane == 0) st_status(st1 + C.chunk, pack_status(ST_PFX, C.ctail, C.Pc + C.Lc));
+        }
+        C.Ftot = sweep(C, false, 0);
+        if (lane == 0) st_status(st2 + C.chunk, pack_status(C.chunk == 0 ? ST_PFX : ST_AGG, 0, C.Ftot));
+    };
+    // ---- B: stuffed-byte offset from chain 2, then the bytes ------------------------------------------
+    auto phase_b = [&](ChunkState &C) {
+        unsigned long long *st2 = P.st_ff + (size_t)C.img * P.nchunks;
+        unsigned long long ffx = 0;
+        if (C.chunk) {
+            uint32_t dummy;
+            ffx = look_back(st2, (int)C.chunk, lane, &dummy, &C.fault);
+            if (lane == 0) st_status(st2 + C.chunk, pack_status(ST_PFX, 0, ffx + C.Ftot));
+        }
+        sweep(C, true, (C.Pc >> 3) + ffx);
+        if (lane == 0 && C.fault) P.overflow[C.img] = 1;
+    };
+
+    ChunkState cur, pend;
+    bool have_pend = false;
+    int buf = 0;
+    for (;;) {
+        uint32_t id = 0;
+        if (lane == 0) id = atomicAdd(P.ticket, 1u);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        const bool have = id < total_chunks;
+        if (have_pend) phase_a(pend);
+        if (have) phase_w(id, buf, cur);
+        if (have_pend) phase_b(pend);
+        if (!have) break;
+        pend = cur;
+        have_pend = true;
+        buf ^= 1;
     }
 }
 
