@@ -65,6 +65,7 @@ constexpr int SLOT_W = 16;         // words of a block's code kept in shared mem
 constexpr int MAX_W = 54;          // worst case: 27 + 63 * 26 = 1665 bits
 constexpr int WIN_W = 256;         // stream words assembled per round (32 bytes per lane)
 constexpr int WIN_B = WIN_W * 4;
+static_assert(WIN_B <= SLOT_W * CB * 4, "phase A parks the assembled window in the chunk's slot buffer");
 constexpr int SBUF_B = 2 * WIN_B + 48;    // stuffed bytes of a window + alignment slack + the head pad
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
@@ -89,12 +90,13 @@ __device__ __forceinline__ unsigned long long pack_status(unsigned long long fla
 
 // Exclusive prefix over chunks [0, chunk) of one image (whole warp; decoupled look-back, 128
 // predecessors per step, four per lane).  tail_in = the 7-bit tail published by chunk-1.
-__device__ unsigned long long look_back(const unsigned long long *st, int chunk, int lane,
-                                        uint32_t *tail_in, bool *fault)
+// Returns the prefix in the low 55 bits, tail_in in bits 55..61, bit 62 = the chain timed out.
+// (Inlined at both call sites: an out-of-line copy measured 2-15 % slower.)
+__device__ __forceinline__ unsigned long long look_back(const unsigned long long *st, int chunk, int lane)
 {
     unsigned long long excl = 0;
     uint32_t tl = 0, spins = 0;
-    bool first = true;
+    bool first = true, fault = false;
     int base = chunk - 1;
     // Chunks finish roughly in ticket order: wait (one lane, sleeping) until the nearest
     // predecessor has published, then the wide scan below almost never has to retry.
@@ -124,7 +126,7 @@ __device__ unsigned long long look_back(const unsigned long long *st, int chunk,
             if (pm) { step += __shfl_sync(0xffffffffu, v[k], stop) & ST_VAL; done = true; break; }
         }
         if (retry) {
-            if (++spins > SPIN_LIMIT) { *fault = true; break; }
+            if (++spins > SPIN_LIMIT) { fault = true; break; }
             __nanosleep(20);
             continue;
         }
@@ -133,8 +135,7 @@ __device__ unsigned long long look_back(const unsigned long long *st, int chunk,
         if (done) break;
         base -= 128;
     }
-    *tail_in = tl;
-    return excl;
+    return (excl & ST_VAL) | ((unsigned long long)tl << 55) | (fault ? 1ull << 62 : 0ull);
 }
 
 // bits 0..15 -> even positions, bits 16..31 -> odd positions (outer perfect shuffle)
@@ -247,7 +248,8 @@ __device__ __forceinline__ uint32_t code_block(uint32_t M0, uint32_t M1, int dif
             nprev = ~pos;
             // coefficient pos sits at stage word pos >> 1, half-word pos & 1
             const int c = lds_s16(sa_stage + pos * (CB * 2) - (pos & 1u) * (CB * 2 - 2));
-            while (run >= 16u) { put(zrl & 0xFFFF0000u, zrl & 31u); run -= 16u; }
+#pragma unroll 1
+            while (run >= 16u) { put(zrl & 0xFFFF0000u, zrl & 31u); run -= 16u; }  // rare: keep it small
             const uint32_t a = (uint32_t)abs(c);
             const uint32_t fl = msb_index(a);  // cat - 1
             const uint32_t e = lds_u32(sa_ac + 4u + run * 64u + fl * 4u);
@@ -299,6 +301,8 @@ struct ChunkState {
     unsigned long long Pc; // uniform: bits before the chunk (after phase A)
     uint32_t tailin;       // uniform: the 7 bits before the chunk
     uint32_t Ftot;         // uniform: 0xFF bytes the chunk owns
+    uint32_t ffb;          // 0xFF bytes before this lane's piece of the kept window
+    bool kept;             // uniform: phase A left the assembled (single) window in the slot buffer
     bool fault;
 };
 
@@ -408,12 +412,67 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         C.Pc = 0;
         C.tailin = 0;
         C.Ftot = 0;
+        C.ffb = 0;
+        C.kept = false;
         __syncwarp();
+    };
+
+    // ---- stuffed bytes of one window (this lane's 32 bytes in wv) -> sbuf -> global ----------------
+    // a, b: the chunk's owned byte range inside the window; ffb / Fr: 0xFF bytes before this
+    // lane's piece / in the whole window; G: output index of the window's first owned byte.
+    auto emit_window = [&](const ChunkState &C, const uint32_t (&wv)[8], uint32_t ffb, uint32_t Fr, int a, int b,
+                           unsigned long long G) {
+        uint8_t *outp = P.out + (size_t)C.img * P.out_cap;
+        const uint32_t nr = (uint32_t)max(b - a, 0) + Fr;
+        const uint32_t shb = (uint32_t)((reinterpret_cast<uintptr_t>(outp) + G) & 15u);
+        // Every lane with owned bytes emits its whole 32-byte piece (bytes outside the owned
+        // range land outside the part of sbuf that is copied out); sbuf index 16 + shb is
+        // the chunk's first owned byte of this window.
+        if (32 * lane < b) {
+            uint32_t dst = 16u + shb + (uint32_t)(32 * lane) - (uint32_t)a + ffb;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t w = wv[j];
+                if (ff_bytes(w) == 0) {
+                    if ((dst & 3u) == 0) {
+                        *reinterpret_cast<uint32_t *>(sbuf + dst) = __byte_perm(w, 0, 0x0123);
+                    } else {
+                        sbuf[dst] = (uint8_t)(w >> 24); sbuf[dst + 1] = (uint8_t)(w >> 16);
+                        sbuf[dst + 2] = (uint8_t)(w >> 8); sbuf[dst + 3] = (uint8_t)w;
+                    }
+                    dst += 4;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t byte = (w >> (24 - 8 * i)) & 0xFFu;
+                        sbuf[dst++] = (uint8_t)byte;
+                        if (byte == 0xFFu) sbuf[dst++] = 0;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (G + nr <= P.out_cap) {
+            uint8_t *gdst = outp + G - shb;  // 16-byte aligned
+            const uint32_t end = shb + nr;
+            const uint32_t full_lo = (shb + 15u) >> 4, full_hi = end >> 4;  // whole 16-byte pieces
+            const uint8_t *sb = sbuf + 16;
+            for (uint32_t c16 = full_lo + lane; c16 < full_hi; c16 += 32)
+                *reinterpret_cast<uint4 *>(gdst + c16 * 16) = *reinterpret_cast<const uint4 *>(sb + c16 * 16);
+            // ragged head (lanes 0-15) and tail (lanes 16-31), one byte per lane
+            const uint32_t hb = (uint32_t)lane < 16u ? shb + lane : max(full_hi, full_lo) * 16u + (lane - 16u);
+            const bool in_head = (uint32_t)lane < 16u && hb < min(full_lo * 16u, end);
+            const bool in_tail = lane >= 16 && full_hi >= full_lo && hb < end;
+            if (in_head || in_tail) gdst[hb] = sb[hb];
+        } else if (lane == 0) {
+            P.overflow[C.img] = 1;
+        }
+        __syncwarp();  // sbuf is rewritten by the next window, or by the next chunk's stage
     };
 
     // ---- assemble the chunk's stream window by window; count its 0xFF bytes (EMIT: and write) ----
     // gbase: output index of the chunk's first owned byte (EMIT only).  Returns the 0xFF count.
-    auto sweep = [&](const ChunkState &C, bool emit, unsigned long long gbase) -> uint32_t {
+    auto sweep = [&](ChunkState &C, bool emit, unsigned long long gbase) -> uint32_t {
         const uint32_t *const slot = M.slot[C.buf];
         const uint32_t *const spl = spill[C.buf];
         const bool last_chunk = C.chunk == P.nchunks - 1;
@@ -423,7 +482,6 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         const uint32_t ob0 = q0 >> 3;                     // owned window bytes [ob0, ob1)
         const uint32_t ob1 = (endbit >> 3) + (padc ? 1u : 0u);
         const int nrounds = max(1, (int)((ob1 + WIN_B - 1) / WIN_B));
-        uint8_t *outp = P.out + (size_t)C.img * P.out_cap;
         // per-lane constants of the funnel-shifted copy
         const uint32_t D = q0 + C.o_t;
         const int d0 = (int)(D >> 5), sh = (int)(D & 31u);
@@ -483,53 +541,17 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             for (int j = 0; j < 8; ++j) cnt += __popc(ff_bytes(wv[j]));
             uint32_t Fr;
             const uint32_t ffb = warp_scan(cnt, lane, &Fr);
+            if (!emit && nrounds == 1) {
+                // the usual case: keep the assembled window (in the chunk's slot buffer, which is
+                // not needed any more) so that phase B emits it without assembling again
+                uint4 *keep = reinterpret_cast<uint4 *>(M.slot[C.buf]);
+                keep[2 * lane] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                keep[2 * lane + 1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+                C.ffb = ffb;
+                C.kept = true;
+            }
             if (emit) {
-                // stuffed bytes of this window -> sbuf -> global
-                const unsigned long long G = gbase + (r == 0 ? 0u : (uint32_t)(wb0 - (int)ob0)) + Fsum;
-                const uint32_t nr = (uint32_t)max(b - a, 0) + Fr;
-                const uint32_t shb = (uint32_t)((reinterpret_cast<uintptr_t>(outp) + G) & 15u);
-                // Every lane with owned bytes emits its whole 32-byte piece (bytes outside the owned
-                // range land outside the part of sbuf that is copied out); sbuf index 16 + shb is
-                // the chunk's first owned byte of this window.
-                if (32 * lane < b) {
-                    uint32_t dst = 16u + shb + (uint32_t)(32 * lane) - (uint32_t)a + ffb;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t w = wv[j];
-                        if (ff_bytes(w) == 0) {
-                            if ((dst & 3u) == 0) {
-                                *reinterpret_cast<uint32_t *>(sbuf + dst) = __byte_perm(w, 0, 0x0123);
-                            } else {
-                                sbuf[dst] = (uint8_t)(w >> 24); sbuf[dst + 1] = (uint8_t)(w >> 16);
-                                sbuf[dst + 2] = (uint8_t)(w >> 8); sbuf[dst + 3] = (uint8_t)w;
-                            }
-                            dst += 4;
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const uint32_t byte = (w >> (24 - 8 * i)) & 0xFFu;
-                                sbuf[dst++] = (uint8_t)byte;
-                                if (byte == 0xFFu) sbuf[dst++] = 0;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                if (G + nr <= P.out_cap) {
-                    uint8_t *gdst = outp + G - shb;  // 16-byte aligned
-                    const uint32_t end = shb + nr;
-                    const uint32_t full_lo = (shb + 15u) >> 4, full_hi = end >> 4;  // whole 16-byte pieces
-                    const uint8_t *sb = sbuf + 16;
-                    for (uint32_t c16 = full_lo + lane; c16 < full_hi; c16 += 32)
-                        *reinterpret_cast<uint4 *>(gdst + c16 * 16) = *reinterpret_cast<const uint4 *>(sb + c16 * 16);
-                    // ragged head (lanes 0-15) and tail (lanes 16-31), one byte per lane
-                    const uint32_t hb = (uint32_t)lane < 16u ? shb + lane : max(full_hi, full_lo) * 16u + (lane - 16u);
-                    const bool in_head = (uint32_t)lane < 16u && hb < min(full_lo * 16u, end);
-                    const bool in_tail = lane >= 16 && full_hi >= full_lo && hb < end;
-                    if (in_head || in_tail) gdst[hb] = sb[hb];
-                } else if (lane == 0) {
-                    P.overflow[C.img] = 1;
-                }
+                emit_window(C, wv, ffb, Fr, a, b, gbase + (r == 0 ? 0u : (uint32_t)(wb0 - (int)ob0)) + Fsum);
             }
             Fsum += Fr;
             __syncwarp();  // obuf / sbuf are rewritten by the next round, or by the next chunk's stage
@@ -547,7 +569,10 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         unsigned long long *st1 = P.st_bits + (size_t)C.img * P.nchunks;
         unsigned long long *st2 = P.st_ff + (size_t)C.img * P.nchunks;
         if (C.chunk) {
-            C.Pc = look_back(st1, (int)C.chunk, lane, &C.tailin, &C.fault);
+            const unsigned long long lb = look_back(st1, (int)C.chunk, lane);
+            C.Pc = lb & ST_VAL;
+            C.tailin = (uint32_t)(lb >> 55) & 0x7Fu;
+            C.fault |= (lb >> 62) != 0;
             if (lane == 0) st_status(st1 + C.chunk, pack_status(ST_PFX, C.ctail, C.Pc + C.Lc));
         }
         C.Ftot = sweep(C, false, 0);
@@ -558,11 +583,29 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         unsigned long long *st2 = P.st_ff + (size_t)C.img * P.nchunks;
         unsigned long long ffx = 0;
         if (C.chunk) {
-            uint32_t dummy;
-            ffx = look_back(st2, (int)C.chunk, lane, &dummy, &C.fault);
+            const unsigned long long lb = look_back(st2, (int)C.chunk, lane);
+            ffx = lb & ST_VAL;
+            C.fault |= (lb >> 62) != 0;
             if (lane == 0) st_status(st2 + C.chunk, pack_status(ST_PFX, 0, ffx + C.Ftot));
         }
-        sweep(C, true, (C.Pc >> 3) + ffx);
+        const unsigned long long gbase = (C.Pc >> 3) + ffx;
+        if (C.kept) {
+            const uint32_t q0 = (uint32_t)C.Pc & 31u, endbit = q0 + C.Lc;
+            const bool last_chunk = C.chunk == P.nchunks - 1;
+            const uint32_t padc = last_chunk ? ((8u - (endbit & 7u)) & 7u) : 0u;
+            const uint32_t ob0 = q0 >> 3, ob1 = (endbit >> 3) + (padc ? 1u : 0u);
+            const uint4 *keep = reinterpret_cast<const uint4 *>(M.slot[C.buf]);
+            const uint4 x = keep[2 * lane], y = keep[2 * lane + 1];
+            const uint32_t wv[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+            emit_window(C, wv, C.ffb, C.Ftot, (int)ob0, (int)ob1, gbase);
+            if (lane == 0 && last_chunk) {
+                const unsigned long long total = ffx + (((C.Pc >> 5) << 2) + ob1) + C.Ftot;
+                P.out_len[C.img] = total;
+                if (total > P.out_cap) P.overflow[C.img] = 1;
+            }
+        } else {
+            sweep(C, true, gbase);
+        }
         if (lane == 0 && C.fault) P.overflow[C.img] = 1;
     };
 
