@@ -179,7 +179,12 @@ int pixo_b200_jpeg_entropy_encode(pixo_b200_ctx *ctx, const int16_t *y, const in
  * Semantics follow the default-feature build (`parallel` on): area <= 4096 forces Sub; for
  * height <= 32 AdaptiveFast is sticky on row 0's winner (:147-166).
  * out: height*(row_bytes+1).  adler32_out (optional): Adler-32 of `out`
- * (src/compress/adler32.rs:11-47), computed on the device in the same pass. */
+ * (src/compress/adler32.rs:11-47), computed on the device in the same pass.
+ * strategy may be OR-ed with PIXO_B200_PNG_OPTIMIZE_ALPHA: the pre-pass encode() runs before
+ * filtering when PngOptions::optimize_alpha is set (maybe_optimize_alpha, src/png/mod.rs:633-671:
+ * colour bytes of fully transparent pixels become 0; bytes_per_pixel 4 = Rgba, 2 = GrayAlpha,
+ * other pixel sizes are left alone) is applied on the fly while the rows are read. */
+#define PIXO_B200_PNG_OPTIMIZE_ALPHA 0x100u
 int pixo_b200_png_filter(pixo_b200_ctx *ctx, const uint8_t *data, uint32_t width,
                          uint32_t height, size_t row_bytes, uint32_t bytes_per_pixel,
                          uint32_t strategy, uint8_t *out, uint32_t *adler32_out);

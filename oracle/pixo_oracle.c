@@ -1020,6 +1020,20 @@ void po_apply_filters(const uint8_t *data, uint32_t width, uint32_t height, size
 }
 
 /* ------------------------------------------------------------------------------------------
+ * optimize_alpha pre-pass — src/png/mod.rs:633-671
+ * ---------------------------------------------------------------------------------------- */
+void po_optimize_alpha(uint8_t *data, size_t n_bytes, int color_type)
+{
+    if (color_type == PO_RGBA) {
+        for (size_t i = 0; i + 4 <= n_bytes; i += 4)
+            if (data[i + 3] == 0) data[i] = data[i + 1] = data[i + 2] = 0;
+    } else if (color_type == PO_GRAY_ALPHA) {
+        for (size_t i = 0; i + 2 <= n_bytes; i += 2)
+            if (data[i + 1] == 0) data[i] = 0;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Checksums — src/compress/adler32.rs:26-47, src/simd/fallback.rs:8-58
  * ---------------------------------------------------------------------------------------- */
 uint32_t po_adler32(const uint8_t *data, size_t n)

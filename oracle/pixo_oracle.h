@@ -127,6 +127,10 @@ void po_apply_filters(const uint8_t *data, uint32_t width, uint32_t height, size
                       size_t bpp, int strategy, int parallel_feature, uint8_t *out,
                       uint32_t row0, uint32_t row1);
 
+/* maybe_optimize_alpha (src/png/mod.rs:633-671), in place: color_type 3 (Rgba) / 1 (GrayAlpha)
+ * zero the colour bytes of pixels whose alpha is 0; other colour types are left alone. */
+void po_optimize_alpha(uint8_t *data, size_t n_bytes, int color_type);
+
 /* adler32 (src/compress/adler32.rs:26-47 == src/simd/fallback.rs:8-25) */
 uint32_t po_adler32(const uint8_t *data, size_t n);
 /* crc32 (src/simd/fallback.rs:27-58), adjacent known-answer only */

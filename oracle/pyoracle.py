@@ -96,6 +96,8 @@ def lib():
         L.po_apply_filters.restype = None
         L.po_apply_filters.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_size_t,
                                        C.c_int, C.c_int, u8p, C.c_uint32, C.c_uint32]
+        L.po_optimize_alpha.restype = None
+        L.po_optimize_alpha.argtypes = [u8p, C.c_size_t, C.c_int]
         L.po_adler32.restype = C.c_uint32
         L.po_adler32.argtypes = [u8p, C.c_size_t]
         L.po_crc32.restype = C.c_uint32
@@ -275,6 +277,13 @@ def apply_filters(data, width, height, bpp, strategy, row_bytes=None, parallel_f
     lib().po_apply_filters(_u8(d), width, height, row_bytes, bpp, strategy, int(parallel_feature),
                            _u8(out), rows[0], rows[1])
     return out
+
+
+def optimize_alpha(data, color_type) -> np.ndarray:
+    """maybe_optimize_alpha(data, color_type, true) (src/png/mod.rs:633-671); returns a copy."""
+    a = _as_u8(data).copy()
+    lib().po_optimize_alpha(_u8(a), a.size, int(color_type))
+    return a
 
 
 def adler32(data) -> int:

@@ -655,7 +655,7 @@ static int validate_png(pixo_b200_ctx *ctx, uint32_t width, uint32_t height, siz
         return set_error(ctx, PIXO_B200_ERR_IMAGE_TOO_LARGE, "Image dimensions %ux%u exceed maximum %u", width, height, 1u << 24);
     if (bpp < 1 || bpp > 4)
         return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "bytes_per_pixel %u not in 1..4", bpp);
-    if (strategy > PIXO_B200_FILTER_BIGRAMS)
+    if ((strategy & ~PIXO_B200_PNG_OPTIMIZE_ALPHA) > PIXO_B200_FILTER_BIGRAMS)
         return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "unknown filter strategy %u", strategy);
     return 0;
 }

@@ -91,6 +91,21 @@ __device__ __forceinline__ void stage_bytes(uint8_t *__restrict__ dst,
     for (int i = (nw << 2) + tid; i < len; i += PNG_THREADS) dst[i] = src[i];
 }
 
+// maybe_optimize_alpha (src/png/mod.rs:633-671) on one little-endian word of a row: Rgba (one
+// pixel per word, alpha = byte 3) or GrayAlpha (two pixels per word, alpha = bytes 1 and 3):
+// a pixel whose alpha is 0 becomes all-zero.
+template <int BPP>
+__device__ __forceinline__ uint32_t zero_transparent(uint32_t w)
+{
+    if (BPP == 4) return (w & 0xFF000000u) ? w : 0u;
+    const uint32_t keep = ((w & 0x0000FF00u) ? 0x0000FFFFu : 0u) | ((w & 0xFF000000u) ? 0xFFFF0000u : 0u);
+    return w & keep;
+}
+__device__ __forceinline__ uint32_t zero_transparent(uint32_t w, int oa /* 0, 2 or 4 */)
+{
+    return oa == 4 ? zero_transparent<4>(w) : oa == 2 ? zero_transparent<2>(w) : w;
+}
+
 struct PngParams {
     const uint8_t *data;
     size_t in_stride;
@@ -101,6 +116,7 @@ struct PngParams {
     uint32_t row_bytes_lo; // row_bytes (rows < 4 GiB)
     uint32_t bpp;
     uint32_t strategy;     // 0..4 fixed, 5/6 adaptive ladder, 7 adaptive-fast ladder
+    uint32_t opt_alpha;    // 0, or the pixel size (2 / 4) whose transparent pixels are zeroed first
     const uint8_t *forced; // per-image filter type decided earlier (sticky AdaptiveFast), or null
     uint8_t *decided;      // per-image: row0's decision is written here when non-null
     unsigned long long *acc; // per-image {A, B} accumulators (may be null)
@@ -132,6 +148,17 @@ __global__ void __launch_bounds__(PNG_THREADS) k_png_filter(const PngParams P)
     const uint32_t bpp = P.bpp;
     const uint32_t ashift = (4 - bpp) * 8;
     const int nseg = (int)((rb + segcap - 1) / segcap);
+    // optimize_alpha: rewrite the staged words (halo included; segments start on 16-byte
+    // multiples, so words never straddle pixels) before anyone reads them
+    auto fix_alpha = [&](int slen) {
+        if (!P.opt_alpha) return;
+        const int nwords = (16 + slen + 3) >> 2;
+        for (int k = tid; k < nwords; k += PNG_THREADS) {
+            reinterpret_cast<uint32_t *>(cur)[k] = zero_transparent(reinterpret_cast<uint32_t *>(cur)[k], (int)P.opt_alpha);
+            reinterpret_cast<uint32_t *>(prev)[k] = zero_transparent(reinterpret_cast<uint32_t *>(prev)[k], (int)P.opt_alpha);
+        }
+        __syncthreads();
+    };
 
     int filter = (int)P.strategy;
     if (P.forced) filter = P.forced[img];
@@ -167,7 +194,10 @@ __global__ void __launch_bounds__(PNG_THREADS) k_png_filter(const PngParams P)
                     stage_bytes(cur + 16, row + s0, slen, lo_b, hi_b, tid);
                     if (prow) stage_bytes(prev + 16, prow + s0, slen, lo_b, hi_b, tid);
                     else for (int i = tid; i < slen; i += PNG_THREADS) prev[16 + i] = 0;
+                    // zero the tail of the last word (defined data for the word-wise passes)
+                    for (int i = slen + tid; i < ((slen + 3) & ~3); i += PNG_THREADS) { cur[16 + i] = 0; prev[16 + i] = 0; }
                     __syncthreads();
+                    fix_alpha(slen);
                 }
                 const uint32_t *c32 = reinterpret_cast<const uint32_t *>(cur) + 4;
                 const uint32_t *p32 = reinterpret_cast<const uint32_t *>(prev) + 4;
@@ -237,6 +267,7 @@ __global__ void __launch_bounds__(PNG_THREADS) k_png_filter(const PngParams P)
                 // zero the tail of the last word so masked lanes read defined data
                 for (int i = slen + tid; i < ((slen + 3) & ~3); i += PNG_THREADS) { cur[16 + i] = 0; prev[16 + i] = 0; }
                 __syncthreads();
+                fix_alpha(slen);
             }
             const uint32_t *c32 = reinterpret_cast<const uint32_t *>(cur) + 4;
             const uint32_t *p32 = reinterpret_cast<const uint32_t *>(prev) + 4;
@@ -433,12 +464,15 @@ struct BandParams {
     uint32_t async16;          // rows are 16-byte aligned: cp.async path
 };
 
+
 __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
                  : "memory");
 }
 
+// OA: 0, or the pixel size (2 / 4) whose transparent pixels are zeroed as the rows are read
+template <int OA>
 __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(const BandParams P)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -498,8 +532,13 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
 
         auto operands = [&](uint32_t k, uint32_t &x, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &mask) {
             x = c32[k]; b = p32[k];
-            a = __funnelshift_r(c32[(int)k - 1], x, ashift);
-            c = __funnelshift_r(p32[(int)k - 1], b, ashift);
+            uint32_t xl = c32[(int)k - 1], bl = p32[(int)k - 1];
+            if (OA) {
+                x = zero_transparent<OA ? OA : 4>(x); b = zero_transparent<OA ? OA : 4>(b);
+                xl = zero_transparent<OA ? OA : 4>(xl); bl = zero_transparent<OA ? OA : 4>(bl);
+            }
+            a = __funnelshift_r(xl, x, ashift);
+            c = __funnelshift_r(bl, b, ashift);
             const int valid = (int)rb - 4 * (int)k;
             mask = valid >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - valid)));
         };
@@ -707,7 +746,8 @@ int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_strid
         return set_error(ctx, PIXO_B200_ERR_IMAGE_TOO_LARGE, "row_bytes too large");
     // apply_filters_with_row_bytes pre-rules, src/png/filter.rs:72-86
     const size_t area = (size_t)width * (size_t)height;
-    uint32_t strat = strategy;
+    uint32_t strat = strategy & 0xFFu;
+    const uint32_t oa = ((strategy & PIXO_B200_PNG_OPTIMIZE_ALPHA) && (bpp == 2 || bpp == 4)) ? bpp : 0u;
     if (area <= 4096 && (strat == PIXO_B200_FILTER_ADAPTIVE || strat == PIXO_B200_FILTER_ADAPTIVE_FAST ||
                          strat == PIXO_B200_FILTER_BIGRAMS))
         strat = PIXO_B200_FILTER_SUB;
@@ -738,7 +778,9 @@ int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_strid
     if (use_band) {
         static bool band_attr[64];
         if (!band_attr[ctx->device & 63]) {
-            PIXO_CUDA(ctx, cudaFuncSetAttribute(k_png_band, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            PIXO_CUDA(ctx, cudaFuncSetAttribute(k_png_band<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            PIXO_CUDA(ctx, cudaFuncSetAttribute(k_png_band<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            PIXO_CUDA(ctx, cudaFuncSetAttribute(k_png_band<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             band_attr[ctx->device & 63] = true;
         }
         const uint32_t nbands = (height + BAND_ROWS - 1) / BAND_ROWS;
@@ -754,7 +796,9 @@ int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_strid
             B.nbands = nbands;
             B.async16 = (row_bytes % 16 == 0 && in_stride % 16 == 0 &&
                          (reinterpret_cast<uintptr_t>(d_data) & 15) == 0) ? 1u : 0u;
-            k_png_band<<<dim3(nbands, nb), PNG_THREADS, band_smem, ctx->stream>>>(B);
+            if (oa == 4) k_png_band<4><<<dim3(nbands, nb), PNG_THREADS, band_smem, ctx->stream>>>(B);
+            else if (oa == 2) k_png_band<2><<<dim3(nbands, nb), PNG_THREADS, band_smem, ctx->stream>>>(B);
+            else k_png_band<0><<<dim3(nbands, nb), PNG_THREADS, band_smem, ctx->stream>>>(B);
             ctx->launches++;
             PIXO_CUDA(ctx, cudaGetLastError());
         }
@@ -771,6 +815,7 @@ int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_strid
         P.row_bytes_lo = (uint32_t)row_bytes;
         P.bpp = bpp;
         P.strategy = strat;
+        P.opt_alpha = oa;
         P.acc = d_adler ? acc + 2 * (size_t)i0 : nullptr;
         P.counter = counter + i0;
         P.adler_out = d_adler ? d_adler + i0 : nullptr;

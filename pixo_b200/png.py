@@ -29,6 +29,9 @@ class FilterStrategy(enum.IntEnum):
     Bigrams = 8
 
 
+OPTIMIZE_ALPHA = 0x100  # PIXO_B200_PNG_OPTIMIZE_ALPHA
+
+
 @dataclasses.dataclass
 class PngOptions:
     """The fields of pixo::png::PngOptions (src/png/mod.rs:41-118) the filter stage reads."""
@@ -36,6 +39,7 @@ class PngOptions:
     height: int = 0
     color_type: ColorType = ColorType.Rgba
     filter_strategy: FilterStrategy = FilterStrategy.Adaptive
+    optimize_alpha: bool = False   # applied on the fly (Rgba / GrayAlpha), src/png/mod.rs:633-671
 
 
 def _as_u8(data) -> np.ndarray:
@@ -57,7 +61,8 @@ def apply_filters_with_row_bytes(data, width, height, row_bytes, bytes_per_pixel
     ad = C.c_uint32()
     rc = _lib.load().pixo_b200_png_filter(ctx.handle, d.ctypes.data, int(width), int(height),
                                           int(row_bytes), int(bytes_per_pixel),
-                                          int(options.filter_strategy), out.ctypes.data,
+                                          int(options.filter_strategy) | (OPTIMIZE_ALPHA if options.optimize_alpha else 0),
+                                          out.ctypes.data,
                                           C.byref(ad) if with_adler else None)
     _lib.check(ctx.handle, rc)
     return (out, ad.value) if with_adler else out

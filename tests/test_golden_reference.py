@@ -41,18 +41,17 @@ def _png_parts(png):
     return ihdr, zlib.decompress(idat), struct.unpack(">I", idat[-4:])[0]
 
 
-def _png_filter_input(c, img):
+def _png_filter_input(c, img, po=None):
     """What pixo hands to filter::apply_filters for this fixture: presets 1/2 enable
     optimize_alpha (src/png/mod.rs:633-671); the inputs are chosen so no colour-type or palette
-    reduction applies (IHDR is asserted to keep the input colour type)."""
+    reduction applies (IHDR is asserted to keep the input colour type).  With `po` the pre-pass
+    is the oracle's (so the fixtures pin it too); without it the raw input is returned and the
+    caller asks the product to fuse the pre-pass."""
     bpp = (1, 2, 3, 4)[c["ct"]]
-    src = img.copy().reshape(-1, bpp)
-    if c["preset"] in (1, 2):
-        if c["ct"] == 3:
-            src[src[:, 3] == 0, :3] = 0
-        elif c["ct"] == 1:
-            src[src[:, 1] == 0, :1] = 0
-    return src.reshape(-1), bpp
+    src = img.copy().reshape(-1)
+    if po is not None and c["preset"] in (1, 2):
+        src = po.optimize_alpha(src, c["ct"])
+    return src, bpp
 
 
 def test_manifest_is_complete():
@@ -75,7 +74,7 @@ def test_oracle_reproduces_pixo_png_filter_stream(po, c):
     assert ihdr[:2] == (c["w"], c["h"])
     if (ihdr[2], ihdr[3]) != (8, (0, 4, 2, 6)[c["ct"]]):
         pytest.skip("pixo's lossless palette/colour-type reduction rewrote this tiny input (outside the filter path)")
-    src, bpp = _png_filter_input(c, img)
+    src, bpp = _png_filter_input(c, img, po)
     # the wasm build has no `parallel` feature: always the sequential loop (sticky AdaptiveFast)
     mine = po.apply_filters(src, c["w"], c["h"], bpp, PNG_STRATEGY[c["preset"]], parallel_feature=False)
     assert mine.tobytes() == raw
@@ -124,7 +123,9 @@ def test_gpu_reproduces_pixo_png_filter_stream(gpu_ctx, c):
         pytest.skip("pixo's lossless palette/colour-type reduction rewrote this tiny input")
     src, bpp = _png_filter_input(c, img)
     st = FilterStrategy(PNG_STRATEGY[c["preset"]])
-    got, ad = png.apply_filters(src, c["w"], c["h"], bpp, PngOptions(c["w"], c["h"], ColorType(c["ct"]), st),
+    # presets 1/2 set optimize_alpha: the product applies it on the fly to the raw input
+    got, ad = png.apply_filters(src, c["w"], c["h"], bpp,
+                                PngOptions(c["w"], c["h"], ColorType(c["ct"]), st, c["preset"] in (1, 2)),
                                 with_adler=True, ctx=gpu_ctx)
     assert got.tobytes() == raw
     assert ad == adler

@@ -120,6 +120,13 @@ def test_png_filter_known_answers(po):
     assert po.score_filter(b"\xff" * 1000) == 1000
 
 
+def test_optimize_alpha_known_answer(po):
+    # src/png/mod.rs:2053-2065 (test_optimize_alpha_zeroes_color) + the GrayAlpha arm :662-668
+    assert po.optimize_alpha([10, 20, 30, 0, 1, 2, 3, 255], 3).tolist() == [0, 0, 0, 0, 1, 2, 3, 255]
+    assert po.optimize_alpha([9, 0, 7, 1], 1).tolist() == [0, 0, 7, 1]
+    assert po.optimize_alpha([9, 0, 7], 2).tolist() == [9, 0, 7]       # Rgb / Gray: untouched
+
+
 def test_small_image_uses_sub(po):
     # src/png/filter.rs:1070 (area <= 4096 forces Sub for the adaptive strategies)
     img = po.gen_noise(64, 64, 4, 3)

@@ -35,6 +35,26 @@ def test_filters_match_oracle(po, gpu_ctx, w, h, bpp):
             assert ad == po.adler32(ref) == zlib.adler32(ref.tobytes())
 
 
+@pytest.mark.parametrize("ct,bpp", [(3, 4), (1, 2), (2, 3)])
+@pytest.mark.parametrize("w,h", [(3, 2), (65, 64), (100, 33), (300, 20), (1000, 70), (4099, 35)])
+def test_optimize_alpha_fused(po, gpu_ctx, w, h, ct, bpp):
+    """PngOptions::optimize_alpha (maybe_optimize_alpha, src/png/mod.rs:633-671) fused into the row
+    reads: same stream as the oracle's pre-pass followed by the plain filter; Rgb is untouched."""
+    rng = np.random.default_rng(w * 31 + h)
+    img = rng.integers(0, 256, (h, w, bpp), dtype=np.uint8)
+    if bpp in (2, 4):
+        img[..., -1] = np.where(rng.random((h, w)) < 0.4, 0, img[..., -1])   # many transparent pixels
+    img = img.reshape(-1)
+    pre = po.optimize_alpha(img, ct)
+    assert (bpp == 3) == np.array_equal(pre, img)
+    for st in STRATS:
+        opts = PngOptions(w, h, ColorType(ct), st, True)
+        got, ad = png.apply_filters(img, w, h, bpp, opts, with_adler=True, ctx=gpu_ctx)
+        ref = po.apply_filters(pre, w, h, bpp, int(st))
+        assert np.array_equal(got, ref), (st, np.flatnonzero(got != ref)[:5])
+        assert ad == zlib.adler32(ref.tobytes())
+
+
 def test_sticky_adaptive_fast_small_height(po, gpu_ctx):
     # height <= 32 takes the sequential path where AdaptiveFast reuses row 0's winner
     for w, h in ((300, 32), (300, 20), (5000, 2)):
