@@ -68,6 +68,7 @@ constexpr int WIN_B = WIN_W * 4;
 static_assert(WIN_B <= SLOT_W * CB * 4, "phase A parks the assembled window in the chunk's slot buffer");
 constexpr int SBUF_B = 2 * WIN_B + 48;    // stuffed bytes of a window + alignment slack + the head pad
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
+constexpr int LB_GROUPS = 4;       // look-back window: 32 * LB_GROUPS predecessors per step (8 measured slower)
 
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_PFX = 2ull << 62;
 constexpr unsigned long long ST_VAL = (1ull << 55) - 1;
@@ -108,14 +109,14 @@ __device__ __forceinline__ unsigned long long look_back(const unsigned long long
     }
     __syncwarp();
     while (base >= 0) {
-        unsigned long long v[4];
+        unsigned long long v[LB_GROUPS];
         const unsigned long long *p = st + (base - lane);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = base - lane - 32 * k >= 0 ? ld_status(p - 32 * k) : ST_PFX;
+        for (int k = 0; k < LB_GROUPS; ++k) v[k] = base - lane - 32 * k >= 0 ? ld_status(p - 32 * k) : ST_PFX;
         unsigned long long step = 0;
         bool retry = false, done = false;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < LB_GROUPS; ++k) {
             const uint32_t flag = (uint32_t)(v[k] >> 62);
             const uint32_t inv = __ballot_sync(0xffffffffu, flag == 0);
             const uint32_t pm = __ballot_sync(0xffffffffu, flag == 2);
@@ -133,7 +134,7 @@ __device__ __forceinline__ unsigned long long look_back(const unsigned long long
         excl += step;
         if (first) { tl = __shfl_sync(0xffffffffu, (uint32_t)(v[0] >> 55) & 0x7Fu, 0); first = false; }
         if (done) break;
-        base -= 128;
+        base -= 32 * LB_GROUPS;
     }
     return (excl & ST_VAL) | ((unsigned long long)tl << 55) | (fault ? 1ull << 62 : 0ull);
 }
@@ -236,24 +237,31 @@ __device__ __forceinline__ uint32_t code_block(uint32_t M0, uint32_t M1, int dif
     }
     const uint32_t zrl = lds_u32(sa_ac + 0xF0 * 4), eob = lds_u32(sa_ac);
     uint32_t nprev = ~0u;  // -(previous position) - 1
+    uint32_t kOne, kNeg2;  // opaque to the compiler, so they stay in registers across the loop
+    asm volatile("mov.b32 %0, 1;" : "=r"(kOne));
+    asm volatile("mov.b32 %0, -2;" : "=r"(kNeg2));
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         uint32_t mb = __brev(half ? M1 : (M0 & ~1u));  // scan order == descending bit index
         const uint32_t top = half * 32 + 31;
         while (mb) {
             const uint32_t f = msb_index(mb);
-            mb &= ~(1u << f);
+            mb &= ~(kOne << f);
             const uint32_t pos = top - f;
             uint32_t run = pos + nprev;
             nprev = ~pos;
-            // coefficient pos sits at stage word pos >> 1, half-word pos & 1
-            const int c = lds_s16(sa_stage + pos * (CB * 2) - (pos & 1u) * (CB * 2 - 2));
+            // coefficient pos sits at stage word pos >> 1, half-word pos & 1:
+            // address = stage + pos * 64 - (pos & 1) * 62, spelled as two multiply-adds
+            uint32_t caddr;
+            asm("{\n\t.reg .b32 h, x;\n\tand.b32 h, %1, 1;\n\tmad.lo.u32 x, %1, 64, %2;\n\tmad.lo.u32 %0, h, -62, x;\n\t}"
+                : "=r"(caddr) : "r"(pos), "r"(sa_stage));
+            const int c = lds_s16(caddr);
 #pragma unroll 1
             while (run >= 16u) { put(zrl & 0xFFFF0000u, zrl & 31u); run -= 16u; }  // rare: keep it small
             const uint32_t a = (uint32_t)abs(c);
             const uint32_t fl = msb_index(a);  // cat - 1
             const uint32_t e = lds_u32(sa_ac + 4u + run * 64u + fl * 4u);
-            const uint32_t amp = a ^ (~(0xFFFFFFFEu << fl) & (uint32_t)(c >> 31));
+            const uint32_t amp = a ^ (~(kNeg2 << fl) & (uint32_t)(c >> 31));
             const uint32_t n = e & 31u;
             put((e & 0xFFFF0000u) | (amp << (32u - n)), n);
         }
