@@ -17,6 +17,9 @@
 #include <cuda.h>
 #include <string.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pixo {
@@ -714,17 +717,15 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
 }
 
 // =========================================================================================
-// K2: RGB 4:4:4 (192 threads: warps 0-1 = Y, 2-3 = Cb, 4-5 = Cr of the same 64 blocks) and
-// Gray (64 threads).  CTA = 64 blocks of one block row; every warp owns 32 consecutive blocks of
-// one component, runs the same packed block pipeline as K1 and flushes its 4 KB stage with
-// coalesced stores.
+// K2: RGB 4:4:4 (warp-autonomous, below) and Gray (64 threads, CTA = 64 blocks of one block
+// row; every warp owns 32 consecutive blocks, runs the same packed block pipeline as K1 and
+// flushes its 4 KB stage with coalesced stores).
 // =========================================================================================
 constexpr int K2_BLOCKS = 64;
 
-// 8 RGB pixels in six words -> (value - 128) as float for component `comp` (0 Y, 1 Cb, 2 Cr)
-__device__ __forceinline__ void comp_row8(const uint32_t (&w)[6], int comp, float (&v)[8])
+// 8 RGB pixels in six words -> the eight raw 4-byte windows (r,g,b,next r) the dot products read
+__device__ __forceinline__ void rgb_windows8(const uint32_t (&w)[6], uint32_t (&win)[8])
 {
-    uint32_t win[8];
     win[0] = w[0];
     win[1] = __funnelshift_r(w[0], w[1], 24);
     win[2] = __funnelshift_r(w[1], w[2], 16);
@@ -733,74 +734,156 @@ __device__ __forceinline__ void comp_row8(const uint32_t (&w)[6], int comp, floa
     win[5] = __funnelshift_r(w[3], w[4], 24);
     win[6] = __funnelshift_r(w[4], w[5], 16);
     win[7] = w[5] >> 8;
+}
+// ... -> Y - 128 as float
+__device__ __forceinline__ void y_row8(const uint32_t (&w)[6], float (&v)[8])
+{
+    uint32_t win[8];
+    rgb_windows8(w, win);
+#pragma unroll
+    for (int x = 0; x < 8; ++x)
+        v[x] = byte1_to_float_minus(__dp4a(win[x], 0x001D964Du, 128u), 8388736.0f);
+}
+// ... -> Cb - 128 / Cr - 128 as float; wgt = 0x0080552B (Cb) or 0x00156B80 (Cr), see ycc_row8
+__device__ __forceinline__ void c_row8(const uint32_t (&w)[6], uint32_t wgt, float (&v)[8])
+{
+    uint32_t win[8];
+    rgb_windows8(w, win);
 #pragma unroll
     for (int x = 0; x < 8; ++x) {
-        if (comp == 0) {
-            const uint32_t ys = __dp4a(win[x], 0x001D964Du, 128u);
-            v[x] = byte1_to_float_minus(ys, 8388736.0f);              // y - 128
-        } else {
-            // byte 1 of u = 256 - c (c = cb or cr before the clamp); c <= 255 <=> u >= -65280
-            const int u = max(dp4a_us(win[x], comp == 1 ? 0x0080552Bu : 0x00156B80u, -32641), -65280);
-            v[x] = FSUB(8388736.0f, __uint_as_float(__byte_perm((uint32_t)u, 0x4B000000u, 0x7651)));  // c - 128
-        }
+        // byte 1 of u = 256 - c (c = cb or cr before the clamp); c <= 255 <=> u >= -65280
+        const int u = max(dp4a_us(win[x], wgt, -32641), -65280);
+        v[x] = FSUB(8388736.0f, __uint_as_float(__byte_perm((uint32_t)u, 0x4B000000u, 0x7651)));  // c - 128
     }
 }
 
+// K2 (4:4:4), on K1's skeleton: persistent warp-autonomous workers, no CTA barrier.  A unit is
+// 32 blocks of one block row (256 x 8 pixels, 6 KB), fetched by one 3-D TMA into one of the
+// warp's TWO tile buffers - the next unit's pixels stream in while this one is transformed (all
+// three component passes read the same RGB tile, so it cannot double as the output stage the way
+// K1's half tiles do).  Lane = block; pass c converts the lane's 8x8 pixels to component c and
+// runs the packed DCT/quantiser; the warp's 4 KB stage goes out as 512-byte coalesced stores.
+constexpr int K4_WARPS = 4;
+constexpr int K4_THREADS = K4_WARPS * 32;
+constexpr int K4_ROW_B = 32 * 8 * 3;           // 768 bytes per tile row
+constexpr int K4_TILE_BYTES = 8 * K4_ROW_B;    // 6 KB
+
+struct __align__(128) K4WarpSmem {
+    uint8_t tile[2][K4_TILE_BYTES];
+    uint4 stage[256];
+    uint64_t bar[2];
+};
+
+struct __align__(128) K4Smem {
+    K4WarpSmem w[K4_WARPS];
+    QuantSmem q;
+};
+
+// K1Params with mcus_x / mcus_y = blocks per row / block rows, units_x = units per block row
+#ifndef K4_MIN_BLOCKS
+#define K4_MIN_BLOCKS 3
+#endif
 template <bool ZIGZAG>
-__global__ void __launch_bounds__(192)
-k_jpeg_444(const uint8_t *__restrict__ pixels, size_t pixel_stride, uint32_t w, uint32_t h,
-           uint32_t blocks_x, uint32_t tiles_x, int16_t *__restrict__ yout, size_t y_stride,
-           int16_t *__restrict__ cbout, int16_t *__restrict__ crout, size_t c_stride,
-           const __grid_constant__ QuantTab qt, const float zero_lo, const float zero_hi)
+__global__ void __launch_bounds__(K4_THREADS, K4_MIN_BLOCKS)
+k_jpeg_444(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab qt,
+           const __grid_constant__ CUtensorMap tmap)
 {
-    constexpr int TB = K2_BLOCKS * 8 * 3;  // 1536
-    __shared__ __align__(16) uint8_t tile[8 * TB];
-    __shared__ __align__(16) uint4 stage[6][256];
-    __shared__ QuantSmem qs;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    K4Smem &S = *reinterpret_cast<K4Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tx = blockIdx.x % tiles_x;
-    const uint32_t brow = blockIdx.x / tiles_x;
-    const uint32_t img = blockIdx.y;
-    const uint8_t *image = pixels + (size_t)img * pixel_stride;
-    fill_quant_smem(&qs, qt, 1.0f, tid, 192);
-    load_tile<3, 8, K2_BLOCKS * 8, 192>(tile, image, w, h, tx * (K2_BLOCKS * 8), brow * 8, tid);
+    K4WarpSmem &WS = S.w[warp];
+    fill_quant_smem(&S.q, qt, 1.0f, tid, K4_THREADS);
+    if (lane == 0) {
+        mbar_init(&WS.bar[0], 1);
+        mbar_init(&WS.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
-    const int comp = warp >> 1;            // warp-uniform: 0 = Y, 1 = Cb, 2 = Cr
-    const int j = (warp & 1) * 32 + lane;  // block within the tile
-    const uint32_t b0 = tx * K2_BLOCKS;
-    const bool active = b0 + j < blocks_x;
-    const f2 zero2 = pk(zero_lo, zero_hi);
-    if (active) {
-        f2 R[4][8];
-        const uint8_t *base = tile + j * 24;
-#pragma unroll
-        for (int rp = 0; rp < 4; ++rp) {
-            float v0[8], v1[8];
-            {
-                const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2) * TB);
-                const uint2 a = p[0], b = p[1], c = p[2];
-                const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-                comp_row8(wds, comp, v0);
-            }
-            {
-                const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2 + 1) * TB);
-                const uint2 a = p[0], b = p[1], c = p[2];
-                const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-                comp_row8(wds, comp, v1);
-            }
-#pragma unroll
-            for (int x = 0; x < 8; ++x) R[rp][x] = pk(v0[x], v1[x]);
+    const f2 zero2 = pk(P.zero[0], P.zero[1]);
+    const uint64_t units_per_img = (uint64_t)P.mcus_y * P.units_x;
+    const uint64_t nunits = units_per_img * P.n_images;
+    const uint64_t stride = (uint64_t)gridDim.x * K4_WARPS;
+    uint32_t phase = 0;  // bit b = parity to wait for on bar[b]
+
+    auto decode = [&](uint64_t u, uint32_t &img, uint32_t &by, uint32_t &ux) {
+        img = (uint32_t)(u / units_per_img);
+        const uint32_t rem = (uint32_t)(u - (uint64_t)img * units_per_img);
+        by = rem / P.units_x;
+        ux = rem - by * P.units_x;
+    };
+    auto unit_by_tma = [&](uint32_t by) { return P.use_tma && (by * 8 + 8 <= P.h); };
+    auto issue_tma = [&](uint64_t u_, int b) {
+        uint32_t img_, by_, ux_;
+        decode(u_, img_, by_, ux_);
+        if (unit_by_tma(by_)) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&WS.bar[b], K4_TILE_BYTES);
+            tma_load_3d(WS.tile[b], &tmap, (int)(ux_ * (K4_ROW_B / 8)), (int)(by_ * 8), (int)img_, &WS.bar[b]);
         }
-        dct_quant_store_x2<ZIGZAG>(R, comp == 0 ? qs.lum : qs.chr, stage[warp] + lane * 8, lane & 7, zero2);
+    };
+
+    uint64_t u = (uint64_t)blockIdx.x * K4_WARPS + warp;
+    int b = 0;
+    if (u < nunits && lane == 0) issue_tma(u, 0);
+    for (; u < nunits; u += stride, b ^= 1) {
+        uint32_t img, by, ux;
+        decode(u, img, by, ux);
+        if (lane == 0 && u + stride < nunits) issue_tma(u + stride, b ^ 1);  // that buffer was released below
+        if (unit_by_tma(by)) {
+            mbar_wait(&WS.bar[b], (phase >> b) & 1u);
+            phase ^= 1u << b;
+        } else {
+            const uint8_t *image = P.pixels + (size_t)img * P.pixel_stride;
+            warp_load_tile_rgb<8, 256>(WS.tile[b], image, P.w, P.h, ux * 256, by * 8, lane);
+            __syncwarp();
+        }
+        const uint32_t bx0 = ux * 32;
+        const bool active = bx0 + lane < P.mcus_x;
+        const uint8_t *base = WS.tile[b] + lane * 24;
+#pragma unroll 1
+        for (int comp = 0; comp < 3; ++comp) {
+            if (active) {
+                f2 R[4][8];
+                auto row_words = [&](int r, uint32_t (&wds)[6]) {
+                    const uint2 *p = reinterpret_cast<const uint2 *>(base + r * K4_ROW_B);
+                    const uint2 a = p[0], c1 = p[1], c2 = p[2];
+                    wds[0] = a.x; wds[1] = a.y; wds[2] = c1.x; wds[3] = c1.y; wds[4] = c2.x; wds[5] = c2.y;
+                };
+                // the component is decided ONCE per pass, not per pixel: two straight-line fills
+                if (comp == 0) {
+#pragma unroll
+                    for (int rp = 0; rp < 4; ++rp) {
+                        float v0[8], v1[8];
+                        uint32_t wa[6], wb[6];
+                        row_words(rp * 2, wa); row_words(rp * 2 + 1, wb);
+                        y_row8(wa, v0); y_row8(wb, v1);
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) R[rp][x] = pk(v0[x], v1[x]);
+                    }
+                } else {
+                    const uint32_t wgt = comp == 1 ? 0x0080552Bu : 0x00156B80u;
+#pragma unroll
+                    for (int rp = 0; rp < 4; ++rp) {
+                        float v0[8], v1[8];
+                        uint32_t wa[6], wb[6];
+                        row_words(rp * 2, wa); row_words(rp * 2 + 1, wb);
+                        c_row8(wa, wgt, v0); c_row8(wb, wgt, v1);
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) R[rp][x] = pk(v0[x], v1[x]);
+                    }
+                }
+                dct_quant_store_x2<ZIGZAG>(R, comp == 0 ? S.q.lum : S.q.chr, WS.stage + lane * 8, lane & 7, zero2);
+            }
+            int16_t *arr = comp == 0 ? P.y + (size_t)img * P.y_stride
+                                     : (comp == 1 ? P.cb : P.cr) + (size_t)img * P.c_stride;
+            uint4 *dbase = reinterpret_cast<uint4 *>(arr + ((size_t)by * P.mcus_x + bx0) * 64);
+            flush_stage(
+                WS.stage, lane, [](int s) { return s & 7; },
+                [&](int s) -> uint4 * { return bx0 + s < P.mcus_x ? dbase + s * 8 : nullptr; });
+        }
+        __syncwarp();  // every lane is done with tile[b]: the TMA issued next iteration may refill it
     }
-    int16_t *arr = comp == 0 ? yout + (size_t)img * y_stride
-                             : (comp == 1 ? cbout : crout) + (size_t)img * c_stride;
-    const uint32_t first = b0 + (warp & 1) * 32;
-    uint4 *dbase = reinterpret_cast<uint4 *>(arr + ((size_t)brow * blocks_x + first) * 64);
-    flush_stage(
-        stage[warp], lane, [](int s) { return s & 7; },
-        [&](int s) -> uint4 * { return first + s < blocks_x ? dbase + s * 8 : nullptr; });
 }
 
 template <bool ZIGZAG>
@@ -1018,7 +1101,7 @@ EncodeTiledFn tensor_map_encoder()
 
 // 3-D view of a batch of interleaved-RGB frames for TMA: (8-byte words per row, rows, frames).
 bool make_rgb_tensor_map(CUtensorMap *tm, const uint8_t *pixels, size_t pixel_stride, uint32_t n,
-                         uint32_t w, uint32_t h)
+                         uint32_t w, uint32_t h, uint32_t box_words, uint32_t box_rows)
 {
     const size_t pitch = (size_t)w * 3;
     if (pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(pixels) & 15) != 0) return false;
@@ -1027,7 +1110,7 @@ bool make_rgb_tensor_map(CUtensorMap *tm, const uint8_t *pixels, size_t pixel_st
     if (!enc) return false;
     const cuuint64_t gdim[3] = {pitch / 8, h, n};
     const cuuint64_t gstr[2] = {pitch, n > 1 ? pixel_stride : pitch * h};
-    const cuuint32_t box[3] = {K1_HB / 8, 16, 1};
+    const cuuint32_t box[3] = {box_words, box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t *>(pixels), gdim, gstr, box,
                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -1046,7 +1129,7 @@ int launch_k1(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint32
     P.zero[0] = 0.0f; P.zero[1] = 0.0f;
     alignas(64) CUtensorMap tm;
     memset(&tm, 0, sizeof tm);
-    P.use_tma = make_rgb_tensor_map(&tm, px, pixel_stride, n, w, h) ? 1u : 0u;
+    P.use_tma = make_rgb_tensor_map(&tm, px, pixel_stride, n, w, h, K1_HB / 8, 16) ? 1u : 0u;
     static int blocks_per_sm[64][2];  // function attributes are per device
     const size_t smem = sizeof(K1Smem);
     auto kern = zigzag ? k_jpeg_420<true> : k_jpeg_420<false>;
@@ -1061,6 +1144,41 @@ int launch_k1(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint32
     uint64_t grid = (uint64_t)ctx->sm_count * bps;
     if (grid > (nunits + K1_WARPS - 1) / K1_WARPS) grid = (nunits + K1_WARPS - 1) / K1_WARPS;
     kern<<<(unsigned)grid, K1_THREADS, smem, ctx->stream>>>(P, qt, tm);
+    ctx->launches++;
+    PIXO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+int launch_k444(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint32_t n, uint32_t w,
+                uint32_t h, int16_t *y, size_t y_stride, int16_t *cb, int16_t *cr, size_t c_stride,
+                const QuantTab &qt, bool zigzag)
+{
+    K1Params P;
+    P.pixels = px; P.pixel_stride = pixel_stride; P.w = w; P.h = h;
+    P.mcus_x = (w + 7) / 8; P.mcus_y = (h + 7) / 8;     // blocks
+    P.units_x = (P.mcus_x + 31) / 32;
+    P.n_images = n; P.y = y; P.cb = cb; P.cr = cr; P.y_stride = y_stride; P.c_stride = c_stride;
+    P.zero[0] = 0.0f; P.zero[1] = 0.0f;
+    alignas(64) CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    P.use_tma = make_rgb_tensor_map(&tm, px, pixel_stride, n, w, h, K4_ROW_B / 8, 8) ? 1u : 0u;
+    static int blocks_per_sm[64][2];  // function attributes are per device
+    const size_t smem = sizeof(K4Smem);
+    auto kern = zigzag ? k_jpeg_444<true> : k_jpeg_444<false>;
+    int &bps = blocks_per_sm[ctx->device & 63][zigzag];
+    if (!bps) {
+        PIXO_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        PIXO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, K4_THREADS, smem));
+        bps = nb > 0 ? nb : 1;
+    }
+    const uint64_t nunits = (uint64_t)P.mcus_y * P.units_x * n;
+    uint64_t grid = (uint64_t)ctx->sm_count * bps;
+    if (grid > (nunits + K4_WARPS - 1) / K4_WARPS) grid = (nunits + K4_WARPS - 1) / K4_WARPS;
+    if (getenv("PIXO_B200_DEBUG"))
+        fprintf(stderr, "k_jpeg_444: use_tma=%u blocks/SM=%d grid=%llu units=%llu\n", P.use_tma, bps,
+                (unsigned long long)grid, (unsigned long long)nunits);
+    kern<<<(unsigned)grid, K4_THREADS, smem, ctx->stream>>>(P, qt, tm);
     ctx->launches++;
     PIXO_CUDA(ctx, cudaGetLastError());
     return 0;
@@ -1121,11 +1239,8 @@ int launch_jpeg_transform(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pi
             if (zigzag) k_jpeg_gray<true><<<grid, 64, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, qt, 0.0f, 0.0f);
             else k_jpeg_gray<false><<<grid, 64, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, qt, 0.0f, 0.0f);
         } else if (subsampling == PIXO_B200_S444) {
-            const uint32_t bx = (w + 7) / 8, by = (h + 7) / 8;
-            const uint32_t tiles_x = (bx + K2_BLOCKS - 1) / K2_BLOCKS;
-            dim3 grid(tiles_x * by, nb);
-            if (zigzag) k_jpeg_444<true><<<grid, 192, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, cb, cr, c_stride, qt, 0.0f, 0.0f);
-            else k_jpeg_444<false><<<grid, 192, 0, ctx->stream>>>(px, pixel_stride, w, h, bx, tiles_x, y, y_stride, cb, cr, c_stride, qt, 0.0f, 0.0f);
+            PIXO_TRY(launch_k444(ctx, px, pixel_stride, nb, w, h, y, y_stride, cb, cr, c_stride, qt, zigzag));
+            continue;
         } else {
             PIXO_TRY(launch_k1(ctx, px, pixel_stride, nb, w, h, y, y_stride, cb, cr, c_stride, qt, zigzag));
             continue;
