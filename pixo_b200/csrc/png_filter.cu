@@ -18,6 +18,8 @@
 // `type byte + row` with aligned word stores.  The row's Adler-32 contribution
 // (A = sum d, B = sum (n-i) d, position-weighted to the end of the image) is accumulated in the
 // same pass; the last CTA of an image folds the accumulators into the checksum.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace pixo {
@@ -530,6 +532,9 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
         const uint32_t *c32 = reinterpret_cast<const uint32_t *>(bufs[r % 3]) + 4;
         const uint32_t *p32 = reinterpret_cast<const uint32_t *>(bufs[(r + 2) % 3]) + 4;
 
+        // words before `full` hold four row bytes; the last word's missing bytes are masked off
+        const uint32_t full = rb >> 2;
+        const uint32_t tailmask = (rb & 3u) ? (0xFFFFFFFFu >> (8 * (4 - (rb & 3u)))) : 0u;
         auto operands = [&](uint32_t k, uint32_t &x, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &mask) {
             x = c32[k]; b = p32[k];
             uint32_t xl = c32[(int)k - 1], bl = p32[(int)k - 1];
@@ -539,23 +544,30 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
             }
             a = __funnelshift_r(xl, x, ashift);
             c = __funnelshift_r(bl, b, ashift);
-            const int valid = (int)rb - 4 * (int)k;
-            mask = valid >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (4 - valid)));
+            mask = k < full ? 0xFFFFFFFFu : tailmask;
         };
 
         int filter = (int)P.strategy;
         if (filter >= 5) {
             uint32_t T[5] = {0, 0, 0, 0, 0};
             const bool fast = P.strategy == PIXO_B200_FILTER_ADAPTIVE_FAST;
-            for (uint32_t k = tid; k < nw; k += PNG_THREADS) {
-                uint32_t x, a, b, c, mask;
-                operands(k, x, a, b, c, mask);
-                T[1] += __vsadu4(__vabsdiffu4(x, a) & mask, 0x80808080u);
-                T[2] += __vsadu4(__vabsdiffu4(x, b) & mask, 0x80808080u);
-                T[4] += __vsadu4(__vabsdiffu4(x, paeth_pred4(a, b, c)) & mask, 0x80808080u);
-                if (!fast) {
+            if (fast) {
+                for (uint32_t k = tid; k < nw; k += PNG_THREADS) {
+                    uint32_t x, a, b, c, mask;
+                    operands(k, x, a, b, c, mask);
+                    T[1] += __vsadu4(__vabsdiffu4(x, a) & mask, 0x80808080u);
+                    T[2] += __vsadu4(__vabsdiffu4(x, b) & mask, 0x80808080u);
+                    T[4] += __vsadu4(__vabsdiffu4(x, paeth_pred4(a, b, c)) & mask, 0x80808080u);
+                }
+            } else {
+                for (uint32_t k = tid; k < nw; k += PNG_THREADS) {
+                    uint32_t x, a, b, c, mask;
+                    operands(k, x, a, b, c, mask);
                     T[0] += __vsadu4(x & mask, 0x80808080u);
+                    T[1] += __vsadu4(__vabsdiffu4(x, a) & mask, 0x80808080u);
+                    T[2] += __vsadu4(__vabsdiffu4(x, b) & mask, 0x80808080u);
                     T[3] += __vsadu4(__vabsdiffu4(x, __vhaddu4(a, b)) & mask, 0x80808080u);
+                    T[4] += __vsadu4(__vabsdiffu4(x, paeth_pred4(a, b, c)) & mask, 0x80808080u);
                 }
             }
 #pragma unroll
@@ -599,47 +611,50 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
             filter = s_filter;
         }
 
-        // ---- emit the winner ----
-        auto filtered = [&](uint32_t k) -> uint32_t {
-            if (k >= nw) return 0u;
-            uint32_t x, a, b, c, mask;
-            operands(k, x, a, b, c, mask);
-            uint32_t pred;
-            switch (filter) {
-            case 0: pred = 0; break;
-            case 1: pred = a; break;
-            case 2: pred = b; break;
-            case 3: pred = __vhaddu4(a, b); break;
-            default: pred = paeth_pred4(a, b, c); break;
-            }
-            return __vsub4(x, pred) & mask;
-        };
+        // ---- emit the winner (the filter is chosen once per row: one straight-line loop per type) ----
         uint8_t *orow = P.out + (size_t)img * P.out_stride + (size_t)r * n_out;
         const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(orow + 1) & 3);
         uint32_t *gal = reinterpret_cast<uint32_t *>(orow + 1 - sh);   // aligned; word j = bytes 4j-sh..
         uint32_t S1 = 0, S2 = 0, S3 = 0;
-        uint32_t carry = j_lo ? filtered(j_lo - 1) : 0u;   // f[j-1] for this warp's first word
-        for (uint32_t j0 = j_lo; j0 < j_hi; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            const uint32_t f = filtered(j);
-            if (j < nw) {
-                const uint32_t s4 = __dp4a(f, 0x01010101u, 0u);
-                S1 += s4; S2 += j * s4; S3 += __dp4a(f, 0x03020100u, 0u);
-            }
-            uint32_t fm1 = __shfl_up_sync(0xffffffffu, f, 1);
-            if (lane == 0) fm1 = carry;
-            carry = __shfl_sync(0xffffffffu, f, 31);
-            if (j < j_hi) {
-                const uint32_t word = __funnelshift_l(fm1, f, 8 * sh);
-                const int i0 = 4 * (int)j - (int)sh;            // first filtered-byte index in this word
-                if (i0 >= 0 && i0 + 3 < (int)rb) {
-                    gal[j] = word;
-                } else {
+        auto emit_row = [&](auto ftag) {
+            constexpr int F = decltype(ftag)::value;
+            auto filtered = [&](uint32_t k) -> uint32_t {
+                if (k >= nw) return 0u;
+                uint32_t x, a, b, c, mask;
+                operands(k, x, a, b, c, mask);
+                const uint32_t pred = F == 0 ? 0u : F == 1 ? a : F == 2 ? b : F == 3 ? __vhaddu4(a, b) : paeth_pred4(a, b, c);
+                return __vsub4(x, pred) & mask;
+            };
+            uint32_t carry = j_lo ? filtered(j_lo - 1) : 0u;   // f[j-1] for this warp's first word
+            for (uint32_t j0 = j_lo; j0 < j_hi; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const uint32_t f = filtered(j);
+                if (j < nw) {
+                    const uint32_t s4 = __dp4a(f, 0x01010101u, 0u);
+                    S1 += s4; S2 += j * s4; S3 += __dp4a(f, 0x03020100u, 0u);
+                }
+                uint32_t fm1 = __shfl_up_sync(0xffffffffu, f, 1);
+                if (lane == 0) fm1 = carry;
+                carry = __shfl_sync(0xffffffffu, f, 31);
+                if (j < j_hi) {
+                    const uint32_t word = __funnelshift_l(fm1, f, 8 * sh);
+                    const int i0 = 4 * (int)j - (int)sh;            // first filtered-byte index in this word
+                    if (i0 >= 0 && i0 + 3 < (int)rb) {
+                        gal[j] = word;
+                    } else {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        if (i0 + t >= 0 && i0 + t < (int)rb) reinterpret_cast<uint8_t *>(gal + j)[t] = (uint8_t)(word >> (8 * t));
+                        for (int t = 0; t < 4; ++t)
+                            if (i0 + t >= 0 && i0 + t < (int)rb) reinterpret_cast<uint8_t *>(gal + j)[t] = (uint8_t)(word >> (8 * t));
+                    }
                 }
             }
+        };
+        switch (filter) {
+        case 0: emit_row(std::integral_constant<int, 0>{}); break;
+        case 1: emit_row(std::integral_constant<int, 1>{}); break;
+        case 2: emit_row(std::integral_constant<int, 2>{}); break;
+        case 3: emit_row(std::integral_constant<int, 3>{}); break;
+        default: emit_row(std::integral_constant<int, 4>{}); break;
         }
         if (tid == 0) orow[0] = (uint8_t)filter;
         if (P.acc) {
