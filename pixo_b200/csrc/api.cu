@@ -452,14 +452,13 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
         const size_t cstride = coef_each / 2;
         PIXO_TRY(launch_jpeg_transform(ctx, d_in + (size_t)slot * G * in_stride, in_stride, cnt, g.width,
                                        g.height, g.color_type, g.subsampling, lum, chr, dy, cstride,
-                                       g.has_chroma ? dcb : nullptr, g.has_chroma ? dcr : nullptr, cstride,
-                                       PIXO_B200_COEF_ZIGZAG));  // the order every consumer below reads
+                                       g.has_chroma ? dcb : nullptr, g.has_chroma ? dcr : nullptr, cstride, 0));
         PIXO_CUDA(ctx, cudaEventRecord(ev_used[slot], ctx->stream));
         std::vector<HuffTables> tables(optimize ? cnt : 1);
         if (optimize) {
             auto *d_hist = reinterpret_cast<uint64_t *>(ctx->d_misc.ptr);
             PIXO_TRY(launch_jpeg_histogram(ctx, dy, cstride, dcb, dcr, cstride, cnt, g.ny, g.nc, g.y_per_mcu,
-                                           restart_interval, true, d_hist));
+                                           restart_interval, false, d_hist));
             PIXO_CUDA(ctx, cudaMemcpyAsync(h_hist, d_hist, (size_t)cnt * kHistWords * sizeof(uint64_t),
                                            cudaMemcpyDeviceToHost, ctx->stream));
             PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -531,7 +530,7 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
                 const size_t body = entropy_encode_scan(reinterpret_cast<int16_t *>(hc),
                                                         reinterpret_cast<int16_t *>(hc + yb),
                                                         reinterpret_cast<int16_t *>(hc + yb + cbb), g,
-                                                        tables[optimize ? k : 0], restart_interval, true,
+                                                        tables[optimize ? k : 0], restart_interval, false,
                                                         o + hdr[k], out_cap_each - hdr[k] - 2, ctx->host_threads);
                 if (body == (size_t)-1)
                     return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small", out_cap_each);
@@ -611,7 +610,7 @@ int pixo_b200_jpeg_encode_dev(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_
     auto *dcr = reinterpret_cast<int16_t *>(d_coef + yb + cbb);
     PIXO_TRY(launch_jpeg_transform(ctx, d_pixels, pixel_stride, n_images, width, height, color_type, subsampling,
                                    lum, chr, dy, coef_each / 2, g.has_chroma ? dcb : nullptr,
-                                   g.has_chroma ? dcr : nullptr, coef_each / 2, PIXO_B200_COEF_ZIGZAG));
+                                   g.has_chroma ? dcr : nullptr, coef_each / 2, 0));
     HuffTables t;
     huff_standard(t);
     uint64_t *len_src = nullptr;

@@ -12,8 +12,8 @@
 // independent of the others; only its POSITION in the stream is not.  The kernel is persistent
 // and every warp works alone (warp-level synchronisation only): it draws a chunk of 32
 // consecutive blocks (scan order) of one image from a ticket counter, then
-//   1. each lane codes its block once into a private shared-memory slot (coefficients arrive in
-//      zig-zag order; a 64-bit non-zero mask drives the symbol loop, so the loop runs once per
+//   1. each lane codes its block once into a private shared-memory slot (the zig-zag reorder
+//      happens in registers on the way in; a 64-bit non-zero mask drives the symbol loop, so the loop runs once per
 //      non-zero coefficient and there is a single, small copy of the symbol code);
 //   2. the block bit lengths are scanned in the warp; the chunk total enters a decoupled
 //      look-back chain (one status word per chunk: bit count + the chunk's last 7 bits), which
@@ -31,6 +31,16 @@
 namespace pixo {
 namespace {
 
+// natural index of zig-zag position i (src/jpeg/quantize.rs:18-22)
+__host__ __device__ constexpr int zz_nat(int i)
+{
+    constexpr int t[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
+                           12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
+                           35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+                           58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    return t[i];
+}
+
 // Huffman tables as the symbol loop wants them: one word per symbol,
 //   entry = (code << (32 - len)) | (len + cat),   cat = symbol & 15 (AC) or the DC category
 // i.e. the code left-aligned in the upper half-word and the total field width (code + amplitude
@@ -41,7 +51,7 @@ struct HuffDev {
 };
 
 struct EntParams {
-    const int16_t *y, *cb, *cr;    // zig-zag ordered blocks
+    const int16_t *y, *cb, *cr;    // blocks in natural order, as compute_all_coefficients returns them
     size_t y_stride, c_stride;     // int16 elements between images
     uint32_t bpm;                  // blocks per MCU in scan order: 6 (4:2:0), 3 (4:4:4), 1 (gray)
     uint32_t y_per_mcu;            // 4, 1, 1
@@ -365,13 +375,22 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             uint32_t e0 = 0, e1 = 0;
             int dc;
             {
-                uint32_t w[32];
+                uint32_t n[32];  // the block as K1 wrote it: natural order, two coefficients per word
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const uint4 v = __ldg(src + q);
-                    w[q * 4] = v.x; w[q * 4 + 1] = v.y; w[q * 4 + 2] = v.z; w[q * 4 + 3] = v.w;
+                    n[q * 4] = v.x; n[q * 4 + 1] = v.y; n[q * 4 + 2] = v.z; n[q * 4 + 3] = v.w;
                 }
-                dc = (int)(int16_t)(w[0] & 0xFFFF);
+                dc = (int)(int16_t)(n[0] & 0xFFFF);
+                // zig-zag reorder (zigzag_reorder, src/jpeg/quantize.rs:107-113) on the way into the
+                // stage: word j = coefficients zz(2j), zz(2j+1); all indices are compile-time
+                uint32_t w[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int i0 = zz_nat(2 * j), i1 = zz_nat(2 * j + 1);
+                    w[j] = __byte_perm(n[i0 >> 1], n[i1 >> 1],
+                                       ((i0 & 1) ? 0x0032 : 0x0010) | ((i1 & 1) ? 0x7600 : 0x5400));
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) M.stage[j * CB + lane] = w[j];
 #pragma unroll
@@ -665,7 +684,7 @@ size_t entropy_scratch_bytes(uint32_t n, const FrameGeometry &g)
     return plan_entropy(n, g.ny + 2 * g.nc).total;
 }
 
-// Enqueue the entropy stage for n images (zig-zag ordered coefficients) on ctx->stream.
+// Enqueue the entropy stage for n images (natural-order coefficient arrays) on ctx->stream.
 // d_scratch: entropy_scratch_bytes.  d_out: n * out_cap bytes of scan data; *d_out_len /
 // *d_overflow point into the scratch.
 int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride, const int16_t *d_cb,

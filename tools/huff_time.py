@@ -29,7 +29,7 @@ for n, kind in [(1, "noise"), (1, "grad"), (8, "mix"), (32, "mix")]:
     def k1():
         _lib.check(ctx.handle, lib.pixo_b200_jpeg_coefficients_dev(
             ctx.handle, px.data_ptr(), H * W * 3, n, W, H, 2, 1, lq.ctypes.data_as(_lib.f32p),
-            cq.ctypes.data_as(_lib.f32p), y.data_ptr(), ny * 64, cb.data_ptr(), cr.data_ptr(), nc * 64, 1, None))
+            cq.ctypes.data_as(_lib.f32p), y.data_ptr(), ny * 64, cb.data_ptr(), cr.data_ptr(), nc * 64, 0, None))
     def t(fn, reps):
         for _ in range(3): fn()
         torch.cuda.synchronize()
