@@ -35,30 +35,30 @@ def frames(w, h, n, distinct=8):
     return torch.from_numpy(np.stack([base[k % len(base)] for k in range(n)])).cuda()
 
 
-def jpeg_config(name, w, h, n, q, reps):
+def jpeg_config(name, w, h, n, q, reps, ss=1):
     px = frames(w, h, n)
     nbytes = w * h * 3
-    ny, nc = jpeg.block_counts(w, h, 2, 1)
+    ny, nc = jpeg.block_counts(w, h, 2, ss)
     _, _, lq, cq = jpeg.quant_tables(q)
     y = torch.empty((n, ny * 64), dtype=torch.int16, device="cuda")
     cb = torch.empty((n, nc * 64), dtype=torch.int16, device="cuda"); cr = torch.empty_like(cb)
-    cap = (nbytes // 2 + 65536 + 8192) // 256 * 256
+    cap = (nbytes * (1 if ss == 0 else 1) // (1 if ss == 0 else 2) + 65536 + 8192) // 256 * 256
     scan = torch.empty((n, cap), dtype=torch.uint8, device="cuda")
     sl = torch.zeros(n, dtype=torch.int64, device="cuda"); so = torch.zeros(n, dtype=torch.int32, device="cuda")
 
     def k1():
         _lib.check(ctx.handle, lib.pixo_b200_jpeg_coefficients_dev(
-            ctx.handle, px.data_ptr(), nbytes, n, w, h, 2, 1, lq.ctypes.data_as(_lib.f32p), cq.ctypes.data_as(_lib.f32p),
+            ctx.handle, px.data_ptr(), nbytes, n, w, h, 2, ss, lq.ctypes.data_as(_lib.f32p), cq.ctypes.data_as(_lib.f32p),
             y.data_ptr(), ny * 64, cb.data_ptr(), cr.data_ptr(), nc * 64, 0, None))
 
     def enc():
-        _lib.check(ctx.handle, lib.pixo_b200_jpeg_encode_dev(ctx.handle, px.data_ptr(), nbytes, n, w, h, 2, q, 1,
+        _lib.check(ctx.handle, lib.pixo_b200_jpeg_encode_dev(ctx.handle, px.data_ptr(), nbytes, n, w, h, 2, q, ss,
                                                              scan.data_ptr(), cap, sl.data_ptr(), so.data_ptr()))
     tk, te = timed(k1, reps), timed(enc, reps)
     assert int(so.sum()) == 0
     pix = n * w * h
     algo = n * (nbytes + (ny + 2 * nc) * 128)
-    return {"config": name, "frames": n, "size": f"{w}x{h}", "quality": q,
+    return {"config": name, "frames": n, "size": f"{w}x{h}", "quality": q, "subsampling": "4:2:0" if ss else "4:4:4",
             "k1_us": tk * 1e6, "k1_mpix_s": pix / tk / 1e6, "k1_gb_s": algo / tk / 1e9, "k1_frac_of_hbm_peak": algo / tk / 1e9 / PEAK,
             "device_path_us": te * 1e6, "device_path_mpix_s": pix / te / 1e6, "jpeg_bytes": int(sl.sum())}
 
@@ -83,6 +83,7 @@ def png_config(name, w, h, n, strat, reps):
 
 res = {"hbm_peak_gb_s": PEAK, "results": []}
 res["results"].append(jpeg_config("C2 (32 x 3840x2160, q80)", 3840, 2160, 32, 80, 10))
+res["results"].append(jpeg_config("pixo default preset (32 x 3840x2160, 4:4:4 q75)", 3840, 2160, 32, 75, 10, ss=0))
 for q in (50, 80, 95):
     res["results"].append(jpeg_config(f"C3 (256 x 1920x1080, q{q})", 1920, 1080, 256, q, 5))
 res["results"].append(jpeg_config("C4 (1 x 16384x16384, q80)", 16384, 16384, 1, 80, 5))
