@@ -43,6 +43,7 @@ struct pixo_b200_ctx {
     pixo::Scratch d_in, d_y, d_cb, d_cr, d_misc, d_out, d_ent, d_coef;
     pixo::Scratch h_in, h_out, h_misc;
     std::vector<cudaEvent_t> events;
+    std::vector<cudaEvent_t> stage_events;  // one per pinned staging slot of h2d_copy
 };
 
 namespace pixo {
