@@ -143,24 +143,38 @@ def cpu_reference_rate(frames: np.ndarray, threads: int, rounds: int) -> tuple[f
     return nf * PIX / dt / 1e6, dt, nf
 
 
+def host_threads() -> int:
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except AttributeError:
+        pass
+    return n
+
+
+def best_thread_count(frames: np.ndarray) -> tuple[int, dict]:
+    """The CPU arm gets the thread count it runs fastest with: all hardware threads, or one per
+    physical core when SMT siblings only fight over the FP units (one calibration round each)."""
+    n = host_threads()
+    tried = {}
+    for t in sorted({n, max(1, n // 2)}, reverse=True):
+        tried[t] = cpu_reference_rate(frames, t, 1)[0]
+    return max(tried, key=tried.get), tried
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1   # every host thread the box has (sched affinity permitting)
-    try:
-        threads = len(os.sched_getaffinity(0)) or threads
-    except AttributeError:
-        pass
-    frames = make_frames(min(16, max(2, threads)))
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_rate(frames, threads, 1)
+    frames = make_frames(min(16, max(2, host_threads())))
+    threads, tried = best_thread_count(frames)   # doubles as the warm-up
     t_total, f_total = 0.0, 0
     for _ in range(args.steps):
         _, dt, nf = cpu_reference_rate(frames, threads, 1)
         t_total += dt; f_total += nf
     rate = f_total * PIX / t_total / 1e6
-    sample = f"{threads} frames of 3840x2160 per step (one per host thread), {args.steps} steps"
+    sample = (f"{threads} frames of 3840x2160 per step (one per thread), {args.steps} steps; thread count chosen "
+              f"by calibration {({k: round(v) for k, v in tried.items()})} Mpix/s")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3,
@@ -307,11 +321,7 @@ def run_ours(args):
     # ---- CPU baseline, rank 0 at N=1 only: bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        try:
-            cores = len(os.sched_getaffinity(0)) or cores
-        except AttributeError:
-            pass
+        cores, _tried = best_thread_count(frames_host)
         rate, dt, nf = cpu_reference_rate(frames_host, cores, 1)
         cpu = {"value": rate, "unit": "Mpix/s", "cores": cores, "kind": "port",
                "sample": f"{nf} frames of 3840x2160 (one per thread), {dt:.1f} s wall; CPU restatement of "

@@ -212,3 +212,17 @@ def test_encode_dev_device_resident(po, gpu_ctx):
                 assert ovf[k] == 0 and scan[k, :lens[k]].tobytes() == refs[k]
             else:
                 assert ovf[k] != 0
+
+
+def test_large_pageable_input_takes_the_staged_copy(po, gpu_ctx):
+    """Sources of 64 MB and more (ordinary, pageable memory) are pushed through the pinned slot
+    ring by several host threads; the pieces must land exactly where a single copy would put them."""
+    w, h = 6000, 4000     # 72 MB of RGB
+    rng = np.random.default_rng(11)
+    img = np.roll(po.gen_gradient_rgb(w, h).reshape(h, w * 3), 7, axis=0).reshape(-1).copy()
+    img[rng.integers(0, img.size, 200000)] ^= 0x5A     # break the regularity at random places
+    for ss in (Subsampling.S420, Subsampling.S444):
+        o = JpegOptions(w, h, ColorType.Rgb, 80, ss)
+        got = jpeg.encode(img, o, ctx=gpu_ctx)
+        ref = po.jpeg_encode(img, w, h, 2, 80, int(ss))
+        assert hashlib.sha256(got).digest() == hashlib.sha256(ref).digest()
