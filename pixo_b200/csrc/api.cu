@@ -426,9 +426,9 @@ static int validate_encode(pixo_b200_ctx *ctx, size_t pixels_len, uint32_t width
 // statistics when optimize_huffman (K3), Huffman bit packing + 0xFF stuffing (jpeg_entropy.cu);
 // host: headers, optimised-table construction, EOI.  Frames are processed in groups; the H2D
 // copy of group g+1 runs on the copy stream under the kernels of group g, and only finished
-// scan bytes come back over PCIe.  restart_interval != 0 (per-interval padding) and capacity
-// overflows (pathological inputs whose JPEG exceeds half the raw size) take the host entropy
-// coder instead, which consumes the same GPU coefficient arrays.
+// scan bytes come back over PCIe (restart intervals included).  Only a capacity overflow (a
+// pathological input whose JPEG exceeds half the raw size) is finished by the host entropy
+// coder, which consumes the same GPU coefficient arrays.
 static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_each, uint32_t n_images,
                          const FrameGeometry &g, uint32_t quality, uint32_t restart_interval,
                          bool optimize, uint8_t *out, size_t out_cap_each, size_t *out_lens)
@@ -443,12 +443,12 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
     // device-side scan capacity per frame; a JPEG that needs more (pathological noise at very high
     // quality) is finished by the host coder from the same coefficients
     const uint64_t scan_cap = align_up((len_each / 2 + 65536) / 8 * 9, 256);
-    const bool gpu_entropy = restart_interval == 0;
+    const bool gpu_entropy = true;  // restart intervals included; the host coder only finishes capacity overflows
 
     uint32_t G = n_images < 16 ? n_images : 16;
     const size_t budget = (size_t)3 << 30;
     auto group_bytes = [&](uint32_t k) {
-        return 2 * (size_t)k * in_stride + (size_t)k * coef_each + entropy_scratch_bytes(k, g) +
+        return 2 * (size_t)k * in_stride + (size_t)k * coef_each + entropy_scratch_bytes(k, g, restart_interval) +
                2 * (size_t)k * scan_cap;
     };
     while (G > 1 && group_bytes(G) > budget) --G;
@@ -457,7 +457,7 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
     PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
     PIXO_TRY(ensure_dev(ctx, ctx->d_in, 2 * (size_t)G * in_stride));
     PIXO_TRY(ensure_dev(ctx, ctx->d_coef, (size_t)G * coef_each));
-    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(G, g)));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(G, g, restart_interval)));
     PIXO_TRY(ensure_dev(ctx, ctx->d_out, 2 * (size_t)G * scan_cap));
     PIXO_TRY(ensure_dev(ctx, ctx->d_misc, (size_t)G * kHistWords * sizeof(uint64_t) + 256));
     PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, (size_t)G * (kHistWords * sizeof(uint64_t) + 32) + 256));
@@ -526,16 +526,16 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
             uint32_t *d_ovf = nullptr;
             auto *ent = reinterpret_cast<uint8_t *>(ctx->d_ent.ptr);
             if (!optimize) {
-                PIXO_TRY(launch_jpeg_entropy(ctx, dy, cstride, dcb, dcr, cstride, cnt, g, tables[0], ent,
+                PIXO_TRY(launch_jpeg_entropy(ctx, dy, cstride, dcb, dcr, cstride, cnt, g, tables[0], restart_interval, ent,
                                              scan, scan_cap, &d_len, &d_ovf));
                 PIXO_CUDA(ctx, cudaMemcpyAsync(h_len, d_len, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
                 PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf, d_ovf, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
             } else {
-                const size_t per = entropy_scratch_bytes(1, g);
+                const size_t per = entropy_scratch_bytes(1, g, restart_interval);
                 for (uint32_t k = 0; k < cnt; ++k) {  // per-image tables: one pass per image
                     PIXO_TRY(launch_jpeg_entropy(ctx, dy + (size_t)k * cstride, cstride, dcb + (size_t)k * cstride,
                                                  dcr + (size_t)k * cstride, cstride, 1, g, tables[k],
-                                                 ent + (size_t)k * per, scan + (size_t)k * scan_cap,
+                                                 restart_interval, ent + (size_t)k * per, scan + (size_t)k * scan_cap,
                                                  scan_cap, &d_len, &d_ovf));
                     PIXO_CUDA(ctx, cudaMemcpyAsync(h_len + k, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
                     PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf + k, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -654,7 +654,7 @@ int pixo_b200_jpeg_encode_dev(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_
     const size_t coef_each = yb + 2 * cbb;
     PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
     PIXO_TRY(ensure_dev(ctx, ctx->d_coef, (size_t)n_images * coef_each));
-    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(n_images, g)));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(n_images, g, 0)));
     auto *d_coef = reinterpret_cast<uint8_t *>(ctx->d_coef.ptr);
     auto *dy = reinterpret_cast<int16_t *>(d_coef);
     auto *dcb = reinterpret_cast<int16_t *>(d_coef + yb);
@@ -666,7 +666,7 @@ int pixo_b200_jpeg_encode_dev(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_
     huff_standard(t);
     uint64_t *len_src = nullptr;
     uint32_t *ovf_src = nullptr;
-    PIXO_TRY(launch_jpeg_entropy(ctx, dy, coef_each / 2, dcb, dcr, coef_each / 2, n_images, g, t,
+    PIXO_TRY(launch_jpeg_entropy(ctx, dy, coef_each / 2, dcb, dcr, coef_each / 2, n_images, g, t, 0,
                                  reinterpret_cast<uint8_t *>(ctx->d_ent.ptr), d_scan, scan_cap_each,
                                  &len_src, &ovf_src));
     PIXO_CUDA(ctx, cudaMemcpyAsync(d_scan_len, len_src, (size_t)n_images * 8, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -83,10 +83,10 @@ int launch_adler32(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t len, uint32
 
 struct FrameGeometry;
 struct HuffTables;
-size_t entropy_scratch_bytes(uint32_t n, const FrameGeometry &g);
+size_t entropy_scratch_bytes(uint32_t n, const FrameGeometry &g, uint32_t restart_interval);
 int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride, const int16_t *d_cb,
                         const int16_t *d_cr, size_t c_stride, uint32_t n, const FrameGeometry &g,
-                        const HuffTables &t, uint8_t *d_scratch, uint8_t *d_out,
+                        const HuffTables &t, uint32_t restart_interval, uint8_t *d_scratch, uint8_t *d_out,
                         uint64_t out_cap, uint64_t **d_out_len, uint32_t **d_overflow);
 
 }  // namespace pixo

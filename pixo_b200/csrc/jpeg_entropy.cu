@@ -57,6 +57,9 @@ struct EntParams {
     uint32_t y_per_mcu;            // 4, 1, 1
     uint32_t nblocks;              // per image, scan order
     uint32_t nchunks;              // per image
+    uint32_t rst_mcus;             // restart interval in MCUs, 0 = none (a chunk never straddles an interval)
+    uint32_t rst_blocks;           // ... in blocks
+    uint32_t cpi;                  // chunks per full interval
     uint32_t nimages;
     unsigned long long *st_bits;   // [n][nchunks] look-back chain 1: stream bits
     unsigned long long *st_ff;     // [n][nchunks] look-back chain 2: 0xFF bytes
@@ -319,6 +322,9 @@ struct ChunkState {
     unsigned long long Pc; // uniform: bits before the chunk (after phase A)
     uint32_t tailin;       // uniform: the 7 bits before the chunk
     uint32_t Ftot;         // uniform: 0xFF bytes the chunk owns
+    uint32_t own;          // uniform: output bytes the chunk writes (owned + stuffed zeros + RSTn marker)
+    uint32_t marker;       // uniform: 0xD0..0xD7 when the chunk closes a restart interval, else 0
+    bool first, last, final_; // uniform: first / last chunk of its bit stream (image or interval); last of the image
     uint32_t ffb;          // 0xFF bytes before this lane's piece of the kept window
     bool kept;             // uniform: phase A left the assembled (single) window in the slot buffer
     bool fault;
@@ -356,12 +362,29 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         C.img = id - C.chunk * P.nimages;
         C.buf = buf;
         C.fault = false;
-        const uint32_t s = C.chunk * CB + lane;
-        const int nv = (int)min((uint32_t)CB, P.nblocks - C.chunk * CB);
+        // the chunk's place: with a restart interval every interval is its own bit stream
+        // (handle_restart, src/jpeg/mod.rs:1423-1445) and is cut into chunks separately
+        uint32_t s0, iend, interval = 0;
+        if (P.rst_blocks) {
+            interval = C.chunk / P.cpi;
+            const uint32_t sub = C.chunk - interval * P.cpi;
+            s0 = interval * P.rst_blocks + sub * CB;
+            iend = (uint32_t)min((unsigned long long)(interval + 1) * P.rst_blocks, (unsigned long long)P.nblocks);
+            C.first = sub == 0;
+        } else {
+            s0 = C.chunk * CB;
+            iend = P.nblocks;
+            C.first = C.chunk == 0;
+        }
+        C.last = s0 + CB >= iend;
+        C.final_ = C.last && iend == P.nblocks;
+        C.marker = (C.last && !C.final_) ? 0xD0u + (interval & 7u) : 0u;
+        const uint32_t s = s0 + lane;
+        const int nv = (int)min((uint32_t)CB, iend - s0);
         uint32_t *const slot = M.slot[buf];
         uint32_t L = 0, tail7 = 0;
         int nwt = 0;
-        if (s < P.nblocks) {
+        if (s < iend) {
             const uint32_t m = s / P.bpm;
             const uint32_t k = s - m * P.bpm;
             const int16_t *arr;
@@ -370,7 +393,9 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             if (k < P.y_per_mcu) { arr = P.y + (size_t)C.img * P.y_stride; idx = (size_t)m * P.y_per_mcu + k; tbl = 0; }
             else if (k == P.y_per_mcu) { arr = P.cb + (size_t)C.img * P.c_stride; idx = m; tbl = 1; }
             else { arr = P.cr + (size_t)C.img * P.c_stride; idx = m; tbl = 1; }
-            const int prev_dc = idx ? arr[(idx - 1) * 64] : 0;
+            // DC predictors restart with the interval (src/jpeg/mod.rs:1433-1443)
+            const bool dc_reset = P.rst_mcus && m % P.rst_mcus == 0 && (k == 0 || k >= P.y_per_mcu);
+            const int prev_dc = (idx && !dc_reset) ? arr[(idx - 1) * 64] : 0;
             const uint4 *src = reinterpret_cast<const uint4 *>(arr + idx * 64);
             uint32_t e0 = 0, e1 = 0;
             int dc;
@@ -433,12 +458,13 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
                 got += take;
             }
             st_status(P.st_bits + (size_t)C.img * P.nchunks + C.chunk,
-                      pack_status(C.chunk == 0 ? ST_PFX : ST_AGG, ctail, C.Lc));
+                      pack_status(C.first ? ST_PFX : ST_AGG, ctail, C.Lc));
         }
         C.ctail = __shfl_sync(0xffffffffu, ctail, 0);
         C.Pc = 0;
         C.tailin = 0;
         C.Ftot = 0;
+        C.own = 0;
         C.ffb = 0;
         C.kept = false;
         __syncwarp();
@@ -447,10 +473,12 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
     // ---- stuffed bytes of one window (this lane's 32 bytes in wv) -> sbuf -> global ----------------
     // a, b: the chunk's owned byte range inside the window; ffb / Fr: 0xFF bytes before this
     // lane's piece / in the whole window; G: output index of the window's first owned byte.
+    // mk: RSTn marker byte to append after the window's bytes (0 = none).
     auto emit_window = [&](const ChunkState &C, const uint32_t (&wv)[8], uint32_t ffb, uint32_t Fr, int a, int b,
-                           unsigned long long G) {
+                           unsigned long long G, uint32_t mk) {
         uint8_t *outp = P.out + (size_t)C.img * P.out_cap;
-        const uint32_t nr = (uint32_t)max(b - a, 0) + Fr;
+        const uint32_t nr0 = (uint32_t)max(b - a, 0) + Fr;
+        const uint32_t nr = nr0 + (mk ? 2u : 0u);
         const uint32_t shb = (uint32_t)((reinterpret_cast<uintptr_t>(outp) + G) & 15u);
         // Every lane with owned bytes emits its whole 32-byte piece (bytes outside the owned
         // range land outside the part of sbuf that is copied out); sbuf index 16 + shb is
@@ -479,6 +507,10 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             }
         }
         __syncwarp();
+        if (mk) {  // 0xFF 0xDn, not subject to stuffing; after the barrier: the last lane's spare bytes land here too
+            if (lane == 0) { sbuf[16u + shb + nr0] = 0xFF; sbuf[16u + shb + nr0 + 1] = (uint8_t)mk; }
+            __syncwarp();
+        }
         if (G + nr <= P.out_cap) {
             uint8_t *gdst = outp + G - shb;  // 16-byte aligned
             const uint32_t end = shb + nr;
@@ -502,7 +534,7 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
     auto sweep = [&](ChunkState &C, bool emit, unsigned long long gbase) -> uint32_t {
         const uint32_t *const slot = M.slot[C.buf];
         const uint32_t *const spl = spill[C.buf];
-        const bool last_chunk = C.chunk == P.nchunks - 1;
+        const bool last_chunk = C.last;
         const uint32_t q0 = (uint32_t)C.Pc & 31u;         // bit offset of the chunk inside window word 0
         const uint32_t endbit = q0 + C.Lc;                // window bit index one past the chunk
         const uint32_t padc = last_chunk ? ((8u - (endbit & 7u)) & 7u) : 0u;   // 1-padding (bits.rs:261-272)
@@ -578,16 +610,18 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
                 C.kept = true;
             }
             if (emit) {
-                emit_window(C, wv, ffb, Fr, a, b, gbase + (r == 0 ? 0u : (uint32_t)(wb0 - (int)ob0)) + Fsum);
+                emit_window(C, wv, ffb, Fr, a, b, gbase + (r == 0 ? 0u : (uint32_t)(wb0 - (int)ob0)) + Fsum,
+                            r == nrounds - 1 ? C.marker : 0u);
             }
             Fsum += Fr;
             __syncwarp();  // obuf / sbuf are rewritten by the next round, or by the next chunk's stage
         }
-        if (emit && lane == 0 && last_chunk) {
-            const unsigned long long total = gbase - (C.Pc >> 3) + (((C.Pc >> 5) << 2) + ob1) + Fsum;
+        if (emit && lane == 0 && C.final_) {
+            const unsigned long long total = gbase + (ob1 - ob0) + Fsum;
             P.out_len[C.img] = total;
             if (total > P.out_cap) P.overflow[C.img] = 1;
         }
+        if (!emit) C.own = (ob1 - ob0) + Fsum + (C.marker ? 2u : 0u);
         return Fsum;
     };
 
@@ -595,7 +629,7 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
     auto phase_a = [&](ChunkState &C) {
         unsigned long long *st1 = P.st_bits + (size_t)C.img * P.nchunks;
         unsigned long long *st2 = P.st_ff + (size_t)C.img * P.nchunks;
-        if (C.chunk) {
+        if (!C.first) {
             const unsigned long long lb = look_back(st1, (int)C.chunk, lane);
             C.Pc = lb & ST_VAL;
             C.tailin = (uint32_t)(lb >> 55) & 0x7Fu;
@@ -603,7 +637,7 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             if (lane == 0) st_status(st1 + C.chunk, pack_status(ST_PFX, C.ctail, C.Pc + C.Lc));
         }
         C.Ftot = sweep(C, false, 0);
-        if (lane == 0) st_status(st2 + C.chunk, pack_status(C.chunk == 0 ? ST_PFX : ST_AGG, 0, C.Ftot));
+        if (lane == 0) st_status(st2 + C.chunk, pack_status(C.chunk == 0 ? ST_PFX : ST_AGG, 0, C.own));
     };
     // ---- B: stuffed-byte offset from chain 2, then the bytes ------------------------------------------
     auto phase_b = [&](ChunkState &C) {
@@ -613,20 +647,19 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             const unsigned long long lb = look_back(st2, (int)C.chunk, lane);
             ffx = lb & ST_VAL;
             C.fault |= (lb >> 62) != 0;
-            if (lane == 0) st_status(st2 + C.chunk, pack_status(ST_PFX, 0, ffx + C.Ftot));
+            if (lane == 0) st_status(st2 + C.chunk, pack_status(ST_PFX, 0, ffx + C.own));
         }
-        const unsigned long long gbase = (C.Pc >> 3) + ffx;
+        const unsigned long long gbase = ffx;  // chain 2 counts every byte written before this chunk
         if (C.kept) {
             const uint32_t q0 = (uint32_t)C.Pc & 31u, endbit = q0 + C.Lc;
-            const bool last_chunk = C.chunk == P.nchunks - 1;
-            const uint32_t padc = last_chunk ? ((8u - (endbit & 7u)) & 7u) : 0u;
+            const uint32_t padc = C.last ? ((8u - (endbit & 7u)) & 7u) : 0u;
             const uint32_t ob0 = q0 >> 3, ob1 = (endbit >> 3) + (padc ? 1u : 0u);
             const uint4 *keep = reinterpret_cast<const uint4 *>(M.slot[C.buf]);
             const uint4 x = keep[2 * lane], y = keep[2 * lane + 1];
             const uint32_t wv[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-            emit_window(C, wv, C.ffb, C.Ftot, (int)ob0, (int)ob1, gbase);
-            if (lane == 0 && last_chunk) {
-                const unsigned long long total = ffx + (((C.Pc >> 5) << 2) + ob1) + C.Ftot;
+            emit_window(C, wv, C.ffb, C.Ftot, (int)ob0, (int)ob1, gbase, C.marker);
+            if (lane == 0 && C.final_) {
+                const unsigned long long total = gbase + (ob1 - ob0) + C.Ftot;
                 P.out_len[C.img] = total;
                 if (total > P.out_cap) P.overflow[C.img] = 1;
             }
@@ -664,10 +697,15 @@ struct EntropyPlan {
 
 static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
 
-static EntropyPlan plan_entropy(uint32_t n, uint64_t nblocks)
+static EntropyPlan plan_entropy(uint32_t n, uint64_t nblocks, uint64_t rst_blocks)
 {
     EntropyPlan p;
     p.nchunks = (size_t)((nblocks + CB - 1) / CB);
+    if (rst_blocks && rst_blocks < nblocks) {  // every interval is chunked on its own
+        const uint64_t n_int = (nblocks + rst_blocks - 1) / rst_blocks, cpi = (rst_blocks + CB - 1) / CB;
+        const uint64_t last = nblocks - (n_int - 1) * rst_blocks;
+        p.nchunks = (size_t)((n_int - 1) * cpi + (last + CB - 1) / CB);
+    }
     size_t o = 0;
     p.off_st1 = o; o += a256((size_t)n * p.nchunks * 8);
     p.off_st2 = o; o += a256((size_t)n * p.nchunks * 8);
@@ -679,9 +717,10 @@ static EntropyPlan plan_entropy(uint32_t n, uint64_t nblocks)
     return p;
 }
 
-size_t entropy_scratch_bytes(uint32_t n, const FrameGeometry &g)
+size_t entropy_scratch_bytes(uint32_t n, const FrameGeometry &g, uint32_t restart_interval)
 {
-    return plan_entropy(n, g.ny + 2 * g.nc).total;
+    const uint64_t bpm = g.y_per_mcu + (g.has_chroma ? 2 : 0);
+    return plan_entropy(n, g.ny + 2 * g.nc, (uint64_t)restart_interval * bpm).total;
 }
 
 // Enqueue the entropy stage for n images (natural-order coefficient arrays) on ctx->stream.
@@ -689,11 +728,14 @@ size_t entropy_scratch_bytes(uint32_t n, const FrameGeometry &g)
 // *d_overflow point into the scratch.
 int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride, const int16_t *d_cb,
                         const int16_t *d_cr, size_t c_stride, uint32_t n, const FrameGeometry &g,
-                        const HuffTables &t, uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap,
-                        uint64_t **d_out_len, uint32_t **d_overflow)
+                        const HuffTables &t, uint32_t restart_interval, uint8_t *d_scratch, uint8_t *d_out,
+                        uint64_t out_cap, uint64_t **d_out_len, uint32_t **d_overflow)
 {
     const uint64_t nblocks = g.ny + 2 * g.nc;
-    const EntropyPlan pl = plan_entropy(n, nblocks);
+    const uint64_t bpm_ = g.y_per_mcu + (g.has_chroma ? 2 : 0);
+    uint64_t rst_blocks = (uint64_t)restart_interval * bpm_;
+    if (rst_blocks >= nblocks) rst_blocks = 0;  // a single interval: no marker is ever written
+    const EntropyPlan pl = plan_entropy(n, nblocks, rst_blocks);
     if (nblocks > 0xFFFFFFFFull || (uint64_t)n * pl.nchunks > 0x7FFFFFFFull)
         return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "entropy stage: too many blocks per call");
     EntParams P;
@@ -702,6 +744,9 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
     P.y_per_mcu = g.y_per_mcu;
     P.nblocks = (uint32_t)nblocks;
     P.nchunks = (uint32_t)pl.nchunks;
+    P.rst_blocks = (uint32_t)rst_blocks;
+    P.rst_mcus = rst_blocks ? restart_interval : 0u;
+    P.cpi = rst_blocks ? (uint32_t)((rst_blocks + CB - 1) / CB) : 0u;
     P.nimages = n;
     P.st_bits = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_st1);
     P.st_ff = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_st2);

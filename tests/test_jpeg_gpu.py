@@ -226,3 +226,18 @@ def test_large_pageable_input_takes_the_staged_copy(po, gpu_ctx):
         got = jpeg.encode(img, o, ctx=gpu_ctx)
         ref = po.jpeg_encode(img, w, h, 2, 80, int(ss))
         assert hashlib.sha256(got).digest() == hashlib.sha256(ref).digest()
+
+
+@pytest.mark.parametrize("w,h,ss,ri", [(256, 256, 1, 1), (256, 256, 1, 5), (333, 222, 0, 7), (640, 480, 1, 40),
+                                       (640, 480, 0, 33), (100, 75, 1, 65535), (1000, 600, 1, 63)])
+def test_restart_intervals_on_the_gpu_coder(po, gpu_ctx, w, h, ss, ri):
+    """handle_restart (src/jpeg/mod.rs:1423-1445): per-interval 1-padding, RSTn markers (not
+    stuffed, none before EOI), DC predictors reset - intervals shorter, equal to and longer than a
+    32-block chunk, not dividing the MCU count, and larger than the image."""
+    for img in (po.gen_noise(w, h, 3, 3), po.gen_gradient_rgb(w, h)):
+        for q, opt in ((80, False), (97, True)):
+            o = JpegOptions(w, h, ColorType.Rgb, q, Subsampling(ss), ri, opt)
+            assert jpeg.encode(img, o, ctx=gpu_ctx) == po.jpeg_encode(img, w, h, 2, q, ss, ri, opt), (q, opt)
+    g = po.gen_noise(w, h, 1, 5)
+    o = JpegOptions(w, h, ColorType.Gray, 85, Subsampling.S444, ri)
+    assert jpeg.encode(g, o, ctx=gpu_ctx) == po.jpeg_encode(g, w, h, 0, 85, 0, ri, False)
