@@ -170,6 +170,17 @@ int pixo_b200_jpeg_entropy_encode(pixo_b200_ctx *ctx, const int16_t *y, const in
                                   uint32_t restart_interval, uint32_t optimize_huffman,
                                   uint8_t *out, size_t out_cap, size_t *out_len);
 
+/* The same for coefficient arrays that live on the DEVICE (natural order, the layout
+ * pixo_b200_jpeg_coefficients_dev writes): optimised-table statistics (K3) and the Huffman /
+ * stuffing / restart stage (k_huff) run on the GPU, only the scan bytes come back; out receives
+ * the complete JPEG.  This is what a frame tiled over several GPUs uses once its bands'
+ * coefficients have been gathered on one of them. */
+int pixo_b200_jpeg_entropy_encode_dev(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb,
+                                      const int16_t *d_cr, uint32_t width, uint32_t height,
+                                      uint32_t color_type, uint32_t quality, uint32_t subsampling,
+                                      uint32_t restart_interval, uint32_t optimize_huffman,
+                                      uint8_t *out, size_t out_cap, size_t *out_len);
+
 /* ---- PNG -------------------------------------------------------------------------------- */
 
 /* Replaces filter::apply_filters_with_row_bytes — src/png/filter.rs:64-206 (+ the rayon path

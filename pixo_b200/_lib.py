@@ -61,6 +61,9 @@ SYMBOLS = {
     "pixo_b200_jpeg_entropy_encode": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32,
                                                 C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp,
                                                 C.c_size_t, szp]),
+    "pixo_b200_jpeg_entropy_encode_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                    C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp,
+                                                    C.c_size_t, szp]),
     "pixo_b200_png_filter": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_size_t, C.c_uint32,
                                        C.c_uint32, vp, u32p]),
     "pixo_b200_png_filter_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32,

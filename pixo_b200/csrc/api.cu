@@ -694,6 +694,66 @@ int pixo_b200_jpeg_entropy_encode(pixo_b200_ctx *ctx, const int16_t *y, const in
                                     threads < 1 ? 1 : threads);
 }
 
+int pixo_b200_jpeg_entropy_encode_dev(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb,
+                                      const int16_t *d_cr, uint32_t width, uint32_t height,
+                                      uint32_t color_type, uint32_t quality, uint32_t subsampling,
+                                      uint32_t restart_interval, uint32_t optimize_huffman,
+                                      uint8_t *out, size_t out_cap, size_t *out_len)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    if (quality == 0 || quality > 100)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_QUALITY, "Invalid quality %u: must be 1-100", quality);
+    if (restart_interval > 65535)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_RESTART, "Invalid restart interval %u", restart_interval);
+    PIXO_TRY(validate_jpeg(ctx, width, height, color_type, subsampling));
+    if (!d_y || !out || !out_len || (color_type != PIXO_B200_GRAY && (!d_cb || !d_cr)))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    if (out_cap < 1024 + 2)
+        return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small", out_cap);
+    const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
+    uint8_t lum_zz[64], chr_zz[64];
+    quant_tables((int)quality, lum_zz, chr_zz, nullptr, nullptr);
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, kHistWords * sizeof(uint64_t) + 256));
+    auto *h_meta = reinterpret_cast<uint8_t *>(ctx->h_misc.ptr);
+    HuffTables t;
+    huff_standard(t);
+    if (optimize_huffman) {
+        PIXO_TRY(ensure_dev(ctx, ctx->d_misc, kHistWords * sizeof(uint64_t) + 256));
+        auto *d_hist = reinterpret_cast<uint64_t *>(ctx->d_misc.ptr);
+        auto *h_hist = reinterpret_cast<uint64_t *>(h_meta + 256);
+        PIXO_TRY(launch_jpeg_histogram(ctx, d_y, 0, d_cb, d_cr, 0, 1, g.ny, g.nc, g.y_per_mcu, restart_interval,
+                                       false, d_hist));
+        PIXO_CUDA(ctx, cudaMemcpyAsync(h_hist, d_hist, kHistWords * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!huff_from_histogram(h_hist, g.has_chroma, t)) huff_standard(t);  // unwrap_or_default
+    }
+    const size_t hdr = write_headers(out, g, lum_zz, chr_zz, t, restart_interval);
+    const size_t scan_cap = (out_cap - hdr - 2) & ~(size_t)15;
+    PIXO_TRY(ensure_dev(ctx, ctx->d_out, scan_cap + 16));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(1, g, restart_interval)));
+    uint64_t *d_len = nullptr;
+    uint32_t *d_ovf = nullptr;
+    auto *d_scan = reinterpret_cast<uint8_t *>(ctx->d_out.ptr);
+    PIXO_TRY(launch_jpeg_entropy(ctx, d_y, 0, d_cb, d_cr, 0, 1, g, t, restart_interval,
+                                 reinterpret_cast<uint8_t *>(ctx->d_ent.ptr), d_scan, scan_cap, &d_len, &d_ovf));
+    auto *h_len = reinterpret_cast<uint64_t *>(h_meta);
+    auto *h_ovf = reinterpret_cast<uint32_t *>(h_meta + 8);
+    PIXO_CUDA(ctx, cudaMemcpyAsync(h_len, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*h_ovf)
+        return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small (need %zu)", out_cap,
+                         hdr + (size_t)*h_len + 2);
+    const size_t body = (size_t)*h_len;
+    PIXO_CUDA(ctx, cudaMemcpyAsync(out + hdr, d_scan, body, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out[hdr + body] = 0xFF;
+    out[hdr + body + 1] = 0xD9;
+    *out_len = hdr + body + 2;
+    return 0;
+}
+
 // ---- PNG ----------------------------------------------------------------------------------
 
 static int validate_png(pixo_b200_ctx *ctx, uint32_t width, uint32_t height, size_t row_bytes,

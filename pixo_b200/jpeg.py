@@ -172,3 +172,21 @@ def entropy_encode(y, cb, cr, options: JpegOptions, ctx: Context | None = None) 
         int(bool(options.optimize_huffman)), buf.ctypes.data, cap, C.byref(n))
     _lib.check(ctx.handle if ctx else None, rc)
     return buf[: n.value].tobytes()
+
+
+def entropy_encode_dev(d_y, d_cb, d_cr, options: JpegOptions, ctx: Context | None = None) -> bytes:
+    """Entropy-code coefficient arrays that live on the device (anything with .data_ptr(), e.g.
+    int16 torch tensors in compute_all_coefficients' layout) into a complete JPEG: Huffman
+    statistics, bit packing, stuffing and restart markers run on the GPU."""
+    ctx = ctx or default_context()
+    cap = output_capacity(options.width, options.height)
+    buf = np.empty(cap, np.uint8)
+    n = C.c_size_t()
+    ptr = lambda t: None if t is None else int(t.data_ptr())
+    rc = _lib.load().pixo_b200_jpeg_entropy_encode_dev(
+        ctx.handle, ptr(d_y), ptr(d_cb), ptr(d_cr), int(options.width), int(options.height),
+        int(options.color_type), int(options.quality), int(options.subsampling),
+        int(options.restart_interval or 0), int(bool(options.optimize_huffman)), buf.ctypes.data, cap,
+        C.byref(n))
+    _lib.check(ctx.handle, rc)
+    return buf[: n.value].tobytes()
