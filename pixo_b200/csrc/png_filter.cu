@@ -551,24 +551,25 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
         if (filter >= 5) {
             uint32_t T[5] = {0, 0, 0, 0, 0};
             const bool fast = P.strategy == PIXO_B200_FILTER_ADAPTIVE_FAST;
-            if (fast) {
-                for (uint32_t k = tid; k < nw; k += PNG_THREADS) {
-                    uint32_t x, a, b, c, mask;
-                    operands(k, x, a, b, c, mask);
-                    T[1] += __vsadu4(__vabsdiffu4(x, a) & mask, 0x80808080u);
-                    T[2] += __vsadu4(__vabsdiffu4(x, b) & mask, 0x80808080u);
-                    T[4] += __vsadu4(__vabsdiffu4(x, paeth_pred4(a, b, c)) & mask, 0x80808080u);
-                }
-            } else {
-                for (uint32_t k = tid; k < nw; k += PNG_THREADS) {
-                    uint32_t x, a, b, c, mask;
-                    operands(k, x, a, b, c, mask);
+            // every word below `full` is whole: no masking there; the ragged last word (rows whose
+            // length is not a multiple of 4) is scored by one thread with its mask
+            auto score = [&](uint32_t k, uint32_t mask, bool all_five) {
+                uint32_t x, a, b, c, unused;
+                operands(k, x, a, b, c, unused);
+                if (all_five) {
                     T[0] += __vsadu4(x & mask, 0x80808080u);
-                    T[1] += __vsadu4(__vabsdiffu4(x, a) & mask, 0x80808080u);
-                    T[2] += __vsadu4(__vabsdiffu4(x, b) & mask, 0x80808080u);
                     T[3] += __vsadu4(__vabsdiffu4(x, __vhaddu4(a, b)) & mask, 0x80808080u);
-                    T[4] += __vsadu4(__vabsdiffu4(x, paeth_pred4(a, b, c)) & mask, 0x80808080u);
                 }
+                T[1] += __vsadu4(__vabsdiffu4(x, a) & mask, 0x80808080u);
+                T[2] += __vsadu4(__vabsdiffu4(x, b) & mask, 0x80808080u);
+                T[4] += __vsadu4(__vabsdiffu4(x, paeth_pred4(a, b, c)) & mask, 0x80808080u);
+            };
+            if (fast) {
+                for (uint32_t k = tid; k < full; k += PNG_THREADS) score(k, 0xFFFFFFFFu, false);
+                if (full < nw && tid == (int)(full % PNG_THREADS)) score(full, tailmask, false);
+            } else {
+                for (uint32_t k = tid; k < full; k += PNG_THREADS) score(k, 0xFFFFFFFFu, true);
+                if (full < nw && tid == (int)(full % PNG_THREADS)) score(full, tailmask, true);
             }
 #pragma unroll
             for (int f = 0; f < 5; ++f) {
