@@ -130,10 +130,11 @@ int pixo_b200_jpeg_coefficients_dev(pixo_b200_ctx *ctx, const uint8_t *d_pixels,
                                     size_t c_stride, uint32_t flags, uint64_t *d_hist);
 
 /* Replaces pixo::jpeg::encode_into — src/jpeg/mod.rs:328-447 (baseline: encode_scan :1408).
- * GPU: colour/subsample/DCT/quantise (+ symbol statistics when optimize_huffman);
- * host: headers (:449-648), Huffman tables (src/jpeg/huffman.rs:100-391) and bit packing
- * (huffman.rs:423-481, src/bits.rs:195-290), byte-identical to the reference.
- * restart_interval 0 = None.  progressive / trellis_quant are outside this path
+ * GPU: colour/subsample/DCT/quantise, symbol statistics when optimize_huffman, Huffman bit
+ * packing with 0xFF stuffing and restart markers (huffman.rs:423-481, src/bits.rs:195-290,
+ * mod.rs:1423-1445); host: headers (:449-648) and Huffman table construction
+ * (src/jpeg/huffman.rs:100-391).  Byte-identical to the reference.  Only the scan bytes come
+ * back over PCIe.  restart_interval 0 = None.  progressive / trellis_quant are outside this path
  * (PIXO_B200_ERR_UNSUPPORTED when non-zero). */
 int pixo_b200_jpeg_encode(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t pixels_len,
                           uint32_t width, uint32_t height, uint32_t color_type, uint32_t quality,
@@ -142,7 +143,7 @@ int pixo_b200_jpeg_encode(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t pixe
                           uint8_t *out, size_t out_cap, size_t *out_len);
 
 /* Batch of n_images frames of identical geometry and options (frame i at pixels + i*len).
- * Transfers, kernels and host entropy coding of different frames overlap.  out: n_images
+ * Transfers and kernels of different frames overlap.  out: n_images
  * slots of out_cap_each bytes; out_lens[i] receives each JPEG's length. */
 int pixo_b200_jpeg_encode_batch(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t pixels_len_each,
                                 uint32_t n_images, uint32_t width, uint32_t height,
@@ -154,7 +155,8 @@ int pixo_b200_jpeg_encode_batch(pixo_b200_ctx *ctx, const uint8_t *pixels, size_
  * frame i at d_pixels + i*pixel_stride -> entropy-coded scan bytes (what encode_scan appends
  * between the SOS header and EOI, src/jpeg/mod.rs:1408-1563) at d_scan + i*scan_cap_each, byte
  * count in d_scan_len[i] (the size needed, also when it did not fit); d_overflow[i] != 0 when
- * scan_cap_each was too small.  Baseline, standard Huffman tables, no restart interval.  Headers/EOI are the caller's (pixo_b200_jpeg_encode* add them). */
+ * scan_cap_each was too small.  Baseline, standard Huffman tables, no restart interval.
+ * Headers/EOI are the caller's (pixo_b200_jpeg_encode* add them). */
 int pixo_b200_jpeg_encode_dev(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pixel_stride,
                               uint32_t n_images, uint32_t width, uint32_t height,
                               uint32_t color_type, uint32_t quality, uint32_t subsampling,
