@@ -61,3 +61,20 @@ def test_product_does_not_link_or_import_the_oracle():
                 assert "pixo_oracle" not in txt and "pyoracle" not in txt, f
     ldd = subprocess.run(["ldd", os.path.join(pkg, "libpixo_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in ldd
+
+
+def test_plain_c_client_compiles_links_and_runs(lib, tmp_path):
+    """include/pixo_b200.h is a C header (strict C11, -Wall -Wextra -Werror -pedantic) and the
+    library links from C: tests/c/abi_client.c exercises the host-only entry points and the loud
+    no-device failure exactly as a cgo / Rust FFI / JNI binding would see them."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "abi_client")
+    pkg = os.path.join(ROOT, "pixo_b200")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_client.c"), "-o", exe, "-L", pkg, "-lpixo_b200",
+                    f"-Wl,-rpath,{pkg}"], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "abi_client ok" in out.stdout, (out.returncode, out.stdout, out.stderr)
