@@ -717,312 +717,6 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
 }
 
 // =========================================================================================
-// K1p: the same path with every block shared by a LANE PAIR (experimental, PIXO_B200_K1_PAIR=1).
-// K1 is bound by dependent-chain latency at 12 warps per SM (168 registers hold a whole block);
-// here lane 2p owns rows 0-3 of block p and lane 2p+1 rows 7,6,5,4, so a lane carries half the
-// state and more warps fit.  The row pass is lane-local.  For the column pass lane h takes the
-// column pairs 2h, 2h+1: the lanes swap the halves they do not keep (one shuffle per packed
-// value) and, because partner rows r and 7-r meet in the first butterfly, both lanes run the
-// SAME code: tmp_r = own + got, tmp_(7-r) = own - got, with the difference negated on the odd
-// lane (b - a == -(a - b) exactly; only the sign of exact zeros can differ, which the
-// quantiser maps to 0 either way).  Unit = 8 MCUs (128 x 16 px, two 3 KB half tiles).
-// =========================================================================================
-constexpr int KP_MCUS = 8;
-constexpr int KP_HB = 4 * 16 * 3;             // 192 bytes per half-tile row (4 MCUs)
-constexpr int KP_HALF_BYTES = 16 * KP_HB;     // 3 KB; also hosts that half's 2 KB output stage
-constexpr int KP_TILE_BYTES = 2 * KP_HALF_BYTES;
-#ifndef KP_MIN_BLOCKS
-#define KP_MIN_BLOCKS 4
-#endif
-
-struct __align__(128) KPWarpSmem {
-    uint8_t tile[2][KP_HALF_BYTES];
-    uint32_t csum[KP_MCUS * 64];
-    uint64_t bar;
-};
-struct __align__(128) KPSmem {
-    KPWarpSmem w[K1_WARPS];
-    QuantSmem q;
-};
-
-// aan_1d_x2_core after its first butterfly stage: t[k] = tmp_k
-__device__ __forceinline__ void aan_1d_x2_tail(const f2 (&t)[8], f2 (&o)[8], const f2 zero2)
-{
-#define MULZ(a, c) fma2((a), K2(c), zero2)
-    const f2 tmp10 = add2(t[0], t[3]), tmp13 = sub2(t[0], t[3]);
-    const f2 tmp11 = add2(t[1], t[2]), tmp12 = sub2(t[1], t[2]);
-    o[0] = add2(tmp10, tmp11);
-    o[4] = sub2(tmp10, tmp11);
-    const f2 z1 = MULZ(add2(tmp12, tmp13), AAN_A1);
-    o[2] = add2(tmp13, z1);
-    o[6] = sub2(tmp13, z1);
-    const f2 u10 = add2(t[4], t[5]), u11 = add2(t[5], t[6]), u12 = add2(t[6], t[7]);
-    const f2 z5 = MULZ(sub2(u10, u12), AAN_A5);
-    const f2 z2 = add2(MULZ(u10, AAN_A2), z5);
-    const f2 z4 = add2(MULZ(u12, AAN_A4), z5);
-    const f2 z3 = MULZ(u11, AAN_A3);
-    const f2 z11 = add2(t[7], z3), z13 = sub2(t[7], z3);
-    o[5] = add2(z13, z2);
-    o[3] = sub2(z13, z2);
-    o[1] = add2(z11, z4);
-    o[7] = sub2(z11, z4);
-#undef MULZ
-}
-
-// R[i][c] = (v[lr 2i][c], v[lr 2i+1][c]) for the lane's four local rows lr (global row lr on the
-// even lane, 7 - lr on the odd one).  `out`: the block's 128-byte stage slot as 16 x 8 bytes.
-__device__ __forceinline__ void dct_quant_store_pair(f2 (&R)[2][8], const QPair *__restrict__ tab,
-                                                     uint2 *__restrict__ out, const int swz,
-                                                     const f2 zero2, const int h, const unsigned pairs)
-{
-    constexpr float SK[8] = {AAN_S0, AAN_S1, AAN_S2, AAN_S3, AAN_S4, AAN_S5, AAN_S6, AAN_S7};
-    f2 Cl[4][4];  // Cl[lr][j] = (V[row][2j], V[row][2j+1]) after the row pass
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        f2 o[8];
-        aan_1d_x2_core(R[i], o, zero2);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float a0, a1, b0, b1;
-            mulc(o[2 * j], SK[2 * j], a0, a1);
-            mulc(o[2 * j + 1], SK[2 * j + 1], b0, b1);
-            Cl[2 * i][j] = pk(a0, b0);
-            Cl[2 * i + 1][j] = pk(a1, b1);
-        }
-    }
-    const f2 neg = h ? 0x8000000080000000ull : 0ull;
-    const f2 half2 = K2(0.5f), magic2 = K2(12582912.0f);
-    uint32_t kSign, kOne;
-    asm("mov.b32 %0, 0x80000000;" : "=r"(kSign));
-    asm("mov.b32 %0, 0x3F800000;" : "=r"(kOne));
-    uint32_t W[8][2];
-#pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-        float4 T[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) T[r] = *reinterpret_cast<const float4 *>(&tab[r * 4 + 2 * h + jj]);
-        f2 t[8];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const f2 X = Cl[r][jj], Y = Cl[r][2 + jj];
-            const f2 snd = h ? X : Y, own = h ? Y : X;
-            const f2 got = __shfl_xor_sync(pairs, snd, 1);   // `pairs`: the lanes of all active pairs
-            t[r] = add2(own, got);            // tmp_r     = d_r + d_(7-r)
-            t[7 - r] = sub2(own, got) ^ neg;  // tmp_(7-r) = d_r - d_(7-r)
-        }
-        f2 o[8];
-        aan_1d_x2_tail(t, o, zero2);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const f2 nd = pk(T[r].x, T[r].y), rc = pk(T[r].z, T[r].w);
-            const f2 x = mul2(o[r], K2(SK[r]));
-            const f2 q0 = mul2(x, rc);
-            const f2 e = fma2(q0, nd, x);
-            const f2 q = fma2(e, rc, q0);
-            uint32_t ql, qh;
-            upk_u(q, ql, qh);
-            uint32_t sl, sh;
-            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(sl) : "r"(ql), "r"(kSign), "r"(kOne));
-            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(sh) : "r"(qh), "r"(kSign), "r"(kOne));
-            const f2 sg = pk(__uint_as_float(sl), __uint_as_float(sh));
-            const f2 w = add2_rz(q, half2);
-            const f2 tt = fma2_rm(w, sg, magic2);
-            uint32_t tl, th, ng;
-            upk_u(tt, tl, th);
-            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(ng) : "r"(ql), "r"(qh), "r"(0xFFBBu));
-            W[r][jj] = __byte_perm(tl, th, 0x5410) ^ ng;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) out[((r ^ swz) << 1) + h] = make_uint2(W[r][0], W[r][1]);
-}
-
-// 16 stage slots (2 KB, swizzled) -> global: instruction j moves slots 4j..4j+3
-template <typename SwzFn, typename DstFn>
-__device__ __forceinline__ void flush_stage16(const uint4 *__restrict__ stage, int lane, SwzFn swz_of,
-                                              DstFn dst_of)
-{
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int s = j * 4 + (lane >> 3), k = lane & 7;
-        const uint4 v = stage[s * 8 + (k ^ swz_of(s))];
-        uint4 *d = dst_of(s);
-        if (d) d[k] = v;
-    }
-    __syncwarp();
-}
-
-// K1Params with units_x = units of 8 MCUs per MCU row
-__global__ void __launch_bounds__(K1_THREADS, KP_MIN_BLOCKS)
-k_jpeg_420p(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab qt,
-            const __grid_constant__ CUtensorMap tmap)
-{
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    KPSmem &S = *reinterpret_cast<KPSmem *>(smem_raw);
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int p = lane >> 1, h = lane & 1;
-    KPWarpSmem &WS = S.w[warp];
-
-    fill_quant_smem(&S.q, qt, 4.0f, tid, K1_THREADS);
-    if (lane == 0) {
-        mbar_init(&WS.bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const f2 zero2 = pk(P.zero[0], P.zero[1]);
-    const uint64_t units_per_img = (uint64_t)P.mcus_y * P.units_x;
-    const uint64_t nunits = units_per_img * P.n_images;
-    const uint64_t stride = (uint64_t)gridDim.x * K1_WARPS;
-    uint32_t phase = 0;
-
-    auto decode = [&](uint64_t u, uint32_t &img, uint32_t &my, uint32_t &ux) {
-        img = (uint32_t)(u / units_per_img);
-        const uint32_t rem = (uint32_t)(u - (uint64_t)img * units_per_img);
-        my = rem / P.units_x;
-        ux = rem - my * P.units_x;
-    };
-    auto unit_by_tma = [&](uint32_t my) { return P.use_tma && (my * 16 + 16 <= P.h); };
-    auto issue_tma = [&](uint64_t u_) {
-        uint32_t img_, my_, ux_;
-        decode(u_, img_, my_, ux_);
-        if (unit_by_tma(my_)) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&WS.bar, KP_TILE_BYTES);
-            tma_load_3d(WS.tile[0], &tmap, (int)(ux_ * (2 * KP_HB / 8)), (int)(my_ * 16), (int)img_, &WS.bar);
-            tma_load_3d(WS.tile[1], &tmap, (int)(ux_ * (2 * KP_HB / 8) + KP_HB / 8), (int)(my_ * 16), (int)img_, &WS.bar);
-        }
-    };
-
-    uint64_t u = (uint64_t)blockIdx.x * K1_WARPS + warp;
-    if (u < nunits && lane == 0) issue_tma(u);
-
-    for (; u < nunits; u += stride) {
-        uint32_t img, my, ux;
-        decode(u, img, my, ux);
-        if (unit_by_tma(my)) {
-            mbar_wait(&WS.bar, phase);
-            phase ^= 1;
-        } else {
-            const uint8_t *image = P.pixels + (size_t)img * P.pixel_stride;
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const uint32_t x0 = ux * (KP_MCUS * 16) + half * 64;
-                if (x0 < P.w) warp_load_tile_rgb<16, 64>(WS.tile[half], image, P.w, P.h, x0, my * 16, lane);
-            }
-            __syncwarp();
-        }
-        const uint32_t mcu0 = ux * KP_MCUS;
-        const uint32_t n_mcu = min((uint32_t)KP_MCUS, P.mcus_x - mcu0);
-        const size_t mcu_base = (size_t)my * P.mcus_x + mcu0;
-
-#pragma unroll 1
-        for (int job = 0; job < 3; ++job) {
-            f2 R[2][8];
-            const QPair *tab;
-            uint4 *stage;
-            int slot, swz;
-            bool active;
-            if (job < 2) {
-                // ---- 16 Y blocks (4 MCUs), a lane pair per block ----
-                const int by = p >> 3, k8 = p & 7;
-                const int mj = k8 >> 1, bx = k8 & 1;
-                const int mcu = job * 4 + mj;
-                active = (uint32_t)mcu < n_mcu;
-                const uint8_t *base = WS.tile[job] + (by * 8) * KP_HB + (mj * 2 + bx) * 24;
-                uint4 *cdst = reinterpret_cast<uint4 *>(WS.csum) + mcu * 16;
-                if (active) {
-#pragma unroll
-                    for (int rp = 0; rp < 2; ++rp) {
-                        const int g0 = h ? 7 - 2 * rp : 2 * rp, g1 = h ? 6 - 2 * rp : 2 * rp + 1;
-                        float y0[8], y1[8];
-                        uint32_t h0[4], h1[4];
-                        {
-                            const uint2 *q = reinterpret_cast<const uint2 *>(base + g0 * KP_HB);
-                            const uint2 a = q[0], b = q[1], c = q[2];
-                            const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-                            ycc_row8(wds, y0, h0);
-                        }
-                        {
-                            const uint2 *q = reinterpret_cast<const uint2 *>(base + g1 * KP_HB);
-                            const uint2 a = q[0], b = q[1], c = q[2];
-                            const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-                            ycc_row8(wds, y1, h1);
-                        }
-#pragma unroll
-                        for (int x = 0; x < 8; ++x) R[rp][x] = sub2(pk(y0[x], y1[x]), K2(8388736.0f));
-                        const int logical = (by * 4 + (g0 >> 1)) * 2 + bx;   // quad row g0 / 2 == g1 / 2
-                        cdst[logical ^ (mcu & 7)] =
-                            make_uint4(h0[0] + h1[0], h0[1] + h1[1], h0[2] + h1[2], h0[3] + h1[3]);
-                    }
-                }
-                __syncwarp();  // every lane is done with this half tile
-                stage = reinterpret_cast<uint4 *>(WS.tile[job]);
-                slot = mj * 4 + by * 2 + bx;
-                swz = ((slot >> 3) << 1) | (slot & 1);
-                tab = S.q.lum;
-            } else {
-                const uint64_t un = u + stride;
-                if (lane == 0 && un < nunits) issue_tma(un);   // both half tiles were flushed
-                // ---- pairs 0-7: Cb of MCU p, pairs 8-15: Cr of MCU p-8 ----
-                const int comp = p >> 3, mcu = p & 7;
-                active = (uint32_t)mcu < n_mcu;
-                const uint4 *csrc = reinterpret_cast<const uint4 *>(WS.csum) + mcu * 16;
-                const uint32_t sel = comp == 0 ? 0x7610u : 0x7632u;
-                const float bias = comp == 0 ? 8453632.0f : 8453635.0f;
-                if (active) {
-#pragma unroll
-                    for (int rp = 0; rp < 2; ++rp) {
-                        const int g0 = h ? 7 - 2 * rp : 2 * rp, g1 = h ? 6 - 2 * rp : 2 * rp + 1;
-                        float v0[8], v1[8];
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const uint4 s0 = csrc[(g0 * 2 + hh) ^ (mcu & 7)];
-                            const uint4 s1 = csrc[(g1 * 2 + hh) ^ (mcu & 7)];
-                            const uint32_t a[4] = {s0.x, s0.y, s0.z, s0.w};
-                            const uint32_t b[4] = {s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                v0[hh * 4 + k] = __uint_as_float(__byte_perm(a[k], 0x4B000000u, sel));
-                                v1[hh * 4 + k] = __uint_as_float(__byte_perm(b[k], 0x4B000000u, sel));
-                            }
-                        }
-#pragma unroll
-                        for (int x = 0; x < 8; ++x) R[rp][x] = sub2(K2(bias), pk(v0[x], v1[x]));
-                    }
-                }
-                __syncwarp();  // every lane has read its chroma sums: the buffer becomes the stage
-                stage = reinterpret_cast<uint4 *>(WS.csum);
-                slot = p;                                   // 0-7 Cb, 8-15 Cr
-                swz = slot & 7;
-                tab = S.q.chr;
-            }
-            // both lanes of a pair take part in the exchange: `active` is pair-uniform
-            const unsigned pairs = __ballot_sync(0xffffffffu, active);
-            if (active) dct_quant_store_pair(R, tab, reinterpret_cast<uint2 *>(stage + slot * 8), swz, zero2, h, pairs);
-            if (job < 2) {
-                uint4 *ybase = reinterpret_cast<uint4 *>(P.y + (size_t)img * P.y_stride +
-                                                         (mcu_base + job * 4) * 4 * 64);
-                const uint32_t first = job * 4;
-                flush_stage16(
-                    stage, lane, [](int s) { return ((s >> 3) << 1) | (s & 1); },
-                    [&](int s) -> uint4 * { return first + (s >> 2) < n_mcu ? ybase + s * 8 : nullptr; });
-            } else {
-                uint4 *cbb = reinterpret_cast<uint4 *>(P.cb + (size_t)img * P.c_stride + mcu_base * 64);
-                uint4 *crb = reinterpret_cast<uint4 *>(P.cr + (size_t)img * P.c_stride + mcu_base * 64);
-                flush_stage16(
-                    stage, lane, [](int s) { return s & 7; },
-                    [&](int s) -> uint4 * {
-                        return (uint32_t)(s & 7) < n_mcu ? (s < 8 ? cbb : crb) + (s & 7) * 8 : nullptr;
-                    });
-            }
-        }
-    }
-}
-
-// =========================================================================================
 // K2: RGB 4:4:4 (warp-autonomous, below) and Gray (64 threads, CTA = 64 blocks of one block
 // row; every warp owns 32 consecutive blocks, runs the same packed block pipeline as K1 and
 // flushes its 4 KB stage with coalesced stores).
@@ -1435,28 +1129,6 @@ int launch_k1(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint32
     P.zero[0] = 0.0f; P.zero[1] = 0.0f;
     alignas(64) CUtensorMap tm;
     memset(&tm, 0, sizeof tm);
-    static const bool pair_kernel = getenv("PIXO_B200_K1_PAIR") != nullptr;  // experimental K1p, natural order only
-    if (pair_kernel && !zigzag) {
-        P.units_x = (P.mcus_x + KP_MCUS - 1) / KP_MCUS;
-        P.use_tma = make_rgb_tensor_map(&tm, px, pixel_stride, n, w, h, KP_HB / 8, 16) ? 1u : 0u;
-        static int bps_p[64];
-        const size_t smem_p = sizeof(KPSmem);
-        int &bp = bps_p[ctx->device & 63];
-        if (!bp) {
-            PIXO_CUDA(ctx, cudaFuncSetAttribute(k_jpeg_420p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-            int nb = 0;
-            PIXO_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_jpeg_420p, K1_THREADS, smem_p));
-            bp = nb > 0 ? nb : 1;
-            if (getenv("PIXO_B200_DEBUG")) fprintf(stderr, "k_jpeg_420p: %d blocks/SM, %zu B smem\n", bp, smem_p);
-        }
-        const uint64_t nunits_p = (uint64_t)P.mcus_y * P.units_x * n;
-        uint64_t grid_p = (uint64_t)ctx->sm_count * bp;
-        if (grid_p > (nunits_p + K1_WARPS - 1) / K1_WARPS) grid_p = (nunits_p + K1_WARPS - 1) / K1_WARPS;
-        k_jpeg_420p<<<(unsigned)grid_p, K1_THREADS, smem_p, ctx->stream>>>(P, qt, tm);
-        ctx->launches++;
-        PIXO_CUDA(ctx, cudaGetLastError());
-        return 0;
-    }
     P.use_tma = make_rgb_tensor_map(&tm, px, pixel_stride, n, w, h, K1_HB / 8, 16) ? 1u : 0u;
     static int blocks_per_sm[64][2];  // function attributes are per device
     const size_t smem = sizeof(K1Smem);
