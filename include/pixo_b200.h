@@ -84,6 +84,16 @@ int pixo_b200_ctx_sync(pixo_b200_ctx *ctx);
 uint64_t pixo_b200_ctx_launch_count(const pixo_b200_ctx *ctx);
 /* number of host threads the host-side entropy coder may use (default: hardware threads) */
 int pixo_b200_ctx_set_host_threads(pixo_b200_ctx *ctx, int n);
+/* Observability of the one place host code can finish device work.  The GPU entropy stage writes
+ * each frame's scan into a device buffer sized by a heuristic (half the raw frame + 64 KiB, x 9/8);
+ * a frame that needs more is coded again on the GPU with the exact size (the kernel reports it),
+ * and only if that is switched off, or the device stage reports a fault, does the host coder
+ * finish the frame from the same GPU coefficient arrays.  host_fallbacks counts those frames
+ * since the context was created (0 in normal operation).
+ * set_scan_capacity: bytes_per_frame 0 restores the heuristic; gpu_retry 0 disables the second
+ * GPU pass (test hook: a tiny capacity with gpu_retry 0 forces the host coder). */
+uint64_t pixo_b200_ctx_host_fallbacks(const pixo_b200_ctx *ctx);
+int pixo_b200_ctx_set_scan_capacity(pixo_b200_ctx *ctx, size_t bytes_per_frame, int gpu_retry);
 
 /* device / pinned memory helpers so a Rust caller need not link the CUDA runtime */
 int pixo_b200_dev_alloc(pixo_b200_ctx *ctx, size_t bytes, void **dptr);
@@ -134,8 +144,10 @@ int pixo_b200_jpeg_coefficients_dev(pixo_b200_ctx *ctx, const uint8_t *d_pixels,
  * packing with 0xFF stuffing and restart markers (huffman.rs:423-481, src/bits.rs:195-290,
  * mod.rs:1423-1445); host: headers (:449-648) and Huffman table construction
  * (src/jpeg/huffman.rs:100-391).  Byte-identical to the reference.  Only the scan bytes come
- * back over PCIe.  restart_interval 0 = None.  progressive / trellis_quant are outside this path
- * (PIXO_B200_ERR_UNSUPPORTED when non-zero). */
+ * back over PCIe.  restart_interval 0 = None.  progressive is outside this path
+ * (PIXO_B200_ERR_UNSUPPORTED when non-zero); trellis_quant is accepted and ignored, exactly as
+ * the reference's baseline encode_scan ignores use_trellis (src/jpeg/mod.rs:1408-1563 always
+ * calls quantize_block). */
 int pixo_b200_jpeg_encode(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t pixels_len,
                           uint32_t width, uint32_t height, uint32_t color_type, uint32_t quality,
                           uint32_t subsampling, uint32_t restart_interval,

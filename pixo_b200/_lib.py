@@ -37,6 +37,8 @@ SYMBOLS = {
     "pixo_b200_ctx_sync": (C.c_int, [vp]),
     "pixo_b200_ctx_launch_count": (C.c_uint64, [vp]),
     "pixo_b200_ctx_set_host_threads": (C.c_int, [vp, C.c_int]),
+    "pixo_b200_ctx_host_fallbacks": (C.c_uint64, [vp]),
+    "pixo_b200_ctx_set_scan_capacity": (C.c_int, [vp, C.c_size_t, C.c_int]),
     "pixo_b200_dev_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
     "pixo_b200_dev_free": (C.c_int, [vp, vp]),
     "pixo_b200_host_alloc_pinned": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),

@@ -47,6 +47,16 @@ class Context:
     def set_host_threads(self, n: int):
         _lib.check(self._h, _lib.load().pixo_b200_ctx_set_host_threads(self._h, n))
 
+    def set_scan_capacity(self, bytes_per_frame: int = 0, gpu_retry: bool = True):
+        """Device scan buffer per frame (0 = heuristic) and whether an overflowing frame is re-coded on
+        the GPU (test hook: a tiny capacity with gpu_retry=False forces the host entropy coder)."""
+        _lib.check(self._h, _lib.load().pixo_b200_ctx_set_scan_capacity(self._h, int(bytes_per_frame), int(gpu_retry)))
+
+    @property
+    def host_fallbacks(self) -> int:
+        """Frames finished by the host entropy coder since the context was created."""
+        return int(_lib.load().pixo_b200_ctx_host_fallbacks(self._h))
+
     @property
     def launch_count(self) -> int:
         return int(_lib.load().pixo_b200_ctx_launch_count(self._h))

@@ -173,7 +173,8 @@ int pixo_b200_ctx_create(int device, pixo_b200_ctx **out)
     }
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         const int rc = cuda_fail(nullptr, e, "cudaStreamCreate");
         delete ctx;
         return rc;
@@ -190,7 +191,7 @@ void pixo_b200_ctx_destroy(pixo_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    Scratch *dev[] = {&ctx->d_in, &ctx->d_y, &ctx->d_cb, &ctx->d_cr, &ctx->d_misc, &ctx->d_out, &ctx->d_ent, &ctx->d_coef};
+    Scratch *dev[] = {&ctx->d_in, &ctx->d_y, &ctx->d_cb, &ctx->d_cr, &ctx->d_misc, &ctx->d_out, &ctx->d_ent, &ctx->d_coef, &ctx->d_retry};
     for (Scratch *s : dev) if (s->ptr) cudaFree(s->ptr);
     Scratch *host[] = {&ctx->h_in, &ctx->h_out, &ctx->h_misc};
     for (Scratch *s : host) if (s->ptr) cudaFreeHost(s->ptr);
@@ -198,6 +199,7 @@ void pixo_b200_ctx_destroy(pixo_b200_ctx *ctx)
     for (cudaEvent_t ev : ctx->stage_events) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     delete ctx;
 }
 
@@ -228,6 +230,16 @@ int pixo_b200_ctx_set_host_threads(pixo_b200_ctx *ctx, int n)
 {
     if (!ctx || n < 1) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "bad host thread count");
     ctx->host_threads = n;
+    return 0;
+}
+
+uint64_t pixo_b200_ctx_host_fallbacks(const pixo_b200_ctx *ctx) { return ctx ? ctx->host_fallbacks : 0; }
+
+int pixo_b200_ctx_set_scan_capacity(pixo_b200_ctx *ctx, size_t bytes_per_frame, int gpu_retry)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    ctx->scan_cap_override = bytes_per_frame;
+    ctx->gpu_retry = gpu_retry != 0;
     return 0;
 }
 
@@ -422,17 +434,46 @@ static int validate_encode(pixo_b200_ctx *ctx, size_t pixels_len, uint32_t width
     return 0;
 }
 
+// Synchronises every stream of the context when an entry point leaves early, so that no queued
+// copy still reads the caller's pixels or writes the caller's output after the error return.
+struct DrainOnError {
+    pixo_b200_ctx *ctx;
+    bool armed = true;
+    explicit DrainOnError(pixo_b200_ctx *c) : ctx(c) {}
+    ~DrainOnError()
+    {
+        if (!armed) return;
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->d2h_stream);
+        cudaGetLastError();
+    }
+};
+
+// Device scan capacity per frame: a JPEG that needs more than half its raw size (noise at very
+// high quality) is coded a second time with the exact size the kernel reported.
+static uint64_t default_scan_cap(const pixo_b200_ctx *ctx, size_t raw_bytes)
+{
+    const size_t want = ctx->scan_cap_override ? ctx->scan_cap_override : (raw_bytes / 2 + 65536) / 8 * 9;
+    return align_up(want < 1024 ? 1024 : want, 256);
+}
+
 // Encode n frames of identical geometry and options.  GPU: colour/DCT/quantise (K1/K2), symbol
-// statistics when optimize_huffman (K3), Huffman bit packing + 0xFF stuffing (jpeg_entropy.cu);
-// host: headers, optimised-table construction, EOI.  Frames are processed in groups; the H2D
-// copy of group g+1 runs on the copy stream under the kernels of group g, and only finished
-// scan bytes come back over PCIe (restart intervals included).  Only a capacity overflow (a
-// pathological input whose JPEG exceeds half the raw size) is finished by the host entropy
-// coder, which consumes the same GPU coefficient arrays.
+// statistics when optimize_huffman (K3), Huffman bit packing + 0xFF stuffing + restart markers
+// (k_huff); host: headers, optimised-table construction, EOI.  Frames are processed in groups of
+// up to 16 on three streams: the H2D copy of group g+1 (copy stream) and the D2H copy of group
+// g-1's scan bytes (d2h stream) run under the kernels of group g, and the host never drains the
+// compute stream between groups - it only waits for the event behind a group's 12-byte-per-frame
+// length readback before it queues that group's D2H.  Only finished scan bytes come back over
+// PCIe.  A frame whose scan outgrows the device buffer is coded again on the GPU with the exact
+// size; the host entropy coder (same GPU coefficient arrays) is the last resort for a faulted
+// device stage and is counted in ctx->host_fallbacks.
 static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_each, uint32_t n_images,
                          const FrameGeometry &g, uint32_t quality, uint32_t restart_interval,
                          bool optimize, uint8_t *out, size_t out_cap_each, size_t *out_lens)
 {
+    if (out_cap_each < 1024 + 2)  // before any GPU work is queued
+        return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small", out_cap_each);
     float lum[64], chr[64];
     uint8_t lum_zz[64], chr_zz[64];
     quant_tables((int)quality, lum_zz, chr_zz, lum, chr);
@@ -440,28 +481,29 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
     const size_t cbb = align_up(g.nc * 64 * sizeof(int16_t), 256);
     const size_t coef_each = yb + 2 * cbb;
     const size_t in_stride = align_up(len_each, 256);
-    // device-side scan capacity per frame; a JPEG that needs more (pathological noise at very high
-    // quality) is finished by the host coder from the same coefficients
-    const uint64_t scan_cap = align_up((len_each / 2 + 65536) / 8 * 9, 256);
-    const bool gpu_entropy = true;  // restart intervals included; the host coder only finishes capacity overflows
+    const uint64_t scan_cap = default_scan_cap(ctx, len_each);
+    const size_t ent_one = entropy_scratch_bytes(1, g, restart_interval);
 
     uint32_t G = n_images < 16 ? n_images : 16;
-    const size_t budget = (size_t)3 << 30;
+    const size_t budget = (size_t)4 << 30;
+    auto ent_bytes = [&](uint32_t k) {  // per-image tables run one k_huff pass per image, each with its own scratch
+        return optimize ? (size_t)k * ent_one : entropy_scratch_bytes(k, g, restart_interval);
+    };
     auto group_bytes = [&](uint32_t k) {
-        return 2 * (size_t)k * in_stride + (size_t)k * coef_each + entropy_scratch_bytes(k, g, restart_interval) +
-               2 * (size_t)k * scan_cap;
+        return 2 * (size_t)k * in_stride + 2 * (size_t)k * coef_each + ent_bytes(k) + 2 * (size_t)k * scan_cap;
     };
     while (G > 1 && group_bytes(G) > budget) --G;
     const uint32_t ngroups = (n_images + G - 1) / G;
 
     PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
     PIXO_TRY(ensure_dev(ctx, ctx->d_in, 2 * (size_t)G * in_stride));
-    PIXO_TRY(ensure_dev(ctx, ctx->d_coef, (size_t)G * coef_each));
-    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(G, g, restart_interval)));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_coef, 2 * (size_t)G * coef_each));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, ent_bytes(G)));
     PIXO_TRY(ensure_dev(ctx, ctx->d_out, 2 * (size_t)G * scan_cap));
     PIXO_TRY(ensure_dev(ctx, ctx->d_misc, (size_t)G * kHistWords * sizeof(uint64_t) + 256));
-    PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, (size_t)G * (kHistWords * sizeof(uint64_t) + 32) + 256));
-    while (ctx->events.size() < 6) {
+    const size_t meta_slot = align_up((size_t)G * 12, 256);
+    PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, 2 * meta_slot + (size_t)G * kHistWords * sizeof(uint64_t) + 256));
+    while (ctx->events.size() < 8) {
         cudaEvent_t ev;
         PIXO_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         ctx->events.push_back(ev);
@@ -469,13 +511,22 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
     cudaEvent_t *ev_in = &ctx->events[0];    // [2] input slot filled
     cudaEvent_t *ev_used = &ctx->events[2];  // [2] input slot consumed by the transform kernel
     cudaEvent_t *ev_out = &ctx->events[4];   // [2] scan bytes of the slot copied back
+    cudaEvent_t *ev_len = &ctx->events[6];   // [2] the slot's lengths / overflow flags are on the host
     auto *d_in = reinterpret_cast<uint8_t *>(ctx->d_in.ptr);
-    auto *d_coef = reinterpret_cast<uint8_t *>(ctx->d_coef.ptr);
     auto *d_scan = reinterpret_cast<uint8_t *>(ctx->d_out.ptr);
     auto *h_meta = reinterpret_cast<uint8_t *>(ctx->h_misc.ptr);
-    auto *h_len = reinterpret_cast<uint64_t *>(h_meta);
-    auto *h_ovf = reinterpret_cast<uint32_t *>(h_meta + (size_t)G * 8);
-    auto *h_hist = reinterpret_cast<uint64_t *>(h_meta + align_up((size_t)G * 12, 256));
+    auto *h_hist = reinterpret_cast<uint64_t *>(h_meta + 2 * meta_slot);
+    auto h_len_of = [&](int slot) { return reinterpret_cast<uint64_t *>(h_meta + (size_t)slot * meta_slot); };
+    auto h_ovf_of = [&](int slot) { return reinterpret_cast<uint32_t *>(h_meta + (size_t)slot * meta_slot + (size_t)G * 8); };
+    struct Coef { int16_t *y, *cb, *cr; };
+    const size_t cstride = coef_each / 2;
+    auto coef_of = [&](int slot) {
+        uint8_t *base = reinterpret_cast<uint8_t *>(ctx->d_coef.ptr) + (size_t)slot * G * coef_each;
+        return Coef{reinterpret_cast<int16_t *>(base), reinterpret_cast<int16_t *>(base + yb),
+                    reinterpret_cast<int16_t *>(base + yb + cbb)};
+    };
+    std::vector<HuffTables> tables[2];
+    DrainOnError drain(ctx);
 
     auto upload = [&](uint32_t gi) -> int {
         const uint32_t first = gi * G, cnt = std::min(G, n_images - first);
@@ -488,110 +539,154 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
         return 0;
     };
 
-    // make the copy stream start after whatever the caller already queued on the main stream
-    PIXO_CUDA(ctx, cudaEventRecord(ev_out[0], ctx->stream));
-    PIXO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev_out[0], 0));
-    PIXO_TRY(upload(0));
-    for (uint32_t gi = 0; gi < ngroups; ++gi) {
+    // queue the kernels of group gi and the readback of its lengths
+    auto compute = [&](uint32_t gi) -> int {
         const uint32_t first = gi * G, cnt = std::min(G, n_images - first);
         const int slot = (int)(gi & 1);
-        if (gi + 1 < ngroups) PIXO_TRY(upload(gi + 1));
+        const Coef c = coef_of(slot);
         PIXO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_in[slot], 0));
-        auto *dy = reinterpret_cast<int16_t *>(d_coef);
-        auto *dcb = reinterpret_cast<int16_t *>(d_coef + yb);
-        auto *dcr = reinterpret_cast<int16_t *>(d_coef + yb + cbb);
-        const size_t cstride = coef_each / 2;
         PIXO_TRY(launch_jpeg_transform(ctx, d_in + (size_t)slot * G * in_stride, in_stride, cnt, g.width,
-                                       g.height, g.color_type, g.subsampling, lum, chr, dy, cstride,
-                                       g.has_chroma ? dcb : nullptr, g.has_chroma ? dcr : nullptr, cstride, 0));
+                                       g.height, g.color_type, g.subsampling, lum, chr, c.y, cstride,
+                                       g.has_chroma ? c.cb : nullptr, g.has_chroma ? c.cr : nullptr, cstride, 0));
         PIXO_CUDA(ctx, cudaEventRecord(ev_used[slot], ctx->stream));
-        std::vector<HuffTables> tables(optimize ? cnt : 1);
+        std::vector<HuffTables> &tb = tables[slot];
+        tb.resize(optimize ? cnt : 1);
         if (optimize) {
             auto *d_hist = reinterpret_cast<uint64_t *>(ctx->d_misc.ptr);
-            PIXO_TRY(launch_jpeg_histogram(ctx, dy, cstride, dcb, dcr, cstride, cnt, g.ny, g.nc, g.y_per_mcu,
+            PIXO_TRY(launch_jpeg_histogram(ctx, c.y, cstride, c.cb, c.cr, cstride, cnt, g.ny, g.nc, g.y_per_mcu,
                                            restart_interval, false, d_hist));
             PIXO_CUDA(ctx, cudaMemcpyAsync(h_hist, d_hist, (size_t)cnt * kHistWords * sizeof(uint64_t),
                                            cudaMemcpyDeviceToHost, ctx->stream));
-            PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the table build needs the statistics
             for (uint32_t k = 0; k < cnt; ++k)  // unwrap_or_default, src/jpeg/mod.rs:379-392
-                if (!huff_from_histogram(h_hist + (size_t)k * kHistWords, g.has_chroma, tables[k])) huff_standard(tables[k]);
+                if (!huff_from_histogram(h_hist + (size_t)k * kHistWords, g.has_chroma, tb[k])) huff_standard(tb[k]);
         } else {
-            huff_standard(tables[0]);
+            huff_standard(tb[0]);
         }
         uint8_t *scan = d_scan + (size_t)slot * G * scan_cap;
-        bool fallback_all = !gpu_entropy;
-        if (gpu_entropy) {
-            if (gi >= 2) PIXO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_out[slot], 0));
-            uint64_t *d_len = nullptr;
-            uint32_t *d_ovf = nullptr;
-            auto *ent = reinterpret_cast<uint8_t *>(ctx->d_ent.ptr);
-            if (!optimize) {
-                PIXO_TRY(launch_jpeg_entropy(ctx, dy, cstride, dcb, dcr, cstride, cnt, g, tables[0], restart_interval, ent,
-                                             scan, scan_cap, &d_len, &d_ovf));
-                PIXO_CUDA(ctx, cudaMemcpyAsync(h_len, d_len, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
-                PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf, d_ovf, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            } else {
-                const size_t per = entropy_scratch_bytes(1, g, restart_interval);
-                for (uint32_t k = 0; k < cnt; ++k) {  // per-image tables: one pass per image
-                    PIXO_TRY(launch_jpeg_entropy(ctx, dy + (size_t)k * cstride, cstride, dcb + (size_t)k * cstride,
-                                                 dcr + (size_t)k * cstride, cstride, 1, g, tables[k],
-                                                 restart_interval, ent + (size_t)k * per, scan + (size_t)k * scan_cap,
-                                                 scan_cap, &d_len, &d_ovf));
-                    PIXO_CUDA(ctx, cudaMemcpyAsync(h_len + k, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
-                    PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf + k, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
-                }
+        if (gi >= 2) PIXO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_out[slot], 0));  // slot's previous D2H drained
+        uint64_t *d_len = nullptr;
+        uint32_t *d_ovf = nullptr;
+        auto *ent = reinterpret_cast<uint8_t *>(ctx->d_ent.ptr);
+        uint64_t *h_len = h_len_of(slot);
+        uint32_t *h_ovf = h_ovf_of(slot);
+        if (!optimize) {
+            PIXO_TRY(launch_jpeg_entropy(ctx, c.y, cstride, c.cb, c.cr, cstride, cnt, g, tb[0], restart_interval, ent,
+                                         scan, scan_cap, &d_len, &d_ovf));
+            PIXO_CUDA(ctx, cudaMemcpyAsync(h_len, d_len, (size_t)cnt * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf, d_ovf, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            for (uint32_t k = 0; k < cnt; ++k) {  // per-image tables: one pass per image, each in its own scratch
+                PIXO_TRY(launch_jpeg_entropy(ctx, c.y + (size_t)k * cstride, cstride, c.cb + (size_t)k * cstride,
+                                             c.cr + (size_t)k * cstride, cstride, 1, g, tb[k],
+                                             restart_interval, ent + (size_t)k * ent_one, scan + (size_t)k * scan_cap,
+                                             scan_cap, &d_len, &d_ovf));
+                PIXO_CUDA(ctx, cudaMemcpyAsync(h_len + k, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf + k, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
             }
-            PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
-        // assemble: headers on the host, scan bytes straight from the device, EOI
+        PIXO_CUDA(ctx, cudaEventRecord(ev_len[slot], ctx->stream));
+        return 0;
+    };
+
+    // headers on the host, scan bytes straight from the device (d2h stream), EOI
+    auto finish = [&](uint32_t gi) -> int {
+        const uint32_t first = gi * G, cnt = std::min(G, n_images - first);
+        const int slot = (int)(gi & 1);
+        const Coef c = coef_of(slot);
+        const std::vector<HuffTables> &tb = tables[slot];
+        uint8_t *scan = d_scan + (size_t)slot * G * scan_cap;
+        const uint64_t *h_len = h_len_of(slot);
+        const uint32_t *h_ovf = h_ovf_of(slot);
+        PIXO_CUDA(ctx, cudaEventSynchronize(ev_len[slot]));
         std::vector<size_t> hdr(cnt);
+        bool redo = false;
         for (uint32_t k = 0; k < cnt; ++k) {
             const uint32_t img = first + k;
             uint8_t *o = out + (size_t)img * out_cap_each;
-            const HuffTables &t = tables[optimize ? k : 0];
-            if (out_cap_each < 1024 + 2)
-                return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small", out_cap_each);
-            hdr[k] = write_headers(o, g, lum_zz, chr_zz, t, restart_interval);
-            if (!fallback_all && !h_ovf[k]) {
-                const size_t body = (size_t)h_len[k];
-                if (hdr[k] + body + 2 > out_cap_each)
-                    return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small (need %zu)",
-                                     out_cap_each, hdr[k] + body + 2);
-                PIXO_CUDA(ctx, cudaMemcpyAsync(o + hdr[k], scan + (size_t)k * scan_cap, body,
-                                               cudaMemcpyDeviceToHost, ctx->stream));
-                o[hdr[k] + body] = 0xFF;
-                o[hdr[k] + body + 1] = 0xD9;
-                out_lens[img] = hdr[k] + body + 2;
-            }
+            hdr[k] = write_headers(o, g, lum_zz, chr_zz, tb[optimize ? k : 0], restart_interval);
+            if (h_ovf[k]) { redo = true; continue; }
+            const size_t body = (size_t)h_len[k];
+            if (hdr[k] + body + 2 > out_cap_each)
+                return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small (need %zu)",
+                                 out_cap_each, hdr[k] + body + 2);
+            PIXO_CUDA(ctx, cudaMemcpyAsync(o + hdr[k], scan + (size_t)k * scan_cap, body, cudaMemcpyDeviceToHost,
+                                           ctx->d2h_stream));
+            o[hdr[k] + body] = 0xFF;
+            o[hdr[k] + body + 1] = 0xD9;
+            out_lens[img] = hdr[k] + body + 2;
         }
-        PIXO_CUDA(ctx, cudaEventRecord(ev_out[slot], ctx->stream));
-        // host entropy coder for the frames the GPU stage did not finish
-        bool any_host = fallback_all;
-        for (uint32_t k = 0; k < cnt && !any_host; ++k) any_host = h_ovf[k] != 0;
-        if (any_host) {
+        PIXO_CUDA(ctx, cudaEventRecord(ev_out[slot], ctx->d2h_stream));
+        if (!redo) return 0;
+        // Frames the first pass did not finish.  Their coefficients are still in this slot of
+        // d_coef (the next group's transform writes the other one).
+        for (uint32_t k = 0; k < cnt; ++k) {
+            if (!h_ovf[k]) continue;
+            const uint32_t img = first + k;
+            uint8_t *o = out + (size_t)img * out_cap_each;
+            const HuffTables &t = tb[optimize ? k : 0];
+            bool done = false;
+            if (h_ovf[k] == 1 && ctx->gpu_retry) {  // capacity only: the kernel reported the size it needs
+                const size_t need = (size_t)h_len[k];
+                if (hdr[k] + need + 2 > out_cap_each)
+                    return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small (need %zu)",
+                                     out_cap_each, hdr[k] + need + 2);
+                const uint64_t cap2 = align_up(need + 64, 256);
+                PIXO_TRY(ensure_dev(ctx, ctx->d_retry, cap2 + ent_one + 256));
+                auto *rbuf = reinterpret_cast<uint8_t *>(ctx->d_retry.ptr);
+                uint64_t *d_len = nullptr;
+                uint32_t *d_ovf = nullptr;
+                PIXO_TRY(launch_jpeg_entropy(ctx, c.y + (size_t)k * cstride, cstride, c.cb + (size_t)k * cstride,
+                                             c.cr + (size_t)k * cstride, cstride, 1, g, t, restart_interval,
+                                             rbuf + cap2, rbuf, cap2, &d_len, &d_ovf));
+                uint64_t len2 = 0;
+                uint32_t ovf2 = 0;
+                PIXO_CUDA(ctx, cudaMemcpyAsync(&len2, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                PIXO_CUDA(ctx, cudaMemcpyAsync(&ovf2, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                if (!ovf2 && len2 == need) {
+                    PIXO_CUDA(ctx, cudaMemcpyAsync(o + hdr[k], rbuf, need, cudaMemcpyDeviceToHost, ctx->stream));
+                    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                    o[hdr[k] + need] = 0xFF;
+                    o[hdr[k] + need + 1] = 0xD9;
+                    out_lens[img] = hdr[k] + need + 2;
+                    done = true;
+                }
+            }
+            if (done) continue;
+            // last resort: the host entropy coder on the GPU's coefficient arrays
+            ctx->host_fallbacks += 1;
             PIXO_TRY(ensure_pinned(ctx, ctx->h_out, coef_each));
             auto *hc = reinterpret_cast<uint8_t *>(ctx->h_out.ptr);
-            for (uint32_t k = 0; k < cnt; ++k) {
-                if (!fallback_all && !h_ovf[k]) continue;
-                const uint32_t img = first + k;
-                uint8_t *o = out + (size_t)img * out_cap_each;
-                PIXO_CUDA(ctx, cudaMemcpyAsync(hc, d_coef + (size_t)k * coef_each, coef_each,
-                                               cudaMemcpyDeviceToHost, ctx->stream));
-                PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                const size_t body = entropy_encode_scan(reinterpret_cast<int16_t *>(hc),
-                                                        reinterpret_cast<int16_t *>(hc + yb),
-                                                        reinterpret_cast<int16_t *>(hc + yb + cbb), g,
-                                                        tables[optimize ? k : 0], restart_interval, false,
-                                                        o + hdr[k], out_cap_each - hdr[k] - 2, ctx->host_threads);
-                if (body == (size_t)-1)
-                    return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small", out_cap_each);
-                o[hdr[k] + body] = 0xFF;
-                o[hdr[k] + body + 1] = 0xD9;
-                out_lens[img] = hdr[k] + body + 2;
-            }
+            PIXO_CUDA(ctx, cudaMemcpyAsync(hc, reinterpret_cast<const uint8_t *>(c.y) + (size_t)k * coef_each, coef_each,
+                                           cudaMemcpyDeviceToHost, ctx->stream));
+            PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            const size_t body = entropy_encode_scan(reinterpret_cast<int16_t *>(hc), reinterpret_cast<int16_t *>(hc + yb),
+                                                    reinterpret_cast<int16_t *>(hc + yb + cbb), g, t, restart_interval,
+                                                    false, o + hdr[k], out_cap_each - hdr[k] - 2, ctx->host_threads);
+            if (body == (size_t)-1)
+                return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small", out_cap_each);
+            o[hdr[k] + body] = 0xFF;
+            o[hdr[k] + body + 1] = 0xD9;
+            out_lens[img] = hdr[k] + body + 2;
         }
+        return 0;
+    };
+
+    // the copy streams start after whatever the caller already queued on the main stream
+    PIXO_CUDA(ctx, cudaEventRecord(ev_out[0], ctx->stream));
+    PIXO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev_out[0], 0));
+    PIXO_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ev_out[0], 0));
+    PIXO_TRY(upload(0));
+    for (uint32_t gi = 0; gi < ngroups; ++gi) {
+        if (gi + 1 < ngroups) PIXO_TRY(upload(gi + 1));
+        PIXO_TRY(compute(gi));
+        if (gi > 0) PIXO_TRY(finish(gi - 1));
     }
+    PIXO_TRY(finish(ngroups - 1));
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
     PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    drain.armed = false;
     return 0;
 }
 
@@ -682,10 +777,19 @@ int pixo_b200_jpeg_entropy_encode(pixo_b200_ctx *ctx, const int16_t *y, const in
 {
     if (quality == 0 || quality > 100)
         return set_error(ctx, PIXO_B200_ERR_INVALID_QUALITY, "Invalid quality %u: must be 1-100", quality);
+    if (restart_interval > 65535)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_RESTART, "Invalid restart interval %u", restart_interval);
     PIXO_TRY(validate_jpeg(ctx, width, height, color_type, subsampling));
     if (!y || !out || !out_len || (color_type != PIXO_B200_GRAY && (!cb || !cr)))
         return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
     const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
+    // baseline Huffman tables code DC differences of category <= 11 and AC values of category <= 10
+    // (what an 8-bit forward DCT can produce); anything else has no code
+    if (!coefficients_in_range(y, g.ny, restart_interval, g.y_per_mcu) ||
+        (g.has_chroma && (!coefficients_in_range(cb, g.nc, restart_interval, 1) ||
+                          !coefficients_in_range(cr, g.nc, restart_interval, 1))))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT,
+                         "coefficient out of the baseline range (|AC| <= 1023, |DC difference| <= 2047)");
     uint64_t hist[536];
     if (optimize_huffman) host_histogram(y, cb, cr, g, restart_interval, hist);
     int threads = ctx ? ctx->host_threads : (int)std::thread::hardware_concurrency();
@@ -729,22 +833,33 @@ int pixo_b200_jpeg_entropy_encode_dev(pixo_b200_ctx *ctx, const int16_t *d_y, co
         if (!huff_from_histogram(h_hist, g.has_chroma, t)) huff_standard(t);  // unwrap_or_default
     }
     const size_t hdr = write_headers(out, g, lum_zz, chr_zz, t, restart_interval);
-    const size_t scan_cap = (out_cap - hdr - 2) & ~(size_t)15;
-    PIXO_TRY(ensure_dev(ctx, ctx->d_out, scan_cap + 16));
+    // The device scan buffer follows the size a JPEG of this geometry normally has, not the caller's
+    // worst-case capacity (tens of GB for a gigapixel frame); a scan that needs more is coded again
+    // with the exact size the kernel reported.
+    const size_t raw = (size_t)width * height * (color_type == PIXO_B200_GRAY ? 1 : 3);
+    size_t scan_cap = std::min<size_t>((out_cap - hdr - 2) & ~(size_t)15, (size_t)default_scan_cap(ctx, raw));
     PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(1, g, restart_interval)));
-    uint64_t *d_len = nullptr;
-    uint32_t *d_ovf = nullptr;
-    auto *d_scan = reinterpret_cast<uint8_t *>(ctx->d_out.ptr);
-    PIXO_TRY(launch_jpeg_entropy(ctx, d_y, 0, d_cb, d_cr, 0, 1, g, t, restart_interval,
-                                 reinterpret_cast<uint8_t *>(ctx->d_ent.ptr), d_scan, scan_cap, &d_len, &d_ovf));
     auto *h_len = reinterpret_cast<uint64_t *>(h_meta);
     auto *h_ovf = reinterpret_cast<uint32_t *>(h_meta + 8);
-    PIXO_CUDA(ctx, cudaMemcpyAsync(h_len, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (*h_ovf)
-        return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small (need %zu)", out_cap,
-                         hdr + (size_t)*h_len + 2);
+    uint8_t *d_scan = nullptr;
+    for (int attempt = 0;; ++attempt) {
+        PIXO_TRY(ensure_dev(ctx, ctx->d_out, scan_cap + 16));
+        uint64_t *d_len = nullptr;
+        uint32_t *d_ovf = nullptr;
+        d_scan = reinterpret_cast<uint8_t *>(ctx->d_out.ptr);
+        PIXO_TRY(launch_jpeg_entropy(ctx, d_y, 0, d_cb, d_cr, 0, 1, g, t, restart_interval,
+                                     reinterpret_cast<uint8_t *>(ctx->d_ent.ptr), d_scan, scan_cap, &d_len, &d_ovf));
+        PIXO_CUDA(ctx, cudaMemcpyAsync(h_len, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!*h_ovf) break;
+        if (*h_ovf != 1 || attempt)
+            return set_error(ctx, PIXO_B200_ERR_CUDA, "device entropy stage did not finish (flags %u)", *h_ovf);
+        if (hdr + (size_t)*h_len + 2 > out_cap)
+            return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small (need %zu)", out_cap,
+                             hdr + (size_t)*h_len + 2);
+        scan_cap = align_up((size_t)*h_len + 64, 256);
+    }
     const size_t body = (size_t)*h_len;
     PIXO_CUDA(ctx, cudaMemcpyAsync(out + hdr, d_scan, body, cudaMemcpyDeviceToHost, ctx->stream));
     PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

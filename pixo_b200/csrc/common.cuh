@@ -34,13 +34,17 @@ struct pixo_b200_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of the next group of frames
+    cudaStream_t d2h_stream = nullptr;   // D2H of finished scan bytes
     int sm_count = 0;
     int host_threads = 0;
     uint64_t launches = 0;
+    uint64_t host_fallbacks = 0;   // frames finished by the host entropy coder (see encode_frames)
+    size_t scan_cap_override = 0;  // device scan bytes per frame; 0 = the built-in heuristic
+    bool gpu_retry = true;         // re-run k_huff with the exact size when the heuristic was too small
     std::string err;
     // reusable scratch (device + pinned host)
-    pixo::Scratch d_in, d_y, d_cb, d_cr, d_misc, d_out, d_ent, d_coef;
+    pixo::Scratch d_in, d_y, d_cb, d_cr, d_misc, d_out, d_ent, d_coef, d_retry;
     pixo::Scratch h_in, h_out, h_misc;
     std::vector<cudaEvent_t> events;
     std::vector<cudaEvent_t> stage_events;  // one per pinned staging slot of h2d_copy

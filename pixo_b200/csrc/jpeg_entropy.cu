@@ -24,7 +24,9 @@
 //      the window is copied out with the 0x00s inserted, 16 bytes per store.
 // Tickets are dispensed chunk-major across the images of a batch, so their chains advance side
 // by side.  Nothing but the final scan bytes is written to global memory.  Restart intervals
-// stay on the host coder (jpeg_host.cpp): they need per-interval padding.
+// (handle_restart, src/jpeg/mod.rs:1423-1445) run here too: every interval is a bit stream of its
+// own (chunks never straddle one, chain 1 restarts with it, its last chunk pads and appends the
+// RSTn marker), while chain 2 - every byte written so far - runs across the whole image.
 #include "common.cuh"
 #include "jpeg_host.hpp"
 
@@ -67,7 +69,7 @@ struct EntParams {
     uint8_t *out;                  // [n][out_cap]
     uint64_t out_cap;
     uint64_t *out_len;             // [n] final byte count
-    uint32_t *overflow;            // [n] set when out_cap was exceeded (or the chain faulted)
+    uint32_t *overflow;            // [n] bit 0: out_cap was exceeded (out_len = the size needed); bit 1: a chain timed out
 };
 
 constexpr int CB = 32;             // blocks per chunk == one warp
@@ -524,7 +526,7 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             const bool in_tail = lane >= 16 && full_hi >= full_lo && hb < end;
             if (in_head || in_tail) gdst[hb] = sb[hb];
         } else if (lane == 0) {
-            P.overflow[C.img] = 1;
+            atomicOr(&P.overflow[C.img], 1u);
         }
         __syncwarp();  // sbuf is rewritten by the next window, or by the next chunk's stage
     };
@@ -619,7 +621,7 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         if (emit && lane == 0 && C.final_) {
             const unsigned long long total = gbase + (ob1 - ob0) + Fsum;
             P.out_len[C.img] = total;
-            if (total > P.out_cap) P.overflow[C.img] = 1;
+            if (total > P.out_cap) atomicOr(&P.overflow[C.img], 1u);
         }
         if (!emit) C.own = (ob1 - ob0) + Fsum + (C.marker ? 2u : 0u);
         return Fsum;
@@ -661,12 +663,12 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             if (lane == 0 && C.final_) {
                 const unsigned long long total = gbase + (ob1 - ob0) + C.Ftot;
                 P.out_len[C.img] = total;
-                if (total > P.out_cap) P.overflow[C.img] = 1;
+                if (total > P.out_cap) atomicOr(&P.overflow[C.img], 1u);
             }
         } else {
             sweep(C, true, gbase);
         }
-        if (lane == 0 && C.fault) P.overflow[C.img] = 1;
+        if (lane == 0 && C.fault) atomicOr(&P.overflow[C.img], 2u);
     };
 
     ChunkState cur, pend;

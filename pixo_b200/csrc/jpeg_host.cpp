@@ -374,6 +374,21 @@ struct StuffWriter {
 
 }  // namespace
 
+bool coefficients_in_range(const int16_t *blocks, size_t nblocks, uint32_t restart_interval, uint32_t per_mcu)
+{
+    int prev = 0;
+    for (size_t b = 0; b < nblocks; ++b) {
+        const int16_t *blk = blocks + b * 64;
+        if (restart_interval && b % per_mcu == 0 && (b / per_mcu) % restart_interval == 0) prev = 0;
+        const int diff = (int16_t)(blk[0] - prev);
+        if (diff > 2047 || diff < -2047) return false;
+        prev = blk[0];
+        for (int i = 1; i < 64; ++i)
+            if (blk[i] > 1023 || blk[i] < -1023) return false;
+    }
+    return true;
+}
+
 FrameGeometry make_geometry(uint32_t w, uint32_t h, uint32_t color_type, uint32_t subsampling)
 {
     FrameGeometry g;

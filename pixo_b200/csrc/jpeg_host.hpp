@@ -53,6 +53,10 @@ size_t entropy_encode_scan(const int16_t *y, const int16_t *cb, const int16_t *c
 void host_histogram(const int16_t *y, const int16_t *cb, const int16_t *cr,
                     const FrameGeometry &g, uint32_t restart_interval, uint64_t hist[536]);
 
+// true when every AC coefficient has category <= 10 and every DC difference (previous block of
+// the same component, reset at restart boundaries) category <= 11
+bool coefficients_in_range(const int16_t *blocks, size_t nblocks, uint32_t restart_interval, uint32_t per_mcu);
+
 // run fn(job) for job in [0, n) on up to `threads` std::threads
 void parallel_jobs(int n, int threads, void (*fn)(int, void *), void *arg);
 

@@ -61,6 +61,13 @@ def output_capacity(width: int, height: int) -> int:
     return nb * 600 + 4096
 
 
+def _restart(options) -> int:
+    """Some(0) is InvalidRestartInterval in the reference (src/jpeg/mod.rs:339-345); None -> 0."""
+    if options.restart_interval is not None and int(options.restart_interval) == 0:
+        raise _lib.PixoError(_lib.ERR_INVALID_RESTART, "Invalid restart interval 0")
+    return int(options.restart_interval or 0)
+
+
 def _as_u8(data) -> np.ndarray:
     if isinstance(data, np.ndarray):
         return np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
@@ -117,12 +124,11 @@ def encode_into(output: bytearray, data, options: JpegOptions, ctx: Context | No
     cap = output_capacity(options.width, options.height)
     buf = np.empty(cap, np.uint8)
     n = C.c_size_t()
-    if options.restart_interval is not None and options.restart_interval == 0:
-        raise _lib.PixoError(_lib.ERR_INVALID_RESTART, "Invalid restart interval 0")
+    restart = _restart(options)
     rc = _lib.load().pixo_b200_jpeg_encode(
         ctx.handle, d.ctypes.data, d.size, int(options.width), int(options.height),
         int(options.color_type), int(options.quality), int(options.subsampling),
-        int(options.restart_interval or 0), int(bool(options.optimize_huffman)),
+        restart, int(bool(options.optimize_huffman)),
         int(bool(options.progressive)), int(bool(options.trellis_quant)), buf.ctypes.data, cap,
         C.byref(n))
     _lib.check(ctx.handle, rc)
@@ -141,6 +147,7 @@ def encode_batch(frames: np.ndarray, options: JpegOptions, ctx: Context | None =
                  capacity_each: int | None = None) -> list[bytes]:
     """n frames of identical geometry ([n, h*w*bpp] uint8) -> n JPEG byte strings.
     capacity_each defaults to min(worst case, 2x the raw frame size)."""
+    restart = _restart(options)
     ctx = ctx or default_context()
     f = np.ascontiguousarray(frames, np.uint8)
     n = f.shape[0]
@@ -151,7 +158,7 @@ def encode_batch(frames: np.ndarray, options: JpegOptions, ctx: Context | None =
     rc = _lib.load().pixo_b200_jpeg_encode_batch(
         ctx.handle, f.ctypes.data, each, n, int(options.width), int(options.height),
         int(options.color_type), int(options.quality), int(options.subsampling),
-        int(options.restart_interval or 0), int(bool(options.optimize_huffman)), out.ctypes.data,
+        restart, int(bool(options.optimize_huffman)), out.ctypes.data,
         cap, lens)
     _lib.check(ctx.handle, rc)
     return [out[i, : lens[i]].tobytes() for i in range(n)]
@@ -168,7 +175,7 @@ def entropy_encode(y, cb, cr, options: JpegOptions, ctx: Context | None = None) 
     rc = _lib.load().pixo_b200_jpeg_entropy_encode(
         ctx.handle if ctx else None, y.ctypes.data, cb.ctypes.data, cr.ctypes.data,
         int(options.width), int(options.height), int(options.color_type), int(options.quality),
-        int(options.subsampling), int(options.restart_interval or 0),
+        int(options.subsampling), _restart(options),
         int(bool(options.optimize_huffman)), buf.ctypes.data, cap, C.byref(n))
     _lib.check(ctx.handle if ctx else None, rc)
     return buf[: n.value].tobytes()
@@ -186,7 +193,7 @@ def entropy_encode_dev(d_y, d_cb, d_cr, options: JpegOptions, ctx: Context | Non
     rc = _lib.load().pixo_b200_jpeg_entropy_encode_dev(
         ctx.handle, ptr(d_y), ptr(d_cb), ptr(d_cr), int(options.width), int(options.height),
         int(options.color_type), int(options.quality), int(options.subsampling),
-        int(options.restart_interval or 0), int(bool(options.optimize_huffman)), buf.ctypes.data, cap,
+        _restart(options), int(bool(options.optimize_huffman)), buf.ctypes.data, cap,
         C.byref(n))
     _lib.check(ctx.handle, rc)
     return buf[: n.value].tobytes()

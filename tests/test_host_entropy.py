@@ -69,3 +69,27 @@ def test_entropy_validation_errors():
     with pytest.raises(pixo_b200.PixoError) as e:
         entropy_encode(y, y, y, JpegOptions(1, 1, ColorType.Rgba, 80))
     assert e.value.code == pixo_b200._lib.ERR_UNSUPPORTED_COLOR
+
+
+def test_entropy_rejects_uncodable_coefficients_and_bad_restart():
+    """the standard tables have no code for AC category > 10 / DC-difference category
+    > 11, and the DRI field is 16 bits - reject instead of reading past the tables."""
+    E = pixo_b200._lib
+    o = JpegOptions(8, 8, ColorType.Gray, 80, Subsampling.S444)
+    z = np.zeros((0, 64), np.int16)
+    for pos, val in ((5, 1024), (5, -1024), (0, 2048), (0, -2048)):
+        y = np.zeros((1, 64), np.int16); y[0, pos] = val
+        with pytest.raises(pixo_b200.PixoError) as e:
+            entropy_encode(y, z, z, o)
+        assert e.value.code == E.ERR_INVALID_ARGUMENT
+    y = np.zeros((1, 64), np.int16); y[0, 0] = 2047; y[0, 5] = -1023
+    assert entropy_encode(y, z, z, o)[:2] == b"\xff\xd8"
+    with pytest.raises(pixo_b200.PixoError) as e:
+        entropy_encode(y, z, z, JpegOptions(8, 8, ColorType.Gray, 80, Subsampling.S444, 70000))
+    assert e.value.code == E.ERR_INVALID_RESTART
+    from pixo_b200 import jpeg
+    for fn in (lambda: entropy_encode(y, z, z, JpegOptions(8, 8, ColorType.Gray, 80, Subsampling.S444, 0)),
+               lambda: jpeg.encode_batch(np.zeros((1, 64), np.uint8), JpegOptions(8, 8, ColorType.Gray, 80, restart_interval=0))):
+        with pytest.raises(pixo_b200.PixoError) as e:
+            fn()
+        assert e.value.code == E.ERR_INVALID_RESTART

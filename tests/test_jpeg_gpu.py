@@ -13,6 +13,15 @@ from util import EDGE_CASE_DIMENSIONS, images
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _no_silent_host_fallback(gpu_ctx):
+    """Every test in this file must be served by the GPU entropy stage: the host coder may only
+    run where a test forces it (and resets the expectation itself)."""
+    before = gpu_ctx.host_fallbacks
+    yield
+    assert gpu_ctx.host_fallbacks == before, "a frame was silently finished by the host entropy coder"
+
+
 def _check_coeffs(po, ctx, img, w, h, ct, ss, q):
     y, cb, cr = jpeg.compute_all_coefficients(img, w, h, ColorType(ct), Subsampling(ss), q, ctx=ctx)
     ry, rcb, rcr = po.jpeg_coefficients(img, w, h, ct, ss, q)
@@ -183,6 +192,66 @@ def test_entropy_stage_dense_blocks(po, gpu_ctx, w, h, ct, ss):
         for opt in (False, True):
             o = JpegOptions(w, h, ColorType(ct), q, Subsampling(ss), None, opt)
             assert jpeg.encode(img, o, ctx=gpu_ctx) == po.jpeg_encode(img, w, h, ct, q, ss, 0, opt), (q, opt)
+
+
+def test_dense_frames_are_recoded_on_the_gpu_not_the_host(po):
+    """q=100 noise outgrows the heuristic device scan buffer (half the raw frame): the frame is
+    coded a second time by k_huff with the exact size; the host coder stays idle.  With the retry
+    switched off and a tiny buffer the host coder must take over - and be counted."""
+    w, h = 640, 480
+    img = po.gen_noise(w, h, 3, 7)
+    ref = po.jpeg_encode(img, w, h, 2, 100, 1)
+    assert len(ref) > (w * h * 3 // 2 + 65536) * 9 // 8   # really beyond the heuristic
+    with pixo_b200.Context(0) as ctx:
+        o = JpegOptions(w, h, ColorType.Rgb, 100, Subsampling.S420)
+        l0 = ctx.launch_count
+        assert jpeg.encode(img, o, ctx=ctx) == ref
+        assert ctx.host_fallbacks == 0
+        assert ctx.launch_count - l0 == 3          # K1, k_huff (overflow), k_huff (exact size)
+        batch = np.stack([img, po.gen_gradient_rgb(w, h), img])
+        got = jpeg.encode_batch(batch, o, ctx=ctx, capacity_each=jpeg.output_capacity(w, h))
+        assert got[0] == ref and got[2] == ref and got[1] == po.jpeg_encode(batch[1], w, h, 2, 100, 1)
+        assert ctx.host_fallbacks == 0
+        ctx.set_scan_capacity(4096, gpu_retry=False)
+        assert jpeg.encode(img, o, ctx=ctx) == ref
+        assert ctx.host_fallbacks == 1
+        ctx.set_scan_capacity(4096, gpu_retry=True)      # tiny first buffer, GPU retry on
+        assert jpeg.encode(img, JpegOptions(w, h, ColorType.Rgb, 80, Subsampling.S420), ctx=ctx) == \
+            po.jpeg_encode(img, w, h, 2, 80, 1)
+        assert ctx.host_fallbacks == 1
+        ctx.set_scan_capacity(0)
+
+
+def test_batch_optimize_many_small_frames_fresh_context(po):
+    """per-image optimised tables run one k_huff pass per image, each with its own
+    scratch region - 20 small frames on a context that has never grown its scratch."""
+    w, h, n = 256, 256, 20
+    frames = np.stack([po.gen_noise(w, h, 3, 100 + k) if k % 3 else po.gen_gradient_rgb(w, h) for k in range(n)])
+    with pixo_b200.Context(0) as ctx:
+        for ri in (None, 3):
+            o = JpegOptions(w, h, ColorType.Rgb, 85, Subsampling.S420, ri, True)
+            got = jpeg.encode_batch(frames, o, ctx=ctx)
+            for k in range(n):
+                assert got[k] == po.jpeg_encode(frames[k], w, h, 2, 85, 1, ri or 0, True), (ri, k)
+        assert ctx.host_fallbacks == 0
+
+
+def test_restart_streams_decode_like_the_plain_stream(po, gpu_ctx):
+    """Independent pin for restart intervals (the reference's wasm API cannot produce them): a
+    conforming decoder (libjpeg via PIL) must reconstruct exactly the same pixels from the
+    restart and the non-restart encodes of the same frame, and see the DRI/RSTn structure."""
+    import io
+    from PIL import Image
+    w, h = 333, 222
+    for img in (po.gen_noise(w, h, 3, 9), po.gen_gradient_rgb(w, h)):
+        for ss in (Subsampling.S420, Subsampling.S444):
+            plain = jpeg.encode(img, JpegOptions(w, h, ColorType.Rgb, 85, ss), ctx=gpu_ctx)
+            want = np.asarray(Image.open(io.BytesIO(plain)).convert("RGB"))
+            for ri in (1, 4, 37):
+                rst = jpeg.encode(img, JpegOptions(w, h, ColorType.Rgb, 85, ss, ri), ctx=gpu_ctx)
+                assert b"\xff\xdd\x00\x04" + ri.to_bytes(2, "big") in rst[:700]     # DRI
+                got = np.asarray(Image.open(io.BytesIO(rst)).convert("RGB"))
+                assert np.array_equal(got, want), (ss, ri)
 
 
 def test_encode_dev_device_resident(po, gpu_ctx):
