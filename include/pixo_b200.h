@@ -195,6 +195,58 @@ int pixo_b200_jpeg_entropy_encode_dev(pixo_b200_ctx *ctx, const int16_t *d_y, co
                                       uint32_t restart_interval, uint32_t optimize_huffman,
                                       uint8_t *out, size_t out_cap, size_t *out_len);
 
+/* ---- one frame tiled over several GPUs (BASELINE config C4) --------------
+ * The reference's analogue is compute_all_coefficients_parallel (src/jpeg/mod.rs:1137-1215, rayon
+ * over MCU rows) followed by the sequential encode_scan.  Here every GPU owns a contiguous band of
+ * MCU rows and runs the WHOLE path on it; only finished scan bytes are gathered:
+ *   1. transform: pixo_b200_jpeg_coefficients_dev on the band's pixel rows (a band starts on an
+ *      MCU row, so it is an image of its own: no halo; the frame's bottom clamp falls in the last band);
+ *   2. the DC predictors cross bands: band r starts from band r-1's last DC per component
+ *      (pixo_b200_jpeg_band_last_dc; one tiny all-gather);
+ *   3. [optimize_huffman] pixo_b200_jpeg_band_histogram_dev, statistics summed over the bands
+ *      (all-reduce of 536 u64), identical tables on every rank;
+ *   4. pixo_b200_jpeg_band_entropy_dev: the band's Huffman code as a raw bit string (no 0xFF
+ *      stuffing, no padding: both depend on the bit offset, which is not known yet) plus its bit
+ *      count and last 7 bits (second tiny all-gather -> every band's bit offset in the frame's stream
+ *      and the bits it inherits in its first byte);
+ *   5. pixo_b200_jpeg_band_splice_dev: shift to the bit offset, complete the shared first byte, stuff
+ *      0xFF -> 0xFF00 (src/bits.rs:245-259), 1-pad the frame's last byte (:261-272).  A band owns the
+ *      stream bytes whose LAST bit it wrote;
+ *   6. rank 0 writes pixo_b200_jpeg_write_headers, the bands' bytes in band order, EOI.
+ * No restart interval on this path (every interval would need its own offset exchange).
+ * The `_dev` calls return after their host outputs are valid.  Host twins (no device needed) take
+ * host arrays: they serve the CPU-only tests and a host that merely assembles. */
+int pixo_b200_jpeg_band_last_dc(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb,
+                                const int16_t *d_cr, size_t ny, size_t nc, int32_t last_dc[3]);
+int pixo_b200_jpeg_band_histogram_dev(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb,
+                                      const int16_t *d_cr, uint32_t width, uint32_t band_height,
+                                      uint32_t color_type, uint32_t subsampling,
+                                      const int32_t dc_seed[3], uint64_t *d_hist /* 536, device */);
+/* hist (host, optional): the frame's summed statistics -> optimised tables (standard when NULL or
+ * when they cannot be built, as the reference's unwrap_or_default does). */
+int pixo_b200_jpeg_band_entropy_dev(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb,
+                                    const int16_t *d_cr, uint32_t width, uint32_t band_height,
+                                    uint32_t color_type, uint32_t subsampling,
+                                    const int32_t dc_seed[3], const uint64_t *hist, uint8_t *d_raw,
+                                    size_t raw_cap, uint64_t *nbits, uint32_t *tail7);
+/* start_bit: bits of the frame's stream before this band; tail_in: the last (start_bit % 8) of them. */
+int pixo_b200_jpeg_band_splice_dev(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t nbits,
+                                   uint64_t start_bit, uint32_t tail_in, uint32_t is_last_band,
+                                   uint8_t *d_out, size_t out_cap, uint64_t *out_len);
+int pixo_b200_jpeg_band_entropy(const int16_t *y, const int16_t *cb, const int16_t *cr, uint32_t width,
+                                uint32_t band_height, uint32_t color_type, uint32_t subsampling,
+                                const int32_t dc_seed[3], const uint64_t *hist, uint8_t *raw,
+                                size_t raw_cap, uint64_t *nbits, uint32_t *tail7);
+int pixo_b200_jpeg_band_histogram(const int16_t *y, const int16_t *cb, const int16_t *cr, uint32_t width,
+                                  uint32_t band_height, uint32_t color_type, uint32_t subsampling,
+                                  const int32_t dc_seed[3], uint64_t hist[536]);
+int pixo_b200_jpeg_band_splice(const uint8_t *raw, uint64_t nbits, uint64_t start_bit, uint32_t tail_in,
+                               uint32_t is_last_band, uint8_t *out, size_t out_cap, size_t *out_len);
+/* SOI .. SOS of the frame (src/jpeg/mod.rs:395-430,449-648); out_cap >= 1024.  Host-only. */
+int pixo_b200_jpeg_write_headers(uint32_t width, uint32_t height, uint32_t color_type, uint32_t quality,
+                                 uint32_t subsampling, uint32_t restart_interval, const uint64_t *hist,
+                                 uint8_t *out, size_t out_cap, size_t *out_len);
+
 /* ---- PNG -------------------------------------------------------------------------------- */
 
 /* Replaces filter::apply_filters_with_row_bytes — src/png/filter.rs:64-206 (+ the rayon path
@@ -220,6 +272,21 @@ int pixo_b200_png_filter_dev(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t i
                              uint32_t n_images, uint32_t width, uint32_t height,
                              size_t row_bytes, uint32_t bytes_per_pixel, uint32_t strategy,
                              uint8_t *d_out, size_t out_stride, uint32_t *d_adler);
+
+/* One image's rows in bands (filters read the RAW previous row, so a band
+ * only needs the one raw row above it - an overlapping read, not an exchange).  d_rows: band_rows
+ * rows of the image starting at some row r0; d_row_above: the raw row r0-1 (NULL for r0 == 0 =
+ * zeros, src/png/filter.rs:112-117); image_height: rows of the WHOLE image (the strategy pre-rules
+ * of apply_filters_with_row_bytes look at the whole image).  d_out: band_rows*(row_bytes+1);
+ * d_adler (optional): Adler-32 of this band's slice of the filtered stream, started from the
+ * initial state; combine the bands' values in order (s1 = s1A + s1B - 1, s2 = s2A + s2B +
+ * lenB*(s1A - 1) mod 65521 - pixo_b200_adler32_combine). */
+int pixo_b200_png_filter_rows_dev(pixo_b200_ctx *ctx, const uint8_t *d_rows, const uint8_t *d_row_above,
+                                  uint32_t width, uint32_t image_height, uint32_t band_rows,
+                                  size_t row_bytes, uint32_t bytes_per_pixel, uint32_t strategy,
+                                  uint8_t *d_out, uint32_t *d_adler);
+/* Adler-32 of A ++ B from adler32(A), adler32(B) and len(B).  Host-only. */
+uint32_t pixo_b200_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_t len_b);
 
 /* Replaces compress::adler32::adler32 — src/compress/adler32.rs:11-47 (dispatch
  * src/simd/mod.rs:72-90).  Host buffer in, checksum out. */

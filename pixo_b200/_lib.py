@@ -66,6 +66,23 @@ SYMBOLS = {
     "pixo_b200_jpeg_entropy_encode_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32,
                                                     C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp,
                                                     C.c_size_t, szp]),
+    "pixo_b200_jpeg_band_last_dc": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_size_t, C.POINTER(C.c_int32)]),
+    "pixo_b200_jpeg_band_histogram_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                    C.POINTER(C.c_int32), vp]),
+    "pixo_b200_jpeg_band_entropy_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                  C.POINTER(C.c_int32), u64p, vp, C.c_size_t, u64p, u32p]),
+    "pixo_b200_jpeg_band_splice_dev": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, vp,
+                                                 C.c_size_t, u64p]),
+    "pixo_b200_jpeg_band_entropy": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                              C.POINTER(C.c_int32), u64p, vp, C.c_size_t, u64p, u32p]),
+    "pixo_b200_jpeg_band_histogram": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                C.POINTER(C.c_int32), u64p]),
+    "pixo_b200_jpeg_band_splice": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, vp, C.c_size_t, szp]),
+    "pixo_b200_jpeg_write_headers": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                               u64p, vp, C.c_size_t, szp]),
+    "pixo_b200_png_filter_rows_dev": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t,
+                                                C.c_uint32, C.c_uint32, vp, vp]),
+    "pixo_b200_adler32_combine": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint64]),
     "pixo_b200_png_filter": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_size_t, C.c_uint32,
                                        C.c_uint32, vp, u32p]),
     "pixo_b200_png_filter_dev": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32,

@@ -869,6 +869,160 @@ int pixo_b200_jpeg_entropy_encode_dev(pixo_b200_ctx *ctx, const int16_t *d_y, co
     return 0;
 }
 
+// ---- one frame tiled over several GPUs -----------------------------------------------------------
+
+static void tables_from(const uint64_t *hist, bool has_chroma, HuffTables &t)
+{
+    // build_optimized_huffman_tables(..).unwrap_or_default(), src/jpeg/mod.rs:379-392
+    if (!(hist && huff_from_histogram(hist, has_chroma, t))) huff_standard(t);
+}
+
+int pixo_b200_jpeg_band_last_dc(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb,
+                                const int16_t *d_cr, size_t ny, size_t nc, int32_t last_dc[3])
+{
+    if (!ctx || !last_dc) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null argument");
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    int16_t v[3] = {0, 0, 0};
+    if (ny && d_y) PIXO_CUDA(ctx, cudaMemcpyAsync(&v[0], d_y + (ny - 1) * 64, 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nc && d_cb) PIXO_CUDA(ctx, cudaMemcpyAsync(&v[1], d_cb + (nc - 1) * 64, 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nc && d_cr) PIXO_CUDA(ctx, cudaMemcpyAsync(&v[2], d_cr + (nc - 1) * 64, 2, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 3; ++k) last_dc[k] = v[k];
+    return 0;
+}
+
+int pixo_b200_jpeg_band_histogram_dev(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb,
+                                      const int16_t *d_cr, uint32_t width, uint32_t band_height,
+                                      uint32_t color_type, uint32_t subsampling,
+                                      const int32_t dc_seed[3], uint64_t *d_hist)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    PIXO_TRY(validate_jpeg(ctx, width, band_height, color_type, subsampling));
+    if (!d_y || !d_hist || (color_type != PIXO_B200_GRAY && (!d_cb || !d_cr)))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    const FrameGeometry g = make_geometry(width, band_height, color_type, subsampling);
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_jpeg_histogram(ctx, d_y, 0, d_cb, d_cr, 0, 1, g.ny, g.nc, g.y_per_mcu, 0, false, d_hist, dc_seed);
+}
+
+int pixo_b200_jpeg_band_entropy_dev(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb,
+                                    const int16_t *d_cr, uint32_t width, uint32_t band_height,
+                                    uint32_t color_type, uint32_t subsampling,
+                                    const int32_t dc_seed[3], const uint64_t *hist, uint8_t *d_raw,
+                                    size_t raw_cap, uint64_t *nbits, uint32_t *tail7)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    PIXO_TRY(validate_jpeg(ctx, width, band_height, color_type, subsampling));
+    if (!d_y || !d_raw || !nbits || !tail7 || (color_type != PIXO_B200_GRAY && (!d_cb || !d_cr)))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    if ((raw_cap & 3) || (reinterpret_cast<uintptr_t>(d_raw) & 15))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "raw buffer must be 16-byte aligned, capacity multiple of 4");
+    const FrameGeometry g = make_geometry(width, band_height, color_type, subsampling);
+    HuffTables t;
+    tables_from(hist, g.has_chroma, t);
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(1, g, 0)));
+    PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, 256));
+    uint64_t *d_len = nullptr, *d_tail = nullptr;
+    uint32_t *d_ovf = nullptr;
+    PIXO_TRY(launch_jpeg_entropy(ctx, d_y, 0, d_cb, d_cr, 0, 1, g, t, 0, reinterpret_cast<uint8_t *>(ctx->d_ent.ptr),
+                                 d_raw, raw_cap, &d_len, &d_ovf, dc_seed, &d_tail));
+    auto *h = reinterpret_cast<uint64_t *>(ctx->h_misc.ptr);
+    PIXO_CUDA(ctx, cudaMemcpyAsync(h, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(h + 1, d_tail, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(h + 2, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t ovf = *reinterpret_cast<uint32_t *>(h + 2);
+    *nbits = h[0];
+    *tail7 = (uint32_t)h[1] & 0x7Fu;
+    if (ovf & 2) return set_error(ctx, PIXO_B200_ERR_CUDA, "device entropy stage did not finish (flags %u)", ovf);
+    if (ovf) return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "raw capacity %zu too small (need %llu)", raw_cap,
+                              (unsigned long long)((h[0] + 7) / 8));
+    return 0;
+}
+
+int pixo_b200_jpeg_band_splice_dev(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t nbits,
+                                   uint64_t start_bit, uint32_t tail_in, uint32_t is_last_band,
+                                   uint8_t *d_out, size_t out_cap, uint64_t *out_len)
+{
+    if (!ctx || !d_out || !out_len || (!d_raw && nbits))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null argument");
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_misc, splice_scratch_bytes(nbits)));
+    PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, 256));
+    uint64_t *d_len = nullptr;
+    uint32_t *d_ovf = nullptr;
+    PIXO_TRY(launch_splice(ctx, d_raw, nbits, (uint32_t)(start_bit & 7), tail_in, is_last_band != 0,
+                           reinterpret_cast<uint8_t *>(ctx->d_misc.ptr), d_out, out_cap, &d_len, &d_ovf));
+    auto *h = reinterpret_cast<uint64_t *>(ctx->h_misc.ptr);
+    PIXO_CUDA(ctx, cudaMemcpyAsync(h, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(h + 1, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*reinterpret_cast<uint32_t *>(h + 1))
+        return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "splice output capacity %zu too small", out_cap);
+    *out_len = h[0];
+    return 0;
+}
+
+int pixo_b200_jpeg_band_entropy(const int16_t *y, const int16_t *cb, const int16_t *cr, uint32_t width,
+                                uint32_t band_height, uint32_t color_type, uint32_t subsampling,
+                                const int32_t dc_seed[3], const uint64_t *hist, uint8_t *raw,
+                                size_t raw_cap, uint64_t *nbits, uint32_t *tail7)
+{
+    PIXO_TRY(validate_jpeg(nullptr, width, band_height, color_type, subsampling));
+    if (!y || !raw || !nbits || !tail7 || (color_type != PIXO_B200_GRAY && (!cb || !cr)))
+        return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    const FrameGeometry g = make_geometry(width, band_height, color_type, subsampling);
+    HuffTables t;
+    tables_from(hist, g.has_chroma, t);
+    const uint64_t n = band_encode_raw(y, cb, cr, g, t, dc_seed, raw, raw_cap, tail7);
+    if (n == (uint64_t)-1) return set_error(nullptr, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "raw capacity %zu too small", raw_cap);
+    *nbits = n;
+    return 0;
+}
+
+int pixo_b200_jpeg_band_histogram(const int16_t *y, const int16_t *cb, const int16_t *cr, uint32_t width,
+                                  uint32_t band_height, uint32_t color_type, uint32_t subsampling,
+                                  const int32_t dc_seed[3], uint64_t hist[536])
+{
+    PIXO_TRY(validate_jpeg(nullptr, width, band_height, color_type, subsampling));
+    if (!y || !hist || (color_type != PIXO_B200_GRAY && (!cb || !cr)))
+        return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    const FrameGeometry g = make_geometry(width, band_height, color_type, subsampling);
+    host_histogram(y, cb, cr, g, 0, hist, dc_seed);
+    return 0;
+}
+
+int pixo_b200_jpeg_band_splice(const uint8_t *raw, uint64_t nbits, uint64_t start_bit, uint32_t tail_in,
+                               uint32_t is_last_band, uint8_t *out, size_t out_cap, size_t *out_len)
+{
+    if (!out || !out_len || (!raw && nbits)) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "null argument");
+    const size_t n = band_splice(raw, nbits, (uint32_t)(start_bit & 7), tail_in, is_last_band != 0, out, out_cap);
+    if (n == (size_t)-1) return set_error(nullptr, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "splice output capacity %zu too small", out_cap);
+    *out_len = n;
+    return 0;
+}
+
+int pixo_b200_jpeg_write_headers(uint32_t width, uint32_t height, uint32_t color_type, uint32_t quality,
+                                 uint32_t subsampling, uint32_t restart_interval, const uint64_t *hist,
+                                 uint8_t *out, size_t out_cap, size_t *out_len)
+{
+    if (quality == 0 || quality > 100)
+        return set_error(nullptr, PIXO_B200_ERR_INVALID_QUALITY, "Invalid quality %u: must be 1-100", quality);
+    if (restart_interval > 65535)
+        return set_error(nullptr, PIXO_B200_ERR_INVALID_RESTART, "Invalid restart interval %u", restart_interval);
+    PIXO_TRY(validate_jpeg(nullptr, width, height, color_type, subsampling));
+    if (!out || !out_len) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    if (out_cap < 1024) return set_error(nullptr, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small", out_cap);
+    const FrameGeometry g = make_geometry(width, height, color_type, subsampling);
+    uint8_t lum_zz[64], chr_zz[64];
+    quant_tables((int)quality, lum_zz, chr_zz, nullptr, nullptr);
+    HuffTables t;
+    tables_from(hist, g.has_chroma, t);
+    *out_len = write_headers(out, g, lum_zz, chr_zz, t, restart_interval);
+    return 0;
+}
+
 // ---- PNG ----------------------------------------------------------------------------------
 
 static int validate_png(pixo_b200_ctx *ctx, uint32_t width, uint32_t height, size_t row_bytes,
@@ -921,6 +1075,31 @@ int pixo_b200_png_filter(pixo_b200_ctx *ctx, const uint8_t *data, uint32_t width
         PIXO_CUDA(ctx, cudaMemcpyAsync(adler32_out, d_adler, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+int pixo_b200_png_filter_rows_dev(pixo_b200_ctx *ctx, const uint8_t *d_rows, const uint8_t *d_row_above,
+                                  uint32_t width, uint32_t image_height, uint32_t band_rows,
+                                  size_t row_bytes, uint32_t bytes_per_pixel, uint32_t strategy,
+                                  uint8_t *d_out, uint32_t *d_adler)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    PIXO_TRY(validate_png(ctx, width, image_height, row_bytes, bytes_per_pixel, strategy));
+    if (!d_rows || !d_out) return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    if (band_rows == 0 || band_rows > image_height)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "band_rows %u outside 1..%u", band_rows, image_height);
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_png_filter_rows(ctx, d_rows, row_bytes * band_rows, 1, width, band_rows, row_bytes, bytes_per_pixel,
+                                  strategy, d_out, (row_bytes + 1) * (size_t)band_rows, d_adler, d_row_above,
+                                  image_height);
+}
+
+uint32_t pixo_b200_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_t len_b)
+{
+    const uint64_t M = 65521;
+    const uint64_t a1 = adler_a & 0xFFFF, a2 = adler_a >> 16, b1 = adler_b & 0xFFFF, b2 = adler_b >> 16;
+    const uint64_t s1 = (a1 + b1 + M - 1) % M;
+    const uint64_t s2 = (a2 + b2 + (len_b % M) * ((a1 + M - 1) % M)) % M;
+    return (uint32_t)((s2 << 16) | s1);
 }
 
 int pixo_b200_adler32_dev(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t len, uint32_t *d_out)

@@ -78,11 +78,16 @@ int launch_jpeg_transform(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pi
 int launch_jpeg_histogram(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
                           const int16_t *d_cb, const int16_t *d_cr, size_t c_stride,
                           uint32_t n_images, size_t ny, size_t nc, uint32_t blocks_y_per_mcu,
-                          uint32_t restart_interval, bool zigzag_in, uint64_t *d_hist);
+                          uint32_t restart_interval, bool zigzag_in, uint64_t *d_hist,
+                          const int *dc_seed = nullptr);
 int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_stride,
                       uint32_t n_images, uint32_t width, uint32_t height, size_t row_bytes,
                       uint32_t bpp, uint32_t strategy, uint8_t *d_out, size_t out_stride,
                       uint32_t *d_adler);
+int launch_png_filter_rows(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_stride, uint32_t n_images,
+                           uint32_t width, uint32_t height, size_t row_bytes, uint32_t bpp, uint32_t strategy,
+                           uint8_t *d_out, size_t out_stride, uint32_t *d_adler, const uint8_t *d_above,
+                           uint32_t rule_height);
 int launch_adler32(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t len, uint32_t *d_out);
 
 struct FrameGeometry;
@@ -91,6 +96,11 @@ size_t entropy_scratch_bytes(uint32_t n, const FrameGeometry &g, uint32_t restar
 int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride, const int16_t *d_cb,
                         const int16_t *d_cr, size_t c_stride, uint32_t n, const FrameGeometry &g,
                         const HuffTables &t, uint32_t restart_interval, uint8_t *d_scratch, uint8_t *d_out,
-                        uint64_t out_cap, uint64_t **d_out_len, uint32_t **d_overflow);
+                        uint64_t out_cap, uint64_t **d_out_len, uint32_t **d_overflow,
+                        const int *dc_seed = nullptr, uint64_t **d_raw_tail = nullptr);
+size_t splice_scratch_bytes(uint64_t nbits);
+int launch_splice(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t nbits, uint32_t phase, uint32_t tail_in,
+                  bool last, uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap, uint64_t **d_out_len,
+                  uint32_t **d_overflow);
 
 }  // namespace pixo

@@ -69,6 +69,9 @@ struct EntParams {
     uint8_t *out;                  // [n][out_cap]
     uint64_t out_cap;
     uint64_t *out_len;             // [n] final byte count
+    int dc_seed[3];                // DC predictors (Y, Cb, Cr) before block 0: 0 for a whole image, the previous
+                                   // band's last DCs when the arrays are one band of a frame tiled over several GPUs
+    unsigned long long *out_tail;  // RAW only: [n] the stream's last 7 bits
     uint32_t *overflow;            // [n] bit 0: out_cap was exceeded (out_len = the size needed); bit 1: a chain timed out
 };
 
@@ -339,6 +342,15 @@ struct ChunkState {
 //   B  look back for the stuffed-byte offset, assemble again, emit
 // software-pipelined as  A(j) W(j+1) B(j):  a look-back runs a phase after the value it depends
 // on was published by this warp's neighbours in the chain, so it seldom has to wait for them.
+//
+// RAW (a band of a frame that is tiled over several GPUs, pixo_b200_jpeg_band_entropy_dev): the
+// band's bit string starts at an unknown bit of the frame's stream, so nothing that depends on
+// byte alignment can happen here.  Phase A writes the UNSTUFFED bytes of the band-local string
+// (bit 0 = the band's first bit, the last partial byte zero-filled, no 1-padding) straight from the
+// assembled windows, phase B and chain 2 do not exist, and the final chunk reports the string's
+// bit count and its last 7 bits.  k_splice_* below turn such a string into scan bytes once the
+// bit offset is known.
+template <bool RAW>
 __global__ void __launch_bounds__(32 * HUFF_WARPS, HUFF_CTAS_PER_SM)
 k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
 {
@@ -392,12 +404,13 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             const int16_t *arr;
             size_t idx;
             int tbl;
-            if (k < P.y_per_mcu) { arr = P.y + (size_t)C.img * P.y_stride; idx = (size_t)m * P.y_per_mcu + k; tbl = 0; }
-            else if (k == P.y_per_mcu) { arr = P.cb + (size_t)C.img * P.c_stride; idx = m; tbl = 1; }
-            else { arr = P.cr + (size_t)C.img * P.c_stride; idx = m; tbl = 1; }
+            int seed;
+            if (k < P.y_per_mcu) { arr = P.y + (size_t)C.img * P.y_stride; idx = (size_t)m * P.y_per_mcu + k; tbl = 0; seed = P.dc_seed[0]; }
+            else if (k == P.y_per_mcu) { arr = P.cb + (size_t)C.img * P.c_stride; idx = m; tbl = 1; seed = P.dc_seed[1]; }
+            else { arr = P.cr + (size_t)C.img * P.c_stride; idx = m; tbl = 1; seed = P.dc_seed[2]; }
             // DC predictors restart with the interval (src/jpeg/mod.rs:1433-1443)
             const bool dc_reset = P.rst_mcus && m % P.rst_mcus == 0 && (k == 0 || k >= P.y_per_mcu);
-            const int prev_dc = (idx && !dc_reset) ? arr[(idx - 1) * 64] : 0;
+            const int prev_dc = dc_reset ? 0 : (idx ? arr[(idx - 1) * 64] : seed);
             const uint4 *src = reinterpret_cast<const uint4 *>(arr + idx * 64);
             uint32_t e0 = 0, e1 = 0;
             int dc;
@@ -539,9 +552,9 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         const bool last_chunk = C.last;
         const uint32_t q0 = (uint32_t)C.Pc & 31u;         // bit offset of the chunk inside window word 0
         const uint32_t endbit = q0 + C.Lc;                // window bit index one past the chunk
-        const uint32_t padc = last_chunk ? ((8u - (endbit & 7u)) & 7u) : 0u;   // 1-padding (bits.rs:261-272)
+        const uint32_t padc = (last_chunk && !RAW) ? ((8u - (endbit & 7u)) & 7u) : 0u;   // 1-padding (bits.rs:261-272)
         const uint32_t ob0 = q0 >> 3;                     // owned window bytes [ob0, ob1)
-        const uint32_t ob1 = (endbit >> 3) + (padc ? 1u : 0u);
+        const uint32_t ob1 = RAW ? ((last_chunk ? endbit + 7u : endbit) >> 3) : (endbit >> 3) + (padc ? 1u : 0u);
         const int nrounds = max(1, (int)((ob1 + WIN_B - 1) / WIN_B));
         // per-lane constants of the funnel-shifted copy
         const uint32_t D = q0 + C.o_t;
@@ -597,6 +610,28 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
                 const uint4 y = reinterpret_cast<const uint4 *>(obuf)[2 * lane + 1];
                 wv[0] = x.x; wv[1] = x.y; wv[2] = x.z; wv[3] = x.w; wv[4] = y.x; wv[5] = y.y; wv[6] = y.z; wv[7] = y.w;
             }
+            if (RAW) {
+                // window byte i is byte (Pc >> 5) * 4 + wb0 + i of the band's raw string
+                uint8_t *outp = P.out + (size_t)C.img * P.out_cap;
+                const unsigned long long wbase = (C.Pc >> 5) * 4ull + (unsigned long long)wb0;
+                if (wbase + (unsigned long long)max(b, 0) <= P.out_cap) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int i0 = 32 * lane + 4 * j;
+                        if (i0 >= a && i0 + 4 <= b) {
+                            *reinterpret_cast<uint32_t *>(outp + wbase + i0) = __byte_perm(wv[j], 0, 0x0123);
+                        } else if (i0 + 4 > a && i0 < b) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)
+                                if (i0 + t >= a && i0 + t < b) outp[wbase + i0 + t] = (uint8_t)(wv[j] >> (24 - 8 * t));
+                        }
+                    }
+                } else if (lane == 0) {
+                    atomicOr(&P.overflow[C.img], 1u);
+                }
+                __syncwarp();
+                continue;
+            }
             uint32_t cnt = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) cnt += __popc(ff_bytes(wv[j]));
@@ -639,10 +674,20 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             if (lane == 0) st_status(st1 + C.chunk, pack_status(ST_PFX, C.ctail, C.Pc + C.Lc));
         }
         C.Ftot = sweep(C, false, 0);
+        if (RAW) {
+            if (lane == 0 && C.final_) {
+                P.out_len[C.img] = C.Pc + C.Lc;       // BITS
+                P.out_tail[C.img] = C.ctail;
+                if (((C.Pc + C.Lc + 7) >> 3) > P.out_cap) atomicOr(&P.overflow[C.img], 1u);
+            }
+            if (lane == 0 && C.fault) atomicOr(&P.overflow[C.img], 2u);
+            return;
+        }
         if (lane == 0) st_status(st2 + C.chunk, pack_status(C.chunk == 0 ? ST_PFX : ST_AGG, 0, C.own));
     };
     // ---- B: stuffed-byte offset from chain 2, then the bytes ------------------------------------------
     auto phase_b = [&](ChunkState &C) {
+        if (RAW) return;
         unsigned long long *st2 = P.st_ff + (size_t)C.img * P.nchunks;
         unsigned long long ffx = 0;
         if (C.chunk) {
@@ -694,7 +739,7 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
 // Device scratch layout for n images (all sizes in bytes, 256-aligned)
 struct EntropyPlan {
     size_t nchunks;
-    size_t off_st1, off_st2, off_ticket, off_ovf, zero_bytes, off_outlen, total;
+    size_t off_st1, off_st2, off_ticket, off_ovf, zero_bytes, off_outlen, off_tail, total;
 };
 
 static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
@@ -715,6 +760,7 @@ static EntropyPlan plan_entropy(uint32_t n, uint64_t nblocks, uint64_t rst_block
     p.off_ovf = o; o += a256((size_t)n * 4);
     p.zero_bytes = o;  // everything up to here is cleared per launch
     p.off_outlen = o; o += a256((size_t)n * 8);
+    p.off_tail = o; o += a256((size_t)n * 8);
     p.total = o;
     return p;
 }
@@ -731,8 +777,14 @@ size_t entropy_scratch_bytes(uint32_t n, const FrameGeometry &g, uint32_t restar
 int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride, const int16_t *d_cb,
                         const int16_t *d_cr, size_t c_stride, uint32_t n, const FrameGeometry &g,
                         const HuffTables &t, uint32_t restart_interval, uint8_t *d_scratch, uint8_t *d_out,
-                        uint64_t out_cap, uint64_t **d_out_len, uint32_t **d_overflow)
+                        uint64_t out_cap, uint64_t **d_out_len, uint32_t **d_overflow, const int *dc_seed,
+                        uint64_t **d_raw_tail)
 {
+    const bool raw = d_raw_tail != nullptr;
+    if (raw && restart_interval)
+        return set_error(ctx, PIXO_B200_ERR_UNSUPPORTED, "band-local raw coding does not take a restart interval");
+    if (raw && (out_cap & 3))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "raw buffer capacity must be a multiple of 4");
     const uint64_t nblocks = g.ny + 2 * g.nc;
     const uint64_t bpm_ = g.y_per_mcu + (g.has_chroma ? 2 : 0);
     uint64_t rst_blocks = (uint64_t)restart_interval * bpm_;
@@ -756,8 +808,11 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
     P.overflow = reinterpret_cast<uint32_t *>(d_scratch + pl.off_ovf);
     P.out_len = reinterpret_cast<uint64_t *>(d_scratch + pl.off_outlen);
     P.out = d_out; P.out_cap = out_cap;
+    P.out_tail = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_tail);
+    for (int k = 0; k < 3; ++k) P.dc_seed[k] = dc_seed ? dc_seed[k] : 0;
     *d_out_len = P.out_len;
     *d_overflow = P.overflow;
+    if (raw) *d_raw_tail = reinterpret_cast<uint64_t *>(P.out_tail);
 
     HuffDev T;
     memset(&T, 0, sizeof T);
@@ -775,8 +830,139 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
     PIXO_CUDA(ctx, cudaMemsetAsync(d_scratch, 0, pl.zero_bytes, st));
     const size_t want = ((size_t)n * pl.nchunks + HUFF_WARPS - 1) / HUFF_WARPS;
     const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)ctx->sm_count * HUFF_CTAS_PER_SM);
-    k_huff<<<grid, 32 * HUFF_WARPS, 0, st>>>(P, T);
+    if (raw) k_huff<true><<<grid, 32 * HUFF_WARPS, 0, st>>>(P, T);
+    else k_huff<false><<<grid, 32 * HUFF_WARPS, 0, st>>>(P, T);
     ctx->launches += 1;
+    PIXO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+// ---- splicing a band's raw bit string into the frame's scan ------------------------------------
+// T = tail_in (s bits, the frame's stream bits that precede the band inside its first byte) ++ B
+// (the band's raw string, nbits).  The band owns T's whole bytes; the frame's last band also owns
+// the final partial byte, padded with 1s (BitWriterMsb::flush, src/bits.rs:261-272).  Every 0xFF is
+// followed by 0x00 (flush_byte_with_stuffing, :245-259).  Two small kernels: per-tile 0xFF counts,
+// then every tile sums the counts before it and writes its stuffed bytes.
+namespace {
+
+constexpr int SPL_TILE = 4096;  // T bytes per CTA
+constexpr int SPL_THREADS = 256;
+
+struct SpliceParams {
+    const uint8_t *raw;
+    unsigned long long nbits;
+    uint32_t s, tail_in, last;
+    unsigned long long nbytes;   // T bytes this band emits before stuffing (incl. the padded one)
+    uint32_t *cnt;               // [ntiles]
+    uint8_t *out;
+    unsigned long long out_cap;
+    unsigned long long *out_len;
+    uint32_t *overflow;
+};
+
+// byte m of T (with the final partial byte 1-padded when this is the frame's last band)
+__device__ __forceinline__ uint32_t splice_byte(const SpliceParams &P, unsigned long long m)
+{
+    const unsigned long long rb = (P.nbits + 7) >> 3;   // raw bytes that exist
+    const uint32_t cur = m < rb ? P.raw[m] : 0u;
+    const uint32_t prev = m ? P.raw[m - 1] : P.tail_in;
+    uint32_t v = (((prev << 8) | cur) >> P.s) & 0xFFu;
+    const unsigned long long tbits = P.s + P.nbits;
+    if (m == (tbits >> 3)) v |= 0xFFu >> (uint32_t)(tbits & 7);   // only reached when last && tbits % 8 != 0
+    return v;
+}
+
+__global__ void __launch_bounds__(SPL_THREADS) k_splice_count(const __grid_constant__ SpliceParams P)
+{
+    __shared__ uint32_t red[SPL_THREADS / 32];
+    const unsigned long long m0 = (unsigned long long)blockIdx.x * SPL_TILE + threadIdx.x * 16;
+    uint32_t c = 0;
+    for (int i = 0; i < 16; ++i)
+        if (m0 + i < P.nbytes) c += splice_byte(P, m0 + i) == 0xFFu;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < SPL_THREADS / 32; ++i) t += red[i];
+        P.cnt[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(SPL_THREADS) k_splice_emit(const __grid_constant__ SpliceParams P)
+{
+    __shared__ unsigned long long s_before;
+    __shared__ uint32_t wsum[SPL_THREADS / 32];
+    __shared__ uint8_t sb[2 * SPL_TILE];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // 0xFF bytes in the tiles before this one
+    unsigned long long before = 0;
+    for (uint32_t i = tid; i < blockIdx.x; i += SPL_THREADS) before += P.cnt[i];
+    for (int o = 16; o; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (tid == 0) s_before = 0;
+    __syncthreads();
+    if (lane == 0 && before) atomicAdd(&s_before, before);
+    const unsigned long long m0 = (unsigned long long)blockIdx.x * SPL_TILE + tid * 16;
+    uint32_t v[16], c = 0;
+    for (int i = 0; i < 16; ++i) {
+        v[i] = m0 + i < P.nbytes ? splice_byte(P, m0 + i) : 0x100u;
+        c += v[i] == 0xFFu;
+    }
+    // exclusive scan of the per-thread 0xFF counts over the CTA
+    uint32_t inc = c;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+    for (int i = 0; i < SPL_THREADS / 32; ++i) { if (i < warp) woff += wsum[i]; total += wsum[i]; }
+    uint32_t dst = tid * 16 + woff + inc - c;
+    for (int i = 0; i < 16; ++i) {
+        if (v[i] > 0xFFu) break;
+        sb[dst++] = (uint8_t)v[i];
+        if (v[i] == 0xFFu) sb[dst++] = 0;
+    }
+    __syncthreads();
+    const unsigned long long tile_first = (unsigned long long)blockIdx.x * SPL_TILE;
+    const unsigned long long tile_n = P.nbytes > tile_first ? min((unsigned long long)SPL_TILE, P.nbytes - tile_first) : 0ull;
+    const unsigned long long g0 = tile_first + s_before;
+    const uint32_t nout = (uint32_t)tile_n + total;
+    if (g0 + nout <= P.out_cap) {
+        for (uint32_t i = tid; i < nout; i += SPL_THREADS) P.out[g0 + i] = sb[i];
+    } else if (tid == 0) {
+        atomicOr(P.overflow, 1u);
+    }
+    if (tid == 0 && blockIdx.x == gridDim.x - 1) *P.out_len = g0 + nout;
+}
+
+}  // namespace
+
+size_t splice_scratch_bytes(uint64_t nbits) { return a256(((nbits + 16) / 8 / SPL_TILE + 2) * 4) + 256; }
+
+// d_scratch: splice_scratch_bytes(nbits).  *d_out_len / *d_overflow point into it.
+int launch_splice(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t nbits, uint32_t phase, uint32_t tail_in,
+                  bool last, uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap, uint64_t **d_out_len,
+                  uint32_t **d_overflow)
+{
+    SpliceParams P;
+    P.raw = d_raw; P.nbits = nbits; P.s = phase & 7u; P.tail_in = tail_in & ((1u << (phase & 7u)) - 1u);
+    P.last = last ? 1u : 0u;
+    const uint64_t tbits = (uint64_t)P.s + nbits;
+    P.nbytes = (tbits >> 3) + ((last && (tbits & 7)) ? 1 : 0);
+    const unsigned ntiles = (unsigned)((P.nbytes + SPL_TILE - 1) / SPL_TILE);
+    P.out_len = reinterpret_cast<unsigned long long *>(d_scratch);
+    P.overflow = reinterpret_cast<uint32_t *>(d_scratch + 8);
+    P.cnt = reinterpret_cast<uint32_t *>(d_scratch + 256);
+    P.out = d_out; P.out_cap = out_cap;
+    *d_out_len = reinterpret_cast<uint64_t *>(P.out_len);
+    *d_overflow = P.overflow;
+    PIXO_CUDA(ctx, cudaMemsetAsync(d_scratch, 0, 256, ctx->stream));
+    if (ntiles == 0) return 0;   // nothing owned: length 0
+    k_splice_count<<<ntiles, SPL_THREADS, 0, ctx->stream>>>(P);
+    k_splice_emit<<<ntiles, SPL_THREADS, 0, ctx->stream>>>(P);
+    ctx->launches += 2;
     PIXO_CUDA(ctx, cudaGetLastError());
     return 0;
 }

@@ -239,6 +239,7 @@ struct ScanJob {
     uint32_t restart;
     bool zigzag_in;
     size_t m0, m1;
+    int seed[3] = {0, 0, 0};   // predictors before MCU 0 (a band of a tiled frame)
     RawBits bits;
     uint64_t nbits_total = 0;
 };
@@ -253,6 +254,7 @@ void run_job(ScanJob &j)
     w.buf.resize((j.m1 - j.m0) * (ypm + 2) * 24 + 4096);
     int py = 0, pcb = 0, pcr = 0;
     const bool fresh = j.m0 == 0 || (j.restart && j.m0 % j.restart == 0);
+    if (j.m0 == 0 && !j.restart) { py = j.seed[0]; pcb = j.seed[1]; pcr = j.seed[2]; }
     if (!fresh) {
         py = j.y[(j.m0 * ypm - 1) * 64];
         if (g.has_chroma) { pcb = j.cb[(j.m0 - 1) * 64]; pcr = j.cr[(j.m0 - 1) * 64]; }
@@ -551,8 +553,46 @@ size_t entropy_encode_scan(const int16_t *y, const int16_t *cb, const int16_t *c
     return sw.len;
 }
 
+// One band of a tiled frame -> its raw (unstuffed, unpadded) bit string, left-aligned in bytes.
+// Returns the bit count, or (uint64_t)-1 when `cap` is too small.
+uint64_t band_encode_raw(const int16_t *y, const int16_t *cb, const int16_t *cr, const FrameGeometry &g,
+                         const HuffTables &t, const int seed[3], uint8_t *out, size_t cap, uint32_t *tail7)
+{
+    ScanJob j;
+    j.y = y; j.cb = cb; j.cr = cr; j.g = &g; j.t = &t;
+    j.restart = 0; j.zigzag_in = false; j.m0 = 0; j.m1 = g.total_mcus();
+    for (int k = 0; k < 3; ++k) j.seed[k] = seed ? seed[k] : 0;
+    run_job<false>(j);
+    const size_t nbytes = (size_t)((j.nbits_total + 7) >> 3);
+    if (nbytes > cap) return (uint64_t)-1;
+    memcpy(out, j.bits.buf.data(), nbytes);
+    if (tail7) {   // the string's last 7 bits
+        uint32_t v = 0;
+        for (int b = 0; b < 7; ++b) {
+            if ((uint64_t)b >= j.nbits_total) break;
+            const uint64_t pos = j.nbits_total - 1 - (uint64_t)b;
+            v |= (uint32_t)((out[pos >> 3] >> (7 - (pos & 7))) & 1u) << b;
+        }
+        *tail7 = v;
+    }
+    return j.nbits_total;
+}
+
+// tail_in (phase bits) ++ raw string -> stuffed bytes; the frame's last band pads with 1s.
+size_t band_splice(const uint8_t *raw, uint64_t nbits, uint32_t phase, uint32_t tail_in, bool last,
+                   uint8_t *out, size_t cap)
+{
+    StuffWriter sw;
+    sw.out = out; sw.cap = cap;
+    sw.nbits = (int)(phase & 7u);
+    sw.acc = tail_in & ((1u << (phase & 7u)) - 1u);
+    sw.append(raw, (size_t)((nbits + 7) >> 3), 0, nbits);
+    if (last) sw.pad_flush(); else sw.drain_bytes();
+    return sw.overflow ? (size_t)-1 : sw.len;
+}
+
 void host_histogram(const int16_t *y, const int16_t *cb, const int16_t *cr,
-                    const FrameGeometry &g, uint32_t restart_interval, uint64_t hist[536])
+                    const FrameGeometry &g, uint32_t restart_interval, uint64_t hist[536], const int *seed)
 {
     memset(hist, 0, 536 * sizeof(uint64_t));
     auto count = [&](const int16_t *blk, int prev, uint64_t *dc, uint64_t *ac) {
@@ -570,6 +610,7 @@ void host_histogram(const int16_t *y, const int16_t *cb, const int16_t *cr,
         return d;
     };
     int py = 0, pcb = 0, pcr = 0;
+    if (seed && !restart_interval) { py = seed[0]; pcb = seed[1]; pcr = seed[2]; }
     const size_t total = g.total_mcus();
     for (size_t m = 0; m < total; ++m) {
         if (restart_interval && m && m % restart_interval == 0) py = pcb = pcr = 0;

@@ -51,7 +51,15 @@ size_t entropy_encode_scan(const int16_t *y, const int16_t *cb, const int16_t *c
 
 // histogram of a frame on the host (used by the host-only entropy API)
 void host_histogram(const int16_t *y, const int16_t *cb, const int16_t *cr,
-                    const FrameGeometry &g, uint32_t restart_interval, uint64_t hist[536]);
+                    const FrameGeometry &g, uint32_t restart_interval, uint64_t hist[536],
+                    const int *seed = nullptr);
+
+// A frame tiled over several GPUs: one band's raw bit string and its splice
+// into the frame's scan (host versions of k_huff<RAW> / k_splice_*).
+uint64_t band_encode_raw(const int16_t *y, const int16_t *cb, const int16_t *cr, const FrameGeometry &g,
+                         const HuffTables &t, const int seed[3], uint8_t *out, size_t cap, uint32_t *tail7);
+size_t band_splice(const uint8_t *raw, uint64_t nbits, uint32_t phase, uint32_t tail_in, bool last,
+                   uint8_t *out, size_t cap);
 
 // true when every AC coefficient has category <= 10 and every DC difference (previous block of
 // the same component, reset at restart boundaries) category <= 11

@@ -287,6 +287,17 @@ struct __align__(16) QPair {
     float nd_lo, nd_hi, r_lo, r_hi;
 };
 
+// The quantiser's table as a KERNEL PARAMETER (constant bank): 32 entries per component table, one
+// per output word.  Indexed with compile-time offsets plus a warp-uniform table selector, ptxas
+// fetches the entries with LDCU.128 into UNIFORM registers and feeds them to FMUL2/FFMA2 as UR
+// operands - no LDS, no vector registers and no short-scoreboard wait in the quantiser (the
+// shared-memory table this replaces cost 32 LDS.128 per block, each followed by a dependent
+// FMUL2 because the 168-register budget left no room to fetch ahead; profiles/r01: 15 % of all
+// stall samples).
+struct QPairTab {
+    QPair t[2][32];  // [0] luminance, [1] chrominance (x4 folded in for 4:2:0, see fill_qpair_tab)
+};
+
 // dct_2d (src/jpeg/dct.rs:614-646) + quantize_block (src/jpeg/quantize.rs:99-105) on a block
 // held as row pairs R[i][c] = (v[2i][c], v[2i+1][c]); writes 64 int16 (8 x 16 B).
 //   x / d      : q0 = x*r; q = fma(fma(q0, -d, x), r, q0) == RN(x/d)     (tools/verify_div.c)
@@ -296,8 +307,8 @@ struct __align__(16) QPair {
 // `out` is the block's 128-byte slot in a warp-private shared-memory stage; its eight 16-byte
 // chunks are written at chunk index (k ^ swz) so that the lanes of a quarter warp hit distinct
 // banks (the caller then copies the stage out with fully coalesced 512-byte warp stores).
-template <bool ZIGZAG>
-__device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *__restrict__ tab,
+template <bool ZIGZAG, int TSEL>
+__device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPairTab &qp,
                                                    uint4 *__restrict__ out, const int swz,
                                                    const f2 zero2)
 {
@@ -329,15 +340,15 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPair *_
     asm("mov.b32 %0, 0x3F800000;" : "=r"(kOne));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float4 T[8];
+        QPair T[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) T[r] = *reinterpret_cast<const float4 *>(&tab[r * 4 + j]);
+        for (int r = 0; r < 8; ++r) T[r] = qp.t[TSEL][r * 4 + j];
         const f2 in[8] = {C[0][j], C[1][j], C[2][j], C[3][j], C[4][j], C[5][j], C[6][j], C[7][j]};
         f2 o[8];
         aan_1d_x2_core(in, o, zero2);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const f2 nd = pk(T[r].x, T[r].y), rc = pk(T[r].z, T[r].w);
+            const f2 nd = pk(T[r].nd_lo, T[r].nd_hi), rc = pk(T[r].r_lo, T[r].r_hi);
             const f2 x = mul2(o[r], K2(SK[r]));   // post-scale: feeds only a multiply / fma addend
             const f2 q0 = mul2(x, rc);
             const f2 e = fma2(q0, nd, x);
@@ -388,32 +399,6 @@ __device__ __forceinline__ void flush_stage(const uint4 *__restrict__ stage, int
         if (d) d[k] = v;
     }
     __syncwarp();
-}
-
-// Quantisation tables in the layout dct_quant_store_x2 wants.  scale: the block handed to the
-// DCT is `scale` x the reference's block (4 for 4:2:0 chroma, whose x0.25 is folded in here:
-// power-of-two scaling commutes exactly with every rounding in the pipeline).
-struct QuantSmem {
-    QPair lum[32];
-    QPair chr[32];
-};
-
-__device__ __forceinline__ void fill_quant_smem(QuantSmem *q, const QuantTab &qt, float chr_scale,
-                                                int tid, int nthreads)
-{
-    for (int w = tid; w < 64; w += nthreads) {
-        const bool c = w >= 32;
-        const int i = (w & 31) * 2;
-        const float *d = c ? qt.chr_d : qt.lum_d;
-        const float *r = c ? qt.chr_r : qt.lum_r;
-        const float sc = c ? chr_scale : 1.0f;
-        QPair e;
-        e.nd_lo = -(d[i] * sc);
-        e.nd_hi = -(d[i + 1] * sc);
-        e.r_lo = r[i] / sc;
-        e.r_hi = r[i + 1] / sc;
-        (c ? q->chr : q->lum)[w & 31] = e;
-    }
 }
 
 // ---- TMA / mbarrier plumbing ---------------------------------------------------------------
@@ -495,7 +480,6 @@ struct __align__(128) K1WarpSmem {
 
 struct __align__(128) K1Smem {
     K1WarpSmem w[K1_WARPS];
-    QuantSmem q;
 };
 
 // One RGB row of a Y block (8 px in six words): Y - 128 as float for each pixel and the packed
@@ -541,7 +525,7 @@ __device__ __noinline__ void warp_load_tile_rgb(uint8_t *__restrict__ smem,
 
 template <bool ZIGZAG>
 __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
-k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab qt,
+k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QPairTab qp,
            const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -550,7 +534,6 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
     const int lane = tid & 31, warp = tid >> 5;
     K1WarpSmem &WS = S.w[warp];
 
-    fill_quant_smem(&S.q, qt, 4.0f, tid, K1_THREADS);
     if (lane == 0) {
         mbar_init(&WS.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -611,107 +594,101 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
         const size_t mcu_base = (size_t)my * P.mcus_x + mcu0;
 
 #pragma unroll 1
-        for (int job = 0; job < 3; ++job) {
+        for (int job = 0; job < 2; ++job) {
+            // ---- 32 Y blocks (8 MCUs) + their packed chroma quad sums ----
             f2 R[4][8];
-            const QPair *tab;
-            uint4 *stage;   // this warp's 32 x 128-byte output stage for the job
-            int slot, swz;
-            bool active;
-            if (job < 2) {
-                // ---- 32 Y blocks (8 MCUs) + their packed chroma quad sums ----
-                const int by = lane >> 4, l16 = lane & 15;
-                const int par = l16 >> 3, k8 = l16 & 7;
-                const int mj = (k8 >> 1) * 2 + par;   // MCU within the job; same parity per quarter warp
-                const int mcu = job * 8 + mj;
-                const int bx = k8 & 1;
-                active = (uint32_t)mcu < n_mcu;
-                const uint8_t *base = WS.tile[job] + (by * 8) * K1_HB + (mj * 2 + bx) * 24;
-                uint4 *cdst = reinterpret_cast<uint4 *>(WS.csum) + mcu * 16;
-                if (active) {
+            const int by = lane >> 4, l16 = lane & 15;
+            const int par = l16 >> 3, k8 = l16 & 7;
+            const int mj = (k8 >> 1) * 2 + par;   // MCU within the job; same parity per quarter warp
+            const int mcu = job * 8 + mj;
+            const int bx = k8 & 1;
+            const uint8_t *base = WS.tile[job] + (by * 8) * K1_HB + (mj * 2 + bx) * 24;
+            uint4 *cdst = reinterpret_cast<uint4 *>(WS.csum) + mcu * 16;
+            if ((uint32_t)mcu < n_mcu) {
 #pragma unroll
-                    for (int rp = 0; rp < 4; ++rp) {
-                        float y0[8], y1[8];
-                        uint32_t h0[4], h1[4];
-                        {
-                            const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2) * K1_HB);
-                            const uint2 a = p[0], b = p[1], c = p[2];
-                            const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-                            ycc_row8(wds, y0, h0);
-                        }
-                        {
-                            const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2 + 1) * K1_HB);
-                            const uint2 a = p[0], b = p[1], c = p[2];
-                            const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-                            ycc_row8(wds, y1, h1);
-                        }
+                for (int rp = 0; rp < 4; ++rp) {
+                    float y0[8], y1[8];
+                    uint32_t h0[4], h1[4];
+                    {
+                        const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2) * K1_HB);
+                        const uint2 a = p[0], b = p[1], c = p[2];
+                        const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+                        ycc_row8(wds, y0, h0);
+                    }
+                    {
+                        const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2 + 1) * K1_HB);
+                        const uint2 a = p[0], b = p[1], c = p[2];
+                        const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+                        ycc_row8(wds, y1, h1);
+                    }
 #pragma unroll
-                        for (int x = 0; x < 8; ++x)  // (2^23 + y) - (2^23 + 128) = y - 128, exact
-                            R[rp][x] = sub2(pk(y0[x], y1[x]), K2(8388736.0f));
-                        const int logical = (by * 4 + rp) * 2 + bx;
-                        cdst[logical ^ (mcu & 7)] =
-                            make_uint4(h0[0] + h1[0], h0[1] + h1[1], h0[2] + h1[2], h0[3] + h1[3]);
+                    for (int x = 0; x < 8; ++x)  // (2^23 + y) - (2^23 + 128) = y - 128, exact
+                        R[rp][x] = sub2(pk(y0[x], y1[x]), K2(8388736.0f));
+                    const int logical = (by * 4 + rp) * 2 + bx;
+                    cdst[logical ^ (mcu & 7)] =
+                        make_uint4(h0[0] + h1[0], h0[1] + h1[1], h0[2] + h1[2], h0[3] + h1[3]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) R[i][x] = 0ull;   // MCUs past the right edge
+            }
+            __syncwarp();  // every lane is done with this half tile
+            uint4 *stage = reinterpret_cast<uint4 *>(WS.tile[job]);  // the consumed half becomes the stage
+            const int slot = mj * 4 + by * 2 + bx;              // = block index within the job's 32
+            const int swz = ((slot >> 3) << 1) | (slot & 1);    // distinct across a quarter warp
+            // The transform runs in every lane (edge lanes work on zeros and their slots are never
+            // flushed): the quantiser's table reads are uniform-datapath loads, which exist only in
+            // warp-convergent code.
+            dct_quant_store_x2<ZIGZAG, 0>(R, qp, stage + slot * 8, swz, zero2);
+            uint4 *ybase = reinterpret_cast<uint4 *>(P.y + (size_t)img * P.y_stride + (mcu_base + job * 8) * 4 * 64);
+            const uint32_t first = job * 8;
+            flush_stage(
+                stage, lane, [](int s) { return ((s >> 3) << 1) | (s & 1); },
+                [&](int s) -> uint4 * { return first + (s >> 2) < n_mcu ? ybase + s * 8 : nullptr; });
+        }
+        {
+            const uint64_t un = u + stride;
+            if (lane == 0 && un < nunits) issue_tma(un);   // both half tiles were flushed
+            // ---- lanes 0-15: Cb of MCU lane, lanes 16-31: Cr of MCU lane-16 ----
+            f2 R[4][8];
+            const int comp = lane >> 4, mcu = lane & 15;
+            const uint4 *csrc = reinterpret_cast<const uint4 *>(WS.csum) + mcu * 16;
+            const uint32_t sel = comp == 0 ? 0x7610u : 0x7632u;
+            // low half = 65536 - sum(cb), high half = 65539 - sum(cr)  (see ycc_row8);
+            // block value = 4 * (sum * 0.25 - 128) = sum - 512  (src/jpeg/mod.rs:1642-1653)
+            const float bias = comp == 0 ? 8453632.0f : 8453635.0f;  // 2^23 + 65536(+3) - 512
+            // (edge lanes read sums no Y job wrote for them: finite garbage, never flushed)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v0[8], v1[8];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int l0 = (2 * i) * 2 + hh, l1 = (2 * i + 1) * 2 + hh;
+                    const uint4 s0 = csrc[l0 ^ (mcu & 7)];
+                    const uint4 s1 = csrc[l1 ^ (mcu & 7)];
+                    const uint32_t a[4] = {s0.x, s0.y, s0.z, s0.w};
+                    const uint32_t b[4] = {s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        v0[hh * 4 + k] = __uint_as_float(__byte_perm(a[k], 0x4B000000u, sel));
+                        v1[hh * 4 + k] = __uint_as_float(__byte_perm(b[k], 0x4B000000u, sel));
                     }
                 }
-                __syncwarp();  // every lane is done with this half tile
-                stage = reinterpret_cast<uint4 *>(WS.tile[job]);  // the consumed half becomes the stage
-                slot = mj * 4 + by * 2 + bx;                  // = block index within the job's 32
-                swz = ((slot >> 3) << 1) | (slot & 1);        // distinct across a quarter warp
-                tab = S.q.lum;
-            } else {
-                const uint64_t un = u + stride;
-                if (lane == 0 && un < nunits) issue_tma(un);   // both half tiles were flushed
-                // ---- lanes 0-15: Cb of MCU lane, lanes 16-31: Cr of MCU lane-16 ----
-                const int comp = lane >> 4, mcu = lane & 15;
-                active = (uint32_t)mcu < n_mcu;
-                const uint4 *csrc = reinterpret_cast<const uint4 *>(WS.csum) + mcu * 16;
-                const uint32_t sel = comp == 0 ? 0x7610u : 0x7632u;
-                // low half = 65536 - sum(cb), high half = 65539 - sum(cr)  (see ycc_row8);
-                // block value = 4 * (sum * 0.25 - 128) = sum - 512  (src/jpeg/mod.rs:1642-1653)
-                const float bias = comp == 0 ? 8453632.0f : 8453635.0f;  // 2^23 + 65536(+3) - 512
-                if (active) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float v0[8], v1[8];
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const int l0 = (2 * i) * 2 + hh, l1 = (2 * i + 1) * 2 + hh;
-                            const uint4 s0 = csrc[l0 ^ (mcu & 7)];
-                            const uint4 s1 = csrc[l1 ^ (mcu & 7)];
-                            const uint32_t a[4] = {s0.x, s0.y, s0.z, s0.w};
-                            const uint32_t b[4] = {s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                v0[hh * 4 + k] = __uint_as_float(__byte_perm(a[k], 0x4B000000u, sel));
-                                v1[hh * 4 + k] = __uint_as_float(__byte_perm(b[k], 0x4B000000u, sel));
-                            }
-                        }
-#pragma unroll
-                        for (int x = 0; x < 8; ++x) R[i][x] = sub2(K2(bias), pk(v0[x], v1[x]));
-                    }
-                }
-                __syncwarp();  // every lane has read its chroma sums: the buffer becomes the stage
-                stage = reinterpret_cast<uint4 *>(WS.csum);
-                slot = lane;                                  // 0-15 Cb, 16-31 Cr
-                swz = slot & 7;
-                tab = S.q.chr;
+                for (int x = 0; x < 8; ++x) R[i][x] = sub2(K2(bias), pk(v0[x], v1[x]));
             }
-            if (active) dct_quant_store_x2<ZIGZAG>(R, tab, stage + slot * 8, swz, zero2);
-            if (job < 2) {
-                uint4 *ybase = reinterpret_cast<uint4 *>(P.y + (size_t)img * P.y_stride +
-                                                         (mcu_base + job * 8) * 4 * 64);
-                const uint32_t first = job * 8;
-                flush_stage(
-                    stage, lane, [](int s) { return ((s >> 3) << 1) | (s & 1); },
-                    [&](int s) -> uint4 * { return first + (s >> 2) < n_mcu ? ybase + s * 8 : nullptr; });
-            } else {
-                uint4 *cbb = reinterpret_cast<uint4 *>(P.cb + (size_t)img * P.c_stride + mcu_base * 64);
-                uint4 *crb = reinterpret_cast<uint4 *>(P.cr + (size_t)img * P.c_stride + mcu_base * 64);
-                flush_stage(
-                    stage, lane, [](int s) { return s & 7; },
-                    [&](int s) -> uint4 * {
-                        return (uint32_t)(s & 15) < n_mcu ? (s < 16 ? cbb : crb) + (s & 15) * 8 : nullptr;
-                    });
-            }
+            __syncwarp();  // every lane has read its chroma sums: the buffer becomes the stage
+            uint4 *stage = reinterpret_cast<uint4 *>(WS.csum);
+            dct_quant_store_x2<ZIGZAG, 1>(R, qp, stage + lane * 8, lane & 7, zero2);   // slot = lane: 0-15 Cb, 16-31 Cr
+            uint4 *cbb = reinterpret_cast<uint4 *>(P.cb + (size_t)img * P.c_stride + mcu_base * 64);
+            uint4 *crb = reinterpret_cast<uint4 *>(P.cr + (size_t)img * P.c_stride + mcu_base * 64);
+            flush_stage(
+                stage, lane, [](int s) { return s & 7; },
+                [&](int s) -> uint4 * {
+                    return (uint32_t)(s & 15) < n_mcu ? (s < 16 ? cbb : crb) + (s & 15) * 8 : nullptr;
+                });
         }
     }
 }
@@ -776,7 +753,6 @@ struct __align__(128) K4WarpSmem {
 
 struct __align__(128) K4Smem {
     K4WarpSmem w[K4_WARPS];
-    QuantSmem q;
 };
 
 // K1Params with mcus_x / mcus_y = blocks per row / block rows, units_x = units per block row
@@ -785,14 +761,13 @@ struct __align__(128) K4Smem {
 #endif
 template <bool ZIGZAG>
 __global__ void __launch_bounds__(K4_THREADS, K4_MIN_BLOCKS)
-k_jpeg_444(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab qt,
+k_jpeg_444(const __grid_constant__ K1Params P, const __grid_constant__ QPairTab qp,
            const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     K4Smem &S = *reinterpret_cast<K4Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     K4WarpSmem &WS = S.w[warp];
-    fill_quant_smem(&S.q, qt, 1.0f, tid, K4_THREADS);
     if (lane == 0) {
         mbar_init(&WS.bar[0], 1);
         mbar_init(&WS.bar[1], 1);
@@ -839,48 +814,50 @@ k_jpeg_444(const __grid_constant__ K1Params P, const __grid_constant__ QuantTab 
             __syncwarp();
         }
         const uint32_t bx0 = ux * 32;
-        const bool active = bx0 + lane < P.mcus_x;
+        // Lanes past the right edge transform whatever their 24-byte columns of the tile hold (the
+        // tile is always 32 blocks wide) and are dropped by the flush: the whole pass is
+        // warp-convergent, which the quantiser's uniform-datapath table reads need.
         const uint8_t *base = WS.tile[b] + lane * 24;
-#pragma unroll 1
-        for (int comp = 0; comp < 3; ++comp) {
-            if (active) {
-                f2 R[4][8];
-                auto row_words = [&](int r, uint32_t (&wds)[6]) {
-                    const uint2 *p = reinterpret_cast<const uint2 *>(base + r * K4_ROW_B);
-                    const uint2 a = p[0], c1 = p[1], c2 = p[2];
-                    wds[0] = a.x; wds[1] = a.y; wds[2] = c1.x; wds[3] = c1.y; wds[4] = c2.x; wds[5] = c2.y;
-                };
-                // the component is decided ONCE per pass, not per pixel: two straight-line fills
-                if (comp == 0) {
-#pragma unroll
-                    for (int rp = 0; rp < 4; ++rp) {
-                        float v0[8], v1[8];
-                        uint32_t wa[6], wb[6];
-                        row_words(rp * 2, wa); row_words(rp * 2 + 1, wb);
-                        y_row8(wa, v0); y_row8(wb, v1);
-#pragma unroll
-                        for (int x = 0; x < 8; ++x) R[rp][x] = pk(v0[x], v1[x]);
-                    }
-                } else {
-                    const uint32_t wgt = comp == 1 ? 0x0080552Bu : 0x00156B80u;
-#pragma unroll
-                    for (int rp = 0; rp < 4; ++rp) {
-                        float v0[8], v1[8];
-                        uint32_t wa[6], wb[6];
-                        row_words(rp * 2, wa); row_words(rp * 2 + 1, wb);
-                        c_row8(wa, wgt, v0); c_row8(wb, wgt, v1);
-#pragma unroll
-                        for (int x = 0; x < 8; ++x) R[rp][x] = pk(v0[x], v1[x]);
-                    }
-                }
-                dct_quant_store_x2<ZIGZAG>(R, comp == 0 ? S.q.lum : S.q.chr, WS.stage + lane * 8, lane & 7, zero2);
-            }
-            int16_t *arr = comp == 0 ? P.y + (size_t)img * P.y_stride
-                                     : (comp == 1 ? P.cb : P.cr) + (size_t)img * P.c_stride;
+        auto row_words = [&](int r, uint32_t (&wds)[6]) {
+            const uint2 *p = reinterpret_cast<const uint2 *>(base + r * K4_ROW_B);
+            const uint2 a = p[0], c1 = p[1], c2 = p[2];
+            wds[0] = a.x; wds[1] = a.y; wds[2] = c1.x; wds[3] = c1.y; wds[4] = c2.x; wds[5] = c2.y;
+        };
+        auto flush = [&](int16_t *arr) {
             uint4 *dbase = reinterpret_cast<uint4 *>(arr + ((size_t)by * P.mcus_x + bx0) * 64);
             flush_stage(
                 WS.stage, lane, [](int s) { return s & 7; },
                 [&](int s) -> uint4 * { return bx0 + s < P.mcus_x ? dbase + s * 8 : nullptr; });
+        };
+        {   // the component is decided once per pass, not per pixel: straight-line fills
+            f2 R[4][8];
+#pragma unroll
+            for (int rp = 0; rp < 4; ++rp) {
+                float v0[8], v1[8];
+                uint32_t wa[6], wb[6];
+                row_words(rp * 2, wa); row_words(rp * 2 + 1, wb);
+                y_row8(wa, v0); y_row8(wb, v1);
+#pragma unroll
+                for (int x = 0; x < 8; ++x) R[rp][x] = pk(v0[x], v1[x]);
+            }
+            dct_quant_store_x2<ZIGZAG, 0>(R, qp, WS.stage + lane * 8, lane & 7, zero2);
+            flush(P.y + (size_t)img * P.y_stride);
+        }
+#pragma unroll 1
+        for (int comp = 1; comp < 3; ++comp) {
+            f2 R[4][8];
+            const uint32_t wgt = comp == 1 ? 0x0080552Bu : 0x00156B80u;
+#pragma unroll
+            for (int rp = 0; rp < 4; ++rp) {
+                float v0[8], v1[8];
+                uint32_t wa[6], wb[6];
+                row_words(rp * 2, wa); row_words(rp * 2 + 1, wb);
+                c_row8(wa, wgt, v0); c_row8(wb, wgt, v1);
+#pragma unroll
+                for (int x = 0; x < 8; ++x) R[rp][x] = pk(v0[x], v1[x]);
+            }
+            dct_quant_store_x2<ZIGZAG, 1>(R, qp, WS.stage + lane * 8, lane & 7, zero2);
+            flush((comp == 1 ? P.cb : P.cr) + (size_t)img * P.c_stride);
         }
         __syncwarp();  // every lane is done with tile[b]: the TMA issued next iteration may refill it
     }
@@ -890,24 +867,22 @@ template <bool ZIGZAG>
 __global__ void __launch_bounds__(64)
 k_jpeg_gray(const uint8_t *__restrict__ pixels, size_t pixel_stride, uint32_t w, uint32_t h,
             uint32_t blocks_x, uint32_t tiles_x, int16_t *__restrict__ yout, size_t y_stride,
-            const __grid_constant__ QuantTab qt, const float zero_lo, const float zero_hi)
+            const __grid_constant__ QPairTab qp, const float zero_lo, const float zero_hi)
 {
     constexpr int TB = K2_BLOCKS * 8;  // 512
     __shared__ __align__(16) uint8_t tile[8 * TB];
     __shared__ __align__(16) uint4 stage[2][256];
-    __shared__ QuantSmem qs;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tx = blockIdx.x % tiles_x;
     const uint32_t brow = blockIdx.x / tiles_x;
     const uint32_t img = blockIdx.y;
     const uint8_t *image = pixels + (size_t)img * pixel_stride;
-    fill_quant_smem(&qs, qt, 1.0f, tid, 64);
     load_tile<1, 8, K2_BLOCKS * 8, 64>(tile, image, w, h, tx * (K2_BLOCKS * 8), brow * 8, tid);
     __syncthreads();
     const int j = tid;
     const uint32_t b0 = tx * K2_BLOCKS;
     const f2 zero2 = pk(zero_lo, zero_hi);
-    if (b0 + j < blocks_x) {
+    {   // every lane (the tile is fully defined: load_tile replicates past the right edge; the flush drops them)
         f2 R[4][8];
 #pragma unroll
         for (int rp = 0; rp < 4; ++rp) {
@@ -922,7 +897,7 @@ k_jpeg_gray(const uint8_t *__restrict__ pixels, size_t pixel_stride, uint32_t w,
                 R[rp][x] = sub2(pk(f0, f1), K2(8388736.0f));
             }
         }
-        dct_quant_store_x2<ZIGZAG>(R, qs.lum, stage[warp] + lane * 8, lane & 7, zero2);
+        dct_quant_store_x2<ZIGZAG, 0>(R, qp, stage[warp] + lane * 8, lane & 7, zero2);
     }
     const uint32_t first = b0 + warp * 32;
     uint4 *dbase = reinterpret_cast<uint4 *>(yout + (size_t)img * y_stride + ((size_t)brow * blocks_x + first) * 64);
@@ -949,7 +924,7 @@ __global__ void __launch_bounds__(256)
 k_jpeg_hist(const int16_t *__restrict__ ycoef, size_t y_stride, const int16_t *__restrict__ cbcoef,
             const int16_t *__restrict__ crcoef, size_t c_stride, size_t ny, size_t nc,
             uint32_t blocks_y_per_mcu, uint32_t restart_interval,
-            unsigned long long *__restrict__ hist)
+            unsigned long long *__restrict__ hist, const int seed_y, const int seed_cb, const int seed_cr)
 {
     __shared__ uint32_t sh[kHistWords];
     for (int i = threadIdx.x; i < kHistWords; i += blockDim.x) sh[i] = 0;
@@ -962,9 +937,10 @@ k_jpeg_hist(const int16_t *__restrict__ ycoef, size_t y_stride, const int16_t *_
         size_t idx;
         bool lum;
         uint32_t per_mcu;
-        if (b < ny) { arr = ycoef + (size_t)img * y_stride; idx = b; lum = true; per_mcu = blocks_y_per_mcu; }
-        else if (b < ny + nc) { arr = cbcoef + (size_t)img * c_stride; idx = b - ny; lum = false; per_mcu = 1; }
-        else { arr = crcoef + (size_t)img * c_stride; idx = b - ny - nc; lum = false; per_mcu = 1; }
+        int seed;  // predictor before block 0: non-zero only for a band of a tiled frame
+        if (b < ny) { arr = ycoef + (size_t)img * y_stride; idx = b; lum = true; per_mcu = blocks_y_per_mcu; seed = seed_y; }
+        else if (b < ny + nc) { arr = cbcoef + (size_t)img * c_stride; idx = b - ny; lum = false; per_mcu = 1; seed = seed_cb; }
+        else { arr = crcoef + (size_t)img * c_stride; idx = b - ny - nc; lum = false; per_mcu = 1; seed = seed_cr; }
         const uint4 *src = reinterpret_cast<const uint4 *>(arr + idx * 64);
         uint32_t wv[32];
 #pragma unroll
@@ -973,11 +949,10 @@ k_jpeg_hist(const int16_t *__restrict__ ycoef, size_t y_stride, const int16_t *_
             wv[k * 4] = t.x; wv[k * 4 + 1] = t.y; wv[k * 4 + 2] = t.z; wv[k * 4 + 3] = t.w;
         }
         // DC difference against the previous block of this component
-        int prev = 0;
         const size_t mcu = idx / per_mcu;
         const bool first_in_mcu = (idx % per_mcu) == 0;
-        const bool reset = idx == 0 || (restart_interval && first_in_mcu && (mcu % restart_interval) == 0);
-        if (!reset) prev = arr[(idx - 1) * 64];
+        const bool reset = restart_interval && first_in_mcu && (mcu % restart_interval) == 0;
+        const int prev = reset ? 0 : (idx ? (int)arr[(idx - 1) * 64] : seed);
         const int dc = (int)(int16_t)(wv[0] & 0xFFFF);
         const int diff = (int)(int16_t)(dc - prev);
         atomicAdd(&sh[(lum ? 0 : 12) + category16(diff)], 1u);
@@ -1004,74 +979,24 @@ k_jpeg_hist(const int16_t *__restrict__ ycoef, size_t y_stride, const int16_t *_
         if (sh[i]) atomicAdd(&hist[(size_t)img * kHistWords + i], (unsigned long long)sh[i]);
 }
 
-#ifdef PIXO_UBENCH
-// Development microbenchmark (variant builds only): the block pipeline in isolation.
-//   mode 0: DCT + quant + stage (dct_quant_store_x2) on register data, no colour work
-//   mode 1: Y fill (ycc_row8 from a shared-memory tile) only
-//   mode 2: both, back to back (one Y job without global traffic)
-template <int MODE>
-__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS) k_ubench(int iters, float zlo, float zhi, uint32_t *sink)
+// Table entries (-d, -d', r, r') per output word, r = RN(1/d) (see dct_quant_store_x2).
+// chr_scale: the chroma block handed to the DCT is `chr_scale` x the reference's block (4 for
+// 4:2:0, whose x0.25 is folded in here: power-of-two scaling commutes exactly with every rounding
+// in the pipeline).
+void fill_qpair_tab(const float *lum_q, const float *chr_q, float chr_scale, QPairTab *qp)
 {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    K1Smem &S = *reinterpret_cast<K1Smem *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    K1WarpSmem &WS = S.w[warp];
-    for (int i = tid; i < (int)sizeof(K1Smem) / 4; i += K1_THREADS) reinterpret_cast<uint32_t *>(smem_raw)[i] = i * 2654435761u;
-    __syncthreads();
-    for (int w = tid; w < 64; w += K1_THREADS) {
-        QPair e; e.nd_lo = -(float)(3 + w % 7); e.nd_hi = -(float)(2 + w % 5); e.r_lo = -1.0f / e.nd_lo; e.r_hi = -1.0f / e.nd_hi;
-        (w >= 32 ? S.q.chr : S.q.lum)[w & 31] = e;
-    }
-    __syncthreads();
-    const f2 zero2 = pk(zlo, zhi);
-    uint32_t acc = 0;
-    for (int it = 0; it < iters; ++it) {
-        f2 R[4][8];
-        const int by = lane >> 4, l16 = lane & 15, par = l16 >> 3, k8 = l16 & 7;
-        const int mj = (k8 >> 1) * 2 + par, bx = k8 & 1;
-        if (MODE != 0) {
-            const uint8_t *base = WS.tile[it & 1] + (by * 8) * K1_HB + (mj * 2 + bx) * 24;
-            uint4 *cdst = reinterpret_cast<uint4 *>(WS.csum) + mj * 16;
-#pragma unroll
-            for (int rp = 0; rp < 4; ++rp) {
-                float y0[8], y1[8];
-                uint32_t h0[4], h1[4];
-                { const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2) * K1_HB); const uint2 a = p[0], b = p[1], c = p[2];
-                  const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y}; ycc_row8(wds, y0, h0); }
-                { const uint2 *p = reinterpret_cast<const uint2 *>(base + (rp * 2 + 1) * K1_HB); const uint2 a = p[0], b = p[1], c = p[2];
-                  const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y}; ycc_row8(wds, y1, h1); }
-#pragma unroll
-                for (int x = 0; x < 8; ++x) R[rp][x] = sub2(pk(y0[x], y1[x]), K2(8388736.0f));
-                cdst[((by * 4 + rp) * 2 + bx) ^ (mj & 7)] = make_uint4(h0[0] + h1[0], h0[1] + h1[1], h0[2] + h1[2], h0[3] + h1[3]);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int x = 0; x < 8; ++x) R[i][x] = pk((float)((it + i * 8 + x + lane) & 255) - 128.0f, (float)((it * 3 + x + lane) & 255) - 128.0f);
+    for (int c = 0; c < 2; ++c) {
+        const float *d = c ? chr_q : lum_q;
+        const float sc = c ? chr_scale : 1.0f;
+        for (int w = 0; w < 32; ++w) {
+            volatile float r0 = 1.0f / d[2 * w], r1 = 1.0f / d[2 * w + 1];  // RN(1/d), kept out of x87/fast-math paths
+            QPair e;
+            e.nd_lo = -(d[2 * w] * sc);
+            e.nd_hi = -(d[2 * w + 1] * sc);
+            e.r_lo = r0 / sc;
+            e.r_hi = r1 / sc;
+            qp->t[c][w] = e;
         }
-        if (MODE != 1) {
-            const int slot = mj * 4 + by * 2 + bx;
-            dct_quant_store_x2<false>(R, S.q.lum, reinterpret_cast<uint4 *>(WS.csum) + 256 * 0 + slot * 8, ((slot >> 3) << 1) | (slot & 1), zero2);
-            __syncwarp();
-            acc += WS.csum[(lane * 33 + it) & 1023];
-        } else {
-            uint32_t lo, hi; upk_u(R[it & 3][lane & 7], lo, hi); acc += lo ^ hi;
-        }
-    }
-    if (acc == 0x12345678u) sink[tid] = acc;
-}
-#endif
-
-void make_quant_tab(const float *lum_q, const float *chr_q, QuantTab *qt)
-{
-    for (int i = 0; i < 64; ++i) {
-        qt->lum_d[i] = lum_q[i];
-        qt->chr_d[i] = chr_q[i];
-        volatile float rl = 1.0f / lum_q[i];
-        volatile float rc = 1.0f / chr_q[i];
-        qt->lum_r[i] = rl;
-        qt->chr_r[i] = rc;
     }
 }
 
@@ -1119,7 +1044,7 @@ bool make_rgb_tensor_map(CUtensorMap *tm, const uint8_t *pixels, size_t pixel_st
 
 int launch_k1(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint32_t n, uint32_t w,
               uint32_t h, int16_t *y, size_t y_stride, int16_t *cb, int16_t *cr, size_t c_stride,
-              const QuantTab &qt, bool zigzag)
+              const QPairTab &qt, bool zigzag)
 {
     K1Params P;
     P.pixels = px; P.pixel_stride = pixel_stride; P.w = w; P.h = h;
@@ -1151,7 +1076,7 @@ int launch_k1(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint32
 
 int launch_k444(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint32_t n, uint32_t w,
                 uint32_t h, int16_t *y, size_t y_stride, int16_t *cb, int16_t *cr, size_t c_stride,
-                const QuantTab &qt, bool zigzag)
+                const QPairTab &qt, bool zigzag)
 {
     K1Params P;
     P.pixels = px; P.pixel_stride = pixel_stride; P.w = w; P.h = h;
@@ -1186,37 +1111,14 @@ int launch_k444(pixo_b200_ctx *ctx, const uint8_t *px, size_t pixel_stride, uint
 
 }  // namespace
 
-#ifdef PIXO_UBENCH
-extern "C" int pixo_b200_ubench(pixo_b200_ctx *ctx, int mode, int iters, float *ms_out)
-{
-    const size_t smem = sizeof(K1Smem);
-    uint32_t *sink = nullptr;
-    cudaMalloc(&sink, 4096);
-    auto run = [&](int it) {
-        const int grid = ctx->sm_count * K1_MIN_BLOCKS;
-        if (mode == 0) { cudaFuncSetAttribute(k_ubench<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_ubench<0><<<grid, K1_THREADS, smem, ctx->stream>>>(it, 0.f, 0.f, sink); }
-        if (mode == 1) { cudaFuncSetAttribute(k_ubench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_ubench<1><<<grid, K1_THREADS, smem, ctx->stream>>>(it, 0.f, 0.f, sink); }
-        if (mode == 2) { cudaFuncSetAttribute(k_ubench<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_ubench<2><<<grid, K1_THREADS, smem, ctx->stream>>>(it, 0.f, 0.f, sink); }
-    };
-    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    run(iters);
-    cudaStreamSynchronize(ctx->stream);
-    cudaEventRecord(e0, ctx->stream); run(iters); cudaEventRecord(e1, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
-    cudaEventElapsedTime(ms_out, e0, e1);
-    cudaFree(sink);
-    return (int)cudaGetLastError();
-}
-#endif
-
 int launch_jpeg_transform(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pixel_stride,
                           uint32_t n_images, uint32_t w, uint32_t h, uint32_t color_type,
                           uint32_t subsampling, const float *lum_q, const float *chr_q,
                           int16_t *d_y, size_t y_stride, int16_t *d_cb, int16_t *d_cr,
                           size_t c_stride, uint32_t flags)
 {
-    QuantTab qt;
-    make_quant_tab(lum_q, chr_q, &qt);
+    QPairTab qt;
+    fill_qpair_tab(lum_q, chr_q, (color_type != PIXO_B200_GRAY && subsampling == PIXO_B200_S420) ? 4.0f : 1.0f, &qt);
     const bool zigzag = (flags & PIXO_B200_COEF_ZIGZAG) != 0;
     // the exact-division identity is proved for integer divisors 1..255 only
     for (int i = 0; i < 64; ++i) {
@@ -1254,8 +1156,9 @@ int launch_jpeg_transform(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pi
 int launch_jpeg_histogram(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
                           const int16_t *d_cb, const int16_t *d_cr, size_t c_stride,
                           uint32_t n_images, size_t ny, size_t nc, uint32_t blocks_y_per_mcu,
-                          uint32_t restart_interval, bool zigzag_in, uint64_t *d_hist)
+                          uint32_t restart_interval, bool zigzag_in, uint64_t *d_hist, const int *dc_seed)
 {
+    const int s0 = dc_seed ? dc_seed[0] : 0, s1 = dc_seed ? dc_seed[1] : 0, s2 = dc_seed ? dc_seed[2] : 0;
     PIXO_CUDA(ctx, cudaMemsetAsync(d_hist, 0, (size_t)n_images * kHistWords * sizeof(uint64_t),
                                    ctx->stream));
     const size_t total = ny + 2 * nc;
@@ -1271,9 +1174,9 @@ int launch_jpeg_histogram(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_strid
         const int16_t *cb = d_cb ? d_cb + (size_t)i0 * c_stride : nullptr;
         const int16_t *cr = d_cr ? d_cr + (size_t)i0 * c_stride : nullptr;
         if (zigzag_in)
-            k_jpeg_hist<true><<<grid, 256, 0, ctx->stream>>>(y, y_stride, cb, cr, c_stride, ny, nc, blocks_y_per_mcu, restart_interval, hist);
+            k_jpeg_hist<true><<<grid, 256, 0, ctx->stream>>>(y, y_stride, cb, cr, c_stride, ny, nc, blocks_y_per_mcu, restart_interval, hist, s0, s1, s2);
         else
-            k_jpeg_hist<false><<<grid, 256, 0, ctx->stream>>>(y, y_stride, cb, cr, c_stride, ny, nc, blocks_y_per_mcu, restart_interval, hist);
+            k_jpeg_hist<false><<<grid, 256, 0, ctx->stream>>>(y, y_stride, cb, cr, c_stride, ny, nc, blocks_y_per_mcu, restart_interval, hist, s0, s1, s2);
         ctx->launches++;
         PIXO_CUDA(ctx, cudaGetLastError());
     }

@@ -125,6 +125,7 @@ struct PngParams {
     uint32_t *counter;     // per-image CTA completion counter
     uint32_t *adler_out;   // per-image checksum
     uint32_t rows_total_for_adler; // rows contributing before finalisation
+    const uint8_t *above;  // raw row above row 0 (a row band of a taller image), or null = zeros
 };
 
 // smem layout (dynamic): cur[16 + SEGP] prev[16 + SEGP] sbuf[SEGP + 32]
@@ -145,8 +146,9 @@ __global__ void __launch_bounds__(PNG_THREADS) k_png_filter(const PngParams P)
 
     const uint8_t *image = P.data + (size_t)img * P.in_stride;
     const uint8_t *row = image + (size_t)y * rb;
-    const uint8_t *prow = y ? row - rb : nullptr;
+    const uint8_t *prow = y ? row - rb : P.above;
     const uint8_t *lo_b = image, *hi_b = image + (size_t)P.height * rb;
+    const uint8_t *plo_b = y ? lo_b : P.above, *phi_b = y ? hi_b : P.above + rb;   // bounds of the row above
     const uint32_t bpp = P.bpp;
     const uint32_t ashift = (4 - bpp) * 8;
     const int nseg = (int)((rb + segcap - 1) / segcap);
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(PNG_THREADS) k_png_filter(const PngParams P)
                         prev[tid] = (gi >= 0 && prow) ? prow[gi] : 0;
                     }
                     stage_bytes(cur + 16, row + s0, slen, lo_b, hi_b, tid);
-                    if (prow) stage_bytes(prev + 16, prow + s0, slen, lo_b, hi_b, tid);
+                    if (prow) stage_bytes(prev + 16, prow + s0, slen, plo_b, phi_b, tid);
                     else for (int i = tid; i < slen; i += PNG_THREADS) prev[16 + i] = 0;
                     // zero the tail of the last word (defined data for the word-wise passes)
                     for (int i = slen + tid; i < ((slen + 3) & ~3); i += PNG_THREADS) { cur[16 + i] = 0; prev[16 + i] = 0; }
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(PNG_THREADS) k_png_filter(const PngParams P)
                     prev[tid] = (gi >= 0 && prow) ? prow[gi] : 0;
                 }
                 stage_bytes(cur + 16, row + s0, slen, lo_b, hi_b, tid);
-                if (prow) stage_bytes(prev + 16, prow + s0, slen, lo_b, hi_b, tid);
+                if (prow) stage_bytes(prev + 16, prow + s0, slen, plo_b, phi_b, tid);
                 else for (int i = tid; i < slen; i += PNG_THREADS) prev[16 + i] = 0;
                 // zero the tail of the last word so masked lanes read defined data
                 for (int i = slen + tid; i < ((slen + 3) & ~3); i += PNG_THREADS) { cur[16 + i] = 0; prev[16 + i] = 0; }
@@ -464,6 +466,7 @@ struct BandParams {
     uint32_t *adler_out;
     uint32_t nbands;
     uint32_t async16;          // rows are 16-byte aligned: cp.async path
+    const uint8_t *above;      // raw row above row 0 (a row band of a taller image), or null = zeros
 };
 
 
@@ -515,6 +518,10 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
     if (r0 == 0) {
         for (uint32_t i = tid; i < (pitch - 16) / 4; i += PNG_THREADS)
             reinterpret_cast<uint32_t *>(bufs[(r0 + 2) % 3] + 16)[i] = 0;
+        if (P.above) {
+            __syncthreads();
+            stage_bytes(bufs[(r0 + 2) % 3] + 16, P.above, (int)rb, P.above, P.above + rb, tid);
+        }
     } else {
         load_row(r0 - 1, bufs[(r0 + 2) % 3], false);
     }
@@ -753,22 +760,42 @@ k_adler32(const uint8_t *__restrict__ data, size_t len, unsigned long long *acc,
 
 }  // namespace
 
+int launch_png_filter_rows(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_stride,
+                           uint32_t n_images, uint32_t width, uint32_t height, size_t row_bytes,
+                           uint32_t bpp, uint32_t strategy, uint8_t *d_out, size_t out_stride,
+                           uint32_t *d_adler, const uint8_t *d_above, uint32_t rule_height);
+
 int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_stride,
                       uint32_t n_images, uint32_t width, uint32_t height, size_t row_bytes,
                       uint32_t bpp, uint32_t strategy, uint8_t *d_out, size_t out_stride,
                       uint32_t *d_adler)
 {
+    return launch_png_filter_rows(ctx, d_data, in_stride, n_images, width, height, row_bytes, bpp, strategy, d_out,
+                                  out_stride, d_adler, nullptr, height);
+}
+
+// `height` rows starting at d_data; d_above (single image only): the raw row above them when they
+// are a band of an image of `rule_height` rows (the strategy pre-rules look at the whole image).
+int launch_png_filter_rows(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_stride,
+                           uint32_t n_images, uint32_t width, uint32_t height, size_t row_bytes,
+                           uint32_t bpp, uint32_t strategy, uint8_t *d_out, size_t out_stride,
+                           uint32_t *d_adler, const uint8_t *d_above, uint32_t rule_height)
+{
     if (row_bytes >= (1ull << 32) - 16)
         return set_error(ctx, PIXO_B200_ERR_IMAGE_TOO_LARGE, "row_bytes too large");
+    if (d_above && n_images != 1)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "a row above is given for a single image only");
     // apply_filters_with_row_bytes pre-rules, src/png/filter.rs:72-86
-    const size_t area = (size_t)width * (size_t)height;
+    const size_t area = (size_t)width * (size_t)rule_height;
     uint32_t strat = strategy & 0xFFu;
     const uint32_t oa = ((strategy & PIXO_B200_PNG_OPTIMIZE_ALPHA) && (bpp == 2 || bpp == 4)) ? bpp : 0u;
     if (area <= 4096 && (strat == PIXO_B200_FILTER_ADAPTIVE || strat == PIXO_B200_FILTER_ADAPTIVE_FAST ||
                          strat == PIXO_B200_FILTER_BIGRAMS))
         strat = PIXO_B200_FILTER_SUB;
     // default-feature build: AdaptiveFast takes the sequential (sticky) loop when height <= 32
-    const bool sticky = strat == PIXO_B200_FILTER_ADAPTIVE_FAST && height <= 32;
+    const bool sticky = strat == PIXO_B200_FILTER_ADAPTIVE_FAST && rule_height <= 32;
+    if (sticky && rule_height != height)
+        return set_error(ctx, PIXO_B200_ERR_UNSUPPORTED, "row bands of an image of 32 rows or fewer (sticky AdaptiveFast)");
 
     const size_t band_pitch = 16 + ((row_bytes + 15) & ~(size_t)15) + 16;
     const size_t band_smem = 3 * band_pitch;
@@ -810,6 +837,7 @@ int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_strid
             B.counter = counter + i0;
             B.adler_out = d_adler ? d_adler + i0 : nullptr;
             B.nbands = nbands;
+            B.above = d_above;
             B.async16 = (row_bytes % 16 == 0 && in_stride % 16 == 0 &&
                          (reinterpret_cast<uintptr_t>(d_data) & 15) == 0) ? 1u : 0u;
             if (oa == 4) k_png_band<4><<<dim3(nbands, nb), PNG_THREADS, band_smem, ctx->stream>>>(B);
@@ -836,6 +864,7 @@ int launch_png_filter(pixo_b200_ctx *ctx, const uint8_t *d_data, size_t in_strid
         P.counter = counter + i0;
         P.adler_out = d_adler ? d_adler + i0 : nullptr;
         P.rows_total_for_adler = height;
+        P.above = d_above;
         if (sticky) {
             // row 0 decides (adaptive_filter_fast), every later row reuses that filter
             P.row0 = 0; P.forced = nullptr; P.decided = decided + i0;

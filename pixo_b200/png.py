@@ -82,3 +82,20 @@ def adler32(data, ctx: Context | None = None) -> int:
     _lib.check(ctx.handle, _lib.load().pixo_b200_adler32(ctx.handle, d.ctypes.data if d.size else None,
                                                          d.size, C.byref(out)))
     return out.value
+
+
+def apply_filters_rows_dev(d_rows, d_row_above, width, image_height, band_rows, row_bytes, bytes_per_pixel,
+                           strategy: FilterStrategy, d_out, d_adler=None, optimize_alpha=False,
+                           ctx: Context | None = None):
+    """A band of rows of one image on the device (anything with .data_ptr()): see
+    pixo_b200_png_filter_rows_dev.  Asynchronous on the context's stream."""
+    ctx = ctx or default_context()
+    p = lambda t: None if t is None else int(t.data_ptr())
+    _lib.check(ctx.handle, _lib.load().pixo_b200_png_filter_rows_dev(
+        ctx.handle, p(d_rows), p(d_row_above), int(width), int(image_height), int(band_rows), int(row_bytes),
+        int(bytes_per_pixel), int(strategy) | (OPTIMIZE_ALPHA if optimize_alpha else 0), p(d_out), p(d_adler)))
+
+
+def adler32_combine(adler_a: int, adler_b: int, len_b: int) -> int:
+    """Adler-32 of A ++ B from the two checksums and len(B)."""
+    return int(_lib.load().pixo_b200_adler32_combine(int(adler_a), int(adler_b), int(len_b)))
