@@ -409,24 +409,30 @@ def c4_config(env: Env, steps: int) -> dict:
     env.torch.cuda.synchronize()
     out = {}
 
+    coders = [parallel.DeviceBandCoder(env.ctx, dy, dcb, dcr, w, b.px_row1 - b.px_row0, 2, 1, b.y_blocks, b.c_blocks)
+              for b, (dy, dcb, dcr) in zip(my_bands, coefs)]
+
     def tiled_once():
-        coders = []
+        # transform of every band this rank owns, then the distributed entropy stage; the timed region
+        # ends with the finished scan bytes on rank 0's device (like `value`, which leaves them in HBM)
         for b, px, (dy, dcb, dcr) in zip(my_bands, d_band_px, coefs):
             bh = b.px_row1 - b.px_row0
             env.check(lib.pixo_b200_jpeg_coefficients_dev(env.ctx.handle, px.data_ptr(), px.numel(), 1, w, bh, 2, 1, lqp, cqp,
                                                           dy.data_ptr(), b.y_blocks * 64, dcb.data_ptr(), dcr.data_ptr(),
                                                           b.c_blocks * 64, 0, None))
-            coders.append(parallel.DeviceBandCoder(env.ctx, dy, dcb, dcr, w, bh, 2, 1, b.y_blocks, b.c_blocks))
         if env.world == 1:
-            out["jpg"] = parallel.encode_tiled_local(coders, w, h, 2, q, 1, False)
+            out["parts"], out["hist"] = parallel.tiled_scan_parts_local(coders, False)
         else:
-            out["jpg"] = parallel.encode_tiled(coders[0], w, h, 2, q, 1, False, env.rank, env.world)
+            out["parts"], out["hist"] = parallel.tiled_scan_parts(coders[0], False, env.rank, env.world)
 
-    ms_tiled = env.timed(tiled_once, max(2, steps // 4), warm=1)
+    ms_tiled = env.timed(tiled_once, max(2, steps // 2), warm=2)
+    if env.rank == 0:
+        out["jpg"] = parallel.assemble_tiled(out["parts"], out["hist"], w, h, 2, q, 1)
     res = {"geometry": "16384x16384", "quality": q, "bands": nbands,
            "tiled": {"mpix_s": w * h / (ms_tiled * 1e-3) / 1e6, "ms": ms_tiled,
                      "what": ("band r on rank r: transform + k_huff<RAW> + splice per GPU; all-gather of DC predictors and of "
-                              "(bits, tail), gather of scan bytes to rank 0 over NCCL" if env.world > 1 else
+                              "(bits, tail), gather of scan bytes to rank 0 over NCCL; timed until the scan bytes are on rank "
+                              "0's device" if env.world > 1 else
                               "8 bands, every stage of the distributed path, run one after the other in ONE context"),
                      "nccl_ranks": env.world}}
     tiled_sha = sha(out["jpg"]) if env.rank == 0 else None

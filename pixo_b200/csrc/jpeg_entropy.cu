@@ -47,9 +47,14 @@ __host__ __device__ constexpr int zz_nat(int i)
 //   entry = (code << (32 - len)) | (len + cat),   cat = symbol & 15 (AC) or the DC category
 // i.e. the code left-aligned in the upper half-word and the total field width (code + amplitude
 // bits) in the low five bits.
+// AC entries sit at word  run * 12 + (cat - 1)  (cat 1..10): the 32 entries a warp asks for most
+// (run < 8, cat <= 4) fall into 32 different shared-memory banks, so the per-symbol lookup is
+// conflict-free for typical blocks (the plain run * 16 + cat layout put runs 0/2/4/6 on the same
+// banks: 8.8 M excess wavefronts per 32 4K frames, profiles/r01).  ZRL and EOB follow the grid.
+constexpr int AC_STRIDE = 12, AC_ZRL = 190, AC_EOB = 191, AC_WORDS = 192;
 struct HuffDev {
     uint32_t dc[2][12];
-    uint32_t ac[2][256];
+    uint32_t ac[2][AC_WORDS];
 };
 
 struct EntParams {
@@ -203,7 +208,9 @@ __device__ __forceinline__ uint32_t msb_index(uint32_t v)  // FLO: 31 - clz, v !
 //   !SPILL: later words are dropped (the caller sees the length and runs the SPILL variant).
 // Pending bits are kept left-aligned in `acc`; a symbol arrives left-aligned too (vl, n bits).
 // Returns the block's length in bits; *acc_out = the last, partial word (left-aligned).
-template <bool SPILL>
+// ZRLS == false is the variant for warps none of whose blocks holds a zero run of 16 or more (the
+// caller checks the masks): the symbol loop then carries no ZRL test and no reconvergence point.
+template <bool SPILL, bool ZRLS>
 __device__ __forceinline__ uint32_t code_block(uint32_t M0, uint32_t M1, int diff, const uint32_t *dctab,
                                                uint32_t sa_ac, uint32_t sa_stage, uint32_t sa_slot,
                                                uint32_t *spill, uint32_t *acc_out)
@@ -253,18 +260,20 @@ __device__ __forceinline__ uint32_t code_block(uint32_t M0, uint32_t M1, int dif
         const uint32_t n = e & 31u;
         put((e & 0xFFFF0000u) | (n ? amp << (32u - n) : 0u), n);
     }
-    const uint32_t zrl = lds_u32(sa_ac + 0xF0 * 4), eob = lds_u32(sa_ac);
+    const uint32_t zrl = lds_u32(sa_ac + AC_ZRL * 4), eob = lds_u32(sa_ac + AC_EOB * 4);
     uint32_t nprev = ~0u;  // -(previous position) - 1
-    uint32_t kOne, kNeg2;  // opaque to the compiler, so they stay in registers across the loop
-    asm volatile("mov.b32 %0, 1;" : "=r"(kOne));
-    asm volatile("mov.b32 %0, -2;" : "=r"(kNeg2));
+    // (no constants live across the loop: at 80 registers ptxas re-materialises them every
+    // iteration - the single-bit mask comes from BMSK, the amplitude mask from a shifted sign)
+    const uint32_t sa_ac_top = sa_ac + 31u * 4u;   // entry of (run, cat) = sa_ac_top + run*48 - clz(|c|)*4
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         uint32_t mb = __brev(half ? M1 : (M0 & ~1u));  // scan order == descending bit index
         const uint32_t top = half * 32 + 31;
         while (mb) {
             const uint32_t f = msb_index(mb);
-            mb &= ~(kOne << f);
+            uint32_t bit;
+            asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(bit) : "r"(f));   // 1 << f
+            mb ^= bit;
             const uint32_t pos = top - f;
             uint32_t run = pos + nprev;
             nprev = ~pos;
@@ -274,14 +283,16 @@ __device__ __forceinline__ uint32_t code_block(uint32_t M0, uint32_t M1, int dif
             asm("{\n\t.reg .b32 h, x;\n\tand.b32 h, %1, 1;\n\tmad.lo.u32 x, %1, 64, %2;\n\tmad.lo.u32 %0, h, -62, x;\n\t}"
                 : "=r"(caddr) : "r"(pos), "r"(sa_stage));
             const int c = lds_s16(caddr);
+            if (ZRLS) {
 #pragma unroll 1
-            while (run >= 16u) { put(zrl & 0xFFFF0000u, zrl & 31u); run -= 16u; }  // rare: keep it small
+                while (run >= 16u) { put(zrl & 0xFFFF0000u, zrl & 31u); run -= 16u; }  // rare: keep it small
+            }
             const uint32_t a = (uint32_t)abs(c);
-            const uint32_t fl = msb_index(a);  // cat - 1
-            const uint32_t e = lds_u32(sa_ac + 4u + run * 64u + fl * 4u);
-            const uint32_t amp = a ^ (~(kNeg2 << fl) & (uint32_t)(c >> 31));
+            const uint32_t lz = (uint32_t)__clz((int)a);   // 32 - cat
+            const uint32_t e = lds_u32(sa_ac_top + run * (AC_STRIDE * 4u) - lz * 4u);
+            const uint32_t amp = a ^ ((uint32_t)(c >> 31) >> lz);     // c >= 0: c; c < 0: (c - 1) masked to cat bits
             const uint32_t n = e & 31u;
-            put((e & 0xFFFF0000u) | (amp << (32u - n)), n);
+            put((e & 0xFFFF0000u) | __funnelshift_r(0u, amp, n), n);   // amp << (32 - n), 2 <= n <= 26
         }
     }
     if (nprev != ~63u) put(eob & 0xFFFF0000u, eob & 31u);
@@ -398,12 +409,14 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         uint32_t *const slot = M.slot[buf];
         uint32_t L = 0, tail7 = 0;
         int nwt = 0;
+        uint32_t M0 = 0, M1 = 0;
+        int diff = 0, tbl = 0;
+        bool zrl_here = false;
         if (s < iend) {
             const uint32_t m = s / P.bpm;
             const uint32_t k = s - m * P.bpm;
             const int16_t *arr;
             size_t idx;
-            int tbl;
             int seed;
             if (k < P.y_per_mcu) { arr = P.y + (size_t)C.img * P.y_stride; idx = (size_t)m * P.y_per_mcu + k; tbl = 0; seed = P.dc_seed[0]; }
             else if (k == P.y_per_mcu) { arr = P.cb + (size_t)C.img * P.c_stride; idx = m; tbl = 1; seed = P.dc_seed[1]; }
@@ -440,14 +453,24 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
                 }
             }
             asm volatile("" ::: "memory");  // the stage is read back through ld.shared below
-            const uint32_t M0 = interleave16(e0), M1 = interleave16(e1);  // bit i = coefficient i != 0
-            const int diff = (int)(int16_t)(dc - prev_dc);
+            M0 = interleave16(e0); M1 = interleave16(e1);  // bit i = coefficient i != 0
+            diff = (int)(int16_t)(dc - prev_dc);
+            // does a non-zero coefficient follow 16 or more zeros (a ZRL symbol)?  position 0 (DC)
+            // bounds the first run; a8 bit i = positions i..i+15 all zero
+            const unsigned long long N = ((unsigned long long)M1 << 32) | M0 | 1ull;
+            unsigned long long a = ~N & (~N >> 1);
+            a &= a >> 2; a &= a >> 4; a &= a >> 8;
+            zrl_here = ((a << 16) & N) != 0;
+        }
+        const bool any_zrl = __any_sync(0xffffffffu, zrl_here);   // uniform: which symbol loop the warp runs
+        if (s < iend) {
             const uint32_t sa_ac = (uint32_t)__cvta_generic_to_shared(&T.ac[tbl][0]);
             const uint32_t sa_slot = (uint32_t)__cvta_generic_to_shared(slot) + 4u * lane;
             uint32_t acc;
-            L = code_block<false>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill[buf], &acc);
+            if (any_zrl) L = code_block<false, true>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill[buf], &acc);
+            else L = code_block<false, false>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill[buf], &acc);
             if (L > SLOT_W * 32u)  // long block: run again, keeping the words past the slot in local memory
-                L = code_block<true>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill[buf], &acc);
+                L = code_block<true, true>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill[buf], &acc);
             asm volatile("" ::: "memory");  // slot words were written through st.shared
             const int nw = (int)(L >> 5), filled = (int)(L & 31u);
             nwt = nw;
@@ -499,19 +522,40 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         // range land outside the part of sbuf that is copied out); sbuf index 16 + shb is
         // the chunk's first owned byte of this window.
         if (32 * lane < b) {
+            // The lane's 32 bytes go to sbuf at an arbitrary byte offset.  Words without a 0xFF are
+            // written as whole, ALIGNED words: up to 3 head bytes, then each word merged with the
+            // unwritten tail of its predecessor by one funnel shift (pend = the last `np` bytes not
+            // yet stored, kept in the top of `prev`); a word holding 0xFF first drains the pending
+            // bytes and is expanded byte by byte (0xFF -> 0xFF 0x00).  7 word + ~4 byte stores per
+            // lane instead of 32 byte stores (which were 25 % of the kernel's shared-memory wavefronts).
             uint32_t dst = 16u + shb + (uint32_t)(32 * lane) - (uint32_t)a + ffb;
+            uint32_t prev = 0, np = 0;   // prev: previous little-endian word; its top np bytes are pending at dst
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const uint32_t w = wv[j];
                 if (ff_bytes(w) == 0) {
-                    if ((dst & 3u) == 0) {
-                        *reinterpret_cast<uint32_t *>(sbuf + dst) = __byte_perm(w, 0, 0x0123);
-                    } else {
-                        sbuf[dst] = (uint8_t)(w >> 24); sbuf[dst + 1] = (uint8_t)(w >> 16);
-                        sbuf[dst + 2] = (uint8_t)(w >> 8); sbuf[dst + 3] = (uint8_t)w;
+                    const uint32_t m = __byte_perm(w, 0, 0x0123);   // memory order
+                    if (np == 0) {
+                        const uint32_t al = dst & 3u;
+                        if (al == 0) {
+                            *reinterpret_cast<uint32_t *>(sbuf + dst) = m;
+                            dst += 4;
+                        } else {             // head: 4 - al bytes singly, the other al bytes wait in prev
+                            sbuf[dst] = (uint8_t)m;
+                            if (al < 3) sbuf[dst + 1] = (uint8_t)(m >> 8);
+                            if (al < 2) sbuf[dst + 2] = (uint8_t)(m >> 16);
+                            dst += 4u - al;
+                            np = al;
+                            prev = m;
+                        }
+                    } else {                 // dst is aligned: np pending bytes + 4 - np new ones
+                        *reinterpret_cast<uint32_t *>(sbuf + dst) = __funnelshift_r(prev, m, 32u - 8u * np);
+                        dst += 4;
+                        prev = m;
                     }
-                    dst += 4;
                 } else {
+                    for (uint32_t i = 0; i < np; ++i) sbuf[dst++] = (uint8_t)(prev >> (8u * (4u - np + i)));
+                    np = 0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t byte = (w >> (24 - 8 * i)) & 0xFFu;
@@ -520,6 +564,7 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
                     }
                 }
             }
+            for (uint32_t i = 0; i < np; ++i) sbuf[dst + i] = (uint8_t)(prev >> (8u * (4u - np + i)));
         }
         __syncwarp();
         if (mk) {  // 0xFF 0xDn, not subject to stuffing; after the barrier: the last lane's spare bytes land here too
@@ -821,9 +866,12 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
             if (t.len[k][cat])
                 T.dc[k][cat] = ((uint32_t)t.code[k][cat] << (32 - t.len[k][cat])) | (uint32_t)(t.len[k][cat] + cat);
         for (int rs = 0; rs < 256; ++rs) {
-            const int cat = rs & 15;
-            if (t.len[2 + k][rs] && cat <= 10)
-                T.ac[k][rs] = ((uint32_t)t.code[2 + k][rs] << (32 - t.len[2 + k][rs])) | (uint32_t)(t.len[2 + k][rs] + cat);
+            const int cat = rs & 15, run = rs >> 4;
+            if (!t.len[2 + k][rs] || cat > 10) continue;
+            const uint32_t e = ((uint32_t)t.code[2 + k][rs] << (32 - t.len[2 + k][rs])) | (uint32_t)(t.len[2 + k][rs] + cat);
+            if (rs == 0x00) T.ac[k][AC_EOB] = e;
+            else if (rs == 0xF0) T.ac[k][AC_ZRL] = e;
+            else if (cat >= 1) T.ac[k][run * AC_STRIDE + cat - 1] = e;
         }
     }
     cudaStream_t st = ctx->stream;

@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <string.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -307,15 +308,31 @@ struct QPairTab {
 // `out` is the block's 128-byte slot in a warp-private shared-memory stage; its eight 16-byte
 // chunks are written at chunk index (k ^ swz) so that the lanes of a quarter warp hit distinct
 // banks (the caller then copies the stage out with fully coalesced 512-byte warp stores).
-template <bool ZIGZAG, int TSEL>
-__device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPairTab &qp,
-                                                   uint4 *__restrict__ out, const int swz,
-                                                   const f2 zero2)
+//
+// Where the quantiser's table lives is a build-time choice (K_QMODE), A/B-timed on the B200:
+//   0  shared memory, one copy of the transform (round 1): 32 LDS.128 per block, each followed by
+//      a dependent FMUL2 because the register budget leaves no room to fetch ahead
+//   1  constant bank with STATIC offsets -> ptxas fetches the entries with LDCU into uniform
+//      registers and the packed ops take them as UR operands (no LDS, no vector registers, no
+//      short-scoreboard wait) - but static offsets mean one copy of the transform PER TABLE, and
+//      two copies (2 x 12 KB next to the 9 KB colour fill) overflow the 32 KB instruction-cache
+//      level: no-instruction stalls rise from 0.06 to 0.41 per issue
+//   2  as 1, but only the column pass + quantiser exists per table; the row pass (which reads no
+//      table) is shared
+// (A warp-uniform run-time index into the constant bank is no alternative: ptxas then emits
+// per-thread LDC.64 c[0x0][R+imm] into vector registers, even when the index comes from a vote.)
+#ifndef K_QMODE
+#define K_QMODE 2
+#endif
+struct QuantSmem {
+    QPair t[2][32];
+};
+
+// row pass on row pairs; the post-scale is done lane by lane so the results land in the
+// column-pair layout C[r][j] = (V[r][2j], V[r][2j+1]) without transposes
+__device__ __forceinline__ void dct_rows_x2(f2 (&R)[4][8], f2 (&C)[8][4], const f2 zero2)
 {
     constexpr float SK[8] = {AAN_S0, AAN_S1, AAN_S2, AAN_S3, AAN_S4, AAN_S5, AAN_S6, AAN_S7};
-    // row pass on row pairs; the post-scale is done lane by lane so the results land in the
-    // column-pair layout C[r][j] = (V[r][2j], V[r][2j+1]) without transposes
-    f2 C[8][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         f2 o[8];
@@ -329,10 +346,15 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPairTab
             C[2 * i + 1][j] = pk(a1, b1);
         }
     }
-    // column pass on column pairs, quantising each pair of columns as soon as it is transformed.
-    // The eight table entries of a column pair are fetched BEFORE its butterflies so the
-    // shared-memory latency is covered by the transform (ncu: the quantiser was where the warp
-    // waited on short-scoreboard stalls).
+}
+
+// column pass on column pairs, quantising each pair of columns as soon as it is transformed;
+// tab(i) returns table entry i (one per output word)
+template <bool ZIGZAG, typename TabFn>
+__device__ __forceinline__ void dct_cols_quant_store_x2(f2 (&C)[8][4], TabFn tab, uint4 *__restrict__ out,
+                                                        const int swz, const f2 zero2)
+{
+    constexpr float SK[8] = {AAN_S0, AAN_S1, AAN_S2, AAN_S3, AAN_S4, AAN_S5, AAN_S6, AAN_S7};
     uint32_t W[32];
     const f2 half2 = K2(0.5f), magic2 = K2(12582912.0f);  // 1.5 * 2^23
     uint32_t kSign, kOne;  // in registers so copysign(1.0, q) is ONE lop3: (q & sign) | one
@@ -342,7 +364,7 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPairTab
     for (int j = 0; j < 4; ++j) {
         QPair T[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) T[r] = qp.t[TSEL][r * 4 + j];
+        for (int r = 0; r < 8; ++r) T[r] = tab(r * 4 + j);
         const f2 in[8] = {C[0][j], C[1][j], C[2][j], C[3][j], C[4][j], C[5][j], C[6][j], C[7][j]};
         f2 o[8];
         aan_1d_x2_core(in, o, zero2);
@@ -382,6 +404,36 @@ __device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPairTab
         }
         out[k ^ swz] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+}
+
+// chroma_u MUST be warp-uniform (the callers derive it from a warp vote, so the branch is one).
+template <bool ZIGZAG>
+__device__ __forceinline__ void dct_quant_store_x2(f2 (&R)[4][8], const QPairTab &qp, const QuantSmem *qs,
+                                                   const bool chroma_u, uint4 *__restrict__ out, const int swz,
+                                                   const f2 zero2)
+{
+#if K_QMODE == 0
+    f2 C[8][4];
+    dct_rows_x2(R, C, zero2);
+    const QPair *t = qs->t[chroma_u ? 1 : 0];
+    dct_cols_quant_store_x2<ZIGZAG>(C, [&](int i) { return t[i]; }, out, swz, zero2);
+#elif K_QMODE == 1
+    if (chroma_u) {
+        f2 C[8][4];
+        dct_rows_x2(R, C, zero2);
+        dct_cols_quant_store_x2<ZIGZAG>(C, [&](int i) { return qp.t[1][i]; }, out, swz, zero2);
+    } else {
+        f2 C[8][4];
+        dct_rows_x2(R, C, zero2);
+        dct_cols_quant_store_x2<ZIGZAG>(C, [&](int i) { return qp.t[0][i]; }, out, swz, zero2);
+    }
+#else
+    f2 C[8][4];
+    dct_rows_x2(R, C, zero2);
+    if (chroma_u) dct_cols_quant_store_x2<ZIGZAG>(C, [&](int i) { return qp.t[1][i]; }, out, swz, zero2);
+    else dct_cols_quant_store_x2<ZIGZAG>(C, [&](int i) { return qp.t[0][i]; }, out, swz, zero2);
+    (void)qs;
+#endif
 }
 
 // Copy a warp's 32-slot stage (4 KB, swizzled as above) to global memory: instruction j moves
@@ -480,6 +532,9 @@ struct __align__(128) K1WarpSmem {
 
 struct __align__(128) K1Smem {
     K1WarpSmem w[K1_WARPS];
+#if K_QMODE == 0
+    QuantSmem q;
+#endif
 };
 
 // One RGB row of a Y block (8 px in six words): Y - 128 as float for each pixel and the packed
@@ -533,6 +588,12 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QPairTab 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     K1WarpSmem &WS = S.w[warp];
+#if K_QMODE == 0
+    for (int i = tid; i < 64; i += K1_THREADS) S.q.t[i >> 5][i & 31] = qp.t[i >> 5][i & 31];
+    const QuantSmem *QS = &S.q;
+#else
+    const QuantSmem *QS = nullptr;
+#endif
 
     if (lane == 0) {
         mbar_init(&WS.bar, 1);
@@ -541,70 +602,84 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QPairTab 
     __syncthreads();
 
     const f2 zero2 = pk(P.zero[0], P.zero[1]);
-    const uint64_t units_per_img = (uint64_t)P.mcus_y * P.units_x;
-    const uint64_t nunits = units_per_img * P.n_images;
-    const uint64_t stride = (uint64_t)gridDim.x * K1_WARPS;
+    // Unit coordinates (image, MCU row, unit in the row) advance by a constant stride: the step is
+    // decomposed once, so the loop carries no division (the 64-bit u / units_per_img of round 1 was
+    // 5 % of all executed instructions and two copies of a ~100-instruction routine in the hot loop).
+    const uint32_t units_per_img = P.mcus_y * P.units_x;
+    const uint64_t nunits = (uint64_t)units_per_img * P.n_images;
+    const uint32_t stride = gridDim.x * K1_WARPS;
+    const uint32_t d_ux = stride % P.units_x, d_t = stride / P.units_x;
+    const uint32_t d_my = d_t % P.mcus_y, d_img = d_t / P.mcus_y;
     uint32_t phase = 0;
 
-    auto decode = [&](uint64_t u, uint32_t &img, uint32_t &my, uint32_t &ux) {
-        img = (uint32_t)(u / units_per_img);
-        const uint32_t rem = (uint32_t)(u - (uint64_t)img * units_per_img);
-        my = rem / P.units_x;
-        ux = rem - my * P.units_x;
+    auto advance = [&](uint32_t &img, uint32_t &my, uint32_t &ux) {
+        ux += d_ux;
+        if (ux >= P.units_x) { ux -= P.units_x; ++my; }
+        my += d_my;
+        if (my >= P.mcus_y) { my -= P.mcus_y; ++img; }
+        img += d_img;
     };
     auto unit_by_tma = [&](uint32_t my) { return P.use_tma && (my * 16 + 16 <= P.h); };
-    auto issue_tma = [&](uint64_t u_) {
-        uint32_t img_, my_, ux_;   // both halves under ONE barrier phase (one arrival, 12 KB)
-        decode(u_, img_, my_, ux_);
-        if (unit_by_tma(my_)) {
+    auto issue_tma = [&](uint32_t img_, uint32_t my_, uint32_t ux_) {
+        if (unit_by_tma(my_)) {   // both halves under ONE barrier phase (one arrival, 12 KB)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&WS.bar, K1_TILE_BYTES);
             tma_load_3d(WS.tile[0], &tmap, (int)(ux_ * (2 * K1_HB / 8)), (int)(my_ * 16), (int)img_, &WS.bar);
             tma_load_3d(WS.tile[1], &tmap, (int)(ux_ * (2 * K1_HB / 8) + K1_HB / 8), (int)(my_ * 16), (int)img_, &WS.bar);
         }
     };
-    // wait for / synchronously load half `half` of the current unit
-    auto acquire_half = [&](uint32_t img_, uint32_t my_, uint32_t ux_, int half) {
-        if (unit_by_tma(my_)) {
-            mbar_wait(&WS.bar, phase);
-            phase ^= 1;
-        } else {
-            const uint8_t *image = P.pixels + (size_t)img_ * P.pixel_stride;
-            const uint32_t x0 = ux_ * (K1_MCUS * 16) + half * 128;
-            if (x0 < P.w) warp_load_tile_rgb<16, 128>(WS.tile[half], image, P.w, P.h, x0, my_ * 16, lane);
-            __syncwarp();
-        }
+    // synchronously load half `half` of the current unit (edge rows / unaligned images)
+    auto load_half = [&](uint32_t img_, uint32_t my_, uint32_t ux_, int half) {
+        const uint8_t *image = P.pixels + (size_t)img_ * P.pixel_stride;
+        const uint32_t x0 = ux_ * (K1_MCUS * 16) + half * 128;
+        if (x0 < P.w) warp_load_tile_rgb<16, 128>(WS.tile[half], image, P.w, P.h, x0, my_ * 16, lane);
+        __syncwarp();
     };
 
     uint64_t u = (uint64_t)blockIdx.x * K1_WARPS + warp;
-    if (u < nunits && lane == 0) issue_tma(u);
+    uint32_t img, my, ux;
+    {
+        const uint32_t u0 = blockIdx.x * K1_WARPS + warp;   // < stride <= 2^32
+        img = u0 / units_per_img;
+        const uint32_t rem = u0 - img * units_per_img;
+        my = rem / P.units_x;
+        ux = rem - my * P.units_x;
+    }
+    if (u < nunits && lane == 0) issue_tma(img, my, ux);
 
     for (; u < nunits; u += stride) {
-        uint32_t img, my, ux;
-        decode(u, img, my, ux);
         if (unit_by_tma(my)) {
             mbar_wait(&WS.bar, phase);
             phase ^= 1;
         } else {
-            acquire_half(img, my, ux, 0);
-            acquire_half(img, my, ux, 1);
+            load_half(img, my, ux, 0);
+            load_half(img, my, ux, 1);
         }
+        uint32_t img_n = img, my_n = my, ux_n = ux;   // the warp's next unit: prefetched below, current next time round
+        advance(img_n, my_n, ux_n);
         const uint32_t mcu0 = ux * K1_MCUS;
         const uint32_t n_mcu = min((uint32_t)K1_MCUS, P.mcus_x - mcu0);
         const size_t mcu_base = (size_t)my * P.mcus_x + mcu0;
 
 #pragma unroll 1
-        for (int job = 0; job < 2; ++job) {
-            // ---- 32 Y blocks (8 MCUs) + their packed chroma quad sums ----
+        for (int job = 0; job < 3; ++job) {
+            // a warp vote, so that ptxas knows the flag is uniform (see dct_quant_store_x2)
+            const bool chroma_u = __ballot_sync(0xffffffffu, job == 2) != 0u;
             f2 R[4][8];
-            const int by = lane >> 4, l16 = lane & 15;
-            const int par = l16 >> 3, k8 = l16 & 7;
-            const int mj = (k8 >> 1) * 2 + par;   // MCU within the job; same parity per quarter warp
-            const int mcu = job * 8 + mj;
-            const int bx = k8 & 1;
-            const uint8_t *base = WS.tile[job] + (by * 8) * K1_HB + (mj * 2 + bx) * 24;
-            uint4 *cdst = reinterpret_cast<uint4 *>(WS.csum) + mcu * 16;
-            if ((uint32_t)mcu < n_mcu) {
+            uint4 *stage;   // this warp's 32 x 128-byte output stage for the job
+            int slot, swz;
+            if (!chroma_u) {
+                // ---- 32 Y blocks (8 MCUs) + their packed chroma quad sums ----
+                const int by = lane >> 4, l16 = lane & 15;
+                const int par = l16 >> 3, k8 = l16 & 7;
+                const int mj = (k8 >> 1) * 2 + par;   // MCU within the job; same parity per quarter warp
+                const int mcu = job * 8 + mj;
+                const int bx = k8 & 1;
+                const uint8_t *base = WS.tile[job] + (by * 8) * K1_HB + (mj * 2 + bx) * 24;
+                uint4 *cdst = reinterpret_cast<uint4 *>(WS.csum) + mcu * 16;
+                // No guard for MCUs past the right edge: those lanes convert whatever bytes their tile
+                // columns hold (zero fill / stale pixels - any bytes are fine) and their stage slots and
+                // chroma sums are never flushed: one straight-line, warp-convergent path.
 #pragma unroll
                 for (int rp = 0; rp < 4; ++rp) {
                     float y0[8], y1[8];
@@ -628,68 +703,65 @@ k_jpeg_420(const __grid_constant__ K1Params P, const __grid_constant__ QPairTab 
                     cdst[logical ^ (mcu & 7)] =
                         make_uint4(h0[0] + h1[0], h0[1] + h1[1], h0[2] + h1[2], h0[3] + h1[3]);
                 }
+                __syncwarp();  // every lane is done with this half tile
+                stage = reinterpret_cast<uint4 *>(WS.tile[job]);  // the consumed half becomes the stage
+                slot = mj * 4 + by * 2 + bx;                  // = block index within the job's 32
+                swz = ((slot >> 3) << 1) | (slot & 1);        // distinct across a quarter warp
             } else {
+                if (lane == 0 && u + stride < nunits) issue_tma(img_n, my_n, ux_n);   // both half tiles were flushed
+                // ---- lanes 0-15: Cb of MCU lane, lanes 16-31: Cr of MCU lane-16 ----
+                const int comp = lane >> 4, mcu = lane & 15;
+                const uint4 *csrc = reinterpret_cast<const uint4 *>(WS.csum) + mcu * 16;
+                const uint32_t sel = comp == 0 ? 0x7610u : 0x7632u;
+                // low half = 65536 - sum(cb), high half = 65539 - sum(cr)  (see ycc_row8);
+                // block value = 4 * (sum * 0.25 - 128) = sum - 512  (src/jpeg/mod.rs:1642-1653)
+                const float bias = comp == 0 ? 8453632.0f : 8453635.0f;  // 2^23 + 65536(+3) - 512
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i) {
+                    float v0[8], v1[8];
 #pragma unroll
-                    for (int x = 0; x < 8; ++x) R[i][x] = 0ull;   // MCUs past the right edge
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int l0 = (2 * i) * 2 + hh, l1 = (2 * i + 1) * 2 + hh;
+                        const uint4 s0 = csrc[l0 ^ (mcu & 7)];
+                        const uint4 s1 = csrc[l1 ^ (mcu & 7)];
+                        const uint32_t a[4] = {s0.x, s0.y, s0.z, s0.w};
+                        const uint32_t b[4] = {s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            v0[hh * 4 + k] = __uint_as_float(__byte_perm(a[k], 0x4B000000u, sel));
+                            v1[hh * 4 + k] = __uint_as_float(__byte_perm(b[k], 0x4B000000u, sel));
+                        }
+                    }
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) R[i][x] = sub2(K2(bias), pk(v0[x], v1[x]));
+                }
+                __syncwarp();  // every lane has read its chroma sums: the buffer becomes the stage
+                stage = reinterpret_cast<uint4 *>(WS.csum);
+                slot = lane;                                  // 0-15 Cb, 16-31 Cr
+                swz = slot & 7;
             }
-            __syncwarp();  // every lane is done with this half tile
-            uint4 *stage = reinterpret_cast<uint4 *>(WS.tile[job]);  // the consumed half becomes the stage
-            const int slot = mj * 4 + by * 2 + bx;              // = block index within the job's 32
-            const int swz = ((slot >> 3) << 1) | (slot & 1);    // distinct across a quarter warp
-            // The transform runs in every lane (edge lanes work on zeros and their slots are never
+            // The transform runs in every lane (edge lanes work on garbage and their slots are never
             // flushed): the quantiser's table reads are uniform-datapath loads, which exist only in
             // warp-convergent code.
-            dct_quant_store_x2<ZIGZAG, 0>(R, qp, stage + slot * 8, swz, zero2);
-            uint4 *ybase = reinterpret_cast<uint4 *>(P.y + (size_t)img * P.y_stride + (mcu_base + job * 8) * 4 * 64);
-            const uint32_t first = job * 8;
-            flush_stage(
-                stage, lane, [](int s) { return ((s >> 3) << 1) | (s & 1); },
-                [&](int s) -> uint4 * { return first + (s >> 2) < n_mcu ? ybase + s * 8 : nullptr; });
-        }
-        {
-            const uint64_t un = u + stride;
-            if (lane == 0 && un < nunits) issue_tma(un);   // both half tiles were flushed
-            // ---- lanes 0-15: Cb of MCU lane, lanes 16-31: Cr of MCU lane-16 ----
-            f2 R[4][8];
-            const int comp = lane >> 4, mcu = lane & 15;
-            const uint4 *csrc = reinterpret_cast<const uint4 *>(WS.csum) + mcu * 16;
-            const uint32_t sel = comp == 0 ? 0x7610u : 0x7632u;
-            // low half = 65536 - sum(cb), high half = 65539 - sum(cr)  (see ycc_row8);
-            // block value = 4 * (sum * 0.25 - 128) = sum - 512  (src/jpeg/mod.rs:1642-1653)
-            const float bias = comp == 0 ? 8453632.0f : 8453635.0f;  // 2^23 + 65536(+3) - 512
-            // (edge lanes read sums no Y job wrote for them: finite garbage, never flushed)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float v0[8], v1[8];
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int l0 = (2 * i) * 2 + hh, l1 = (2 * i + 1) * 2 + hh;
-                    const uint4 s0 = csrc[l0 ^ (mcu & 7)];
-                    const uint4 s1 = csrc[l1 ^ (mcu & 7)];
-                    const uint32_t a[4] = {s0.x, s0.y, s0.z, s0.w};
-                    const uint32_t b[4] = {s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        v0[hh * 4 + k] = __uint_as_float(__byte_perm(a[k], 0x4B000000u, sel));
-                        v1[hh * 4 + k] = __uint_as_float(__byte_perm(b[k], 0x4B000000u, sel));
-                    }
-                }
-#pragma unroll
-                for (int x = 0; x < 8; ++x) R[i][x] = sub2(K2(bias), pk(v0[x], v1[x]));
+            dct_quant_store_x2<ZIGZAG>(R, qp, QS, chroma_u, stage + slot * 8, swz, zero2);
+            if (!chroma_u) {
+                uint4 *ybase = reinterpret_cast<uint4 *>(P.y + (size_t)img * P.y_stride +
+                                                         (mcu_base + job * 8) * 4 * 64);
+                const uint32_t first = job * 8;
+                flush_stage(
+                    stage, lane, [](int s) { return ((s >> 3) << 1) | (s & 1); },
+                    [&](int s) -> uint4 * { return first + (s >> 2) < n_mcu ? ybase + s * 8 : nullptr; });
+            } else {
+                uint4 *cbb = reinterpret_cast<uint4 *>(P.cb + (size_t)img * P.c_stride + mcu_base * 64);
+                uint4 *crb = reinterpret_cast<uint4 *>(P.cr + (size_t)img * P.c_stride + mcu_base * 64);
+                flush_stage(
+                    stage, lane, [](int s) { return s & 7; },
+                    [&](int s) -> uint4 * {
+                        return (uint32_t)(s & 15) < n_mcu ? (s < 16 ? cbb : crb) + (s & 15) * 8 : nullptr;
+                    });
             }
-            __syncwarp();  // every lane has read its chroma sums: the buffer becomes the stage
-            uint4 *stage = reinterpret_cast<uint4 *>(WS.csum);
-            dct_quant_store_x2<ZIGZAG, 1>(R, qp, stage + lane * 8, lane & 7, zero2);   // slot = lane: 0-15 Cb, 16-31 Cr
-            uint4 *cbb = reinterpret_cast<uint4 *>(P.cb + (size_t)img * P.c_stride + mcu_base * 64);
-            uint4 *crb = reinterpret_cast<uint4 *>(P.cr + (size_t)img * P.c_stride + mcu_base * 64);
-            flush_stage(
-                stage, lane, [](int s) { return s & 7; },
-                [&](int s) -> uint4 * {
-                    return (uint32_t)(s & 15) < n_mcu ? (s < 16 ? cbb : crb) + (s & 15) * 8 : nullptr;
-                });
         }
+        img = img_n; my = my_n; ux = ux_n;
     }
 }
 
@@ -753,6 +825,9 @@ struct __align__(128) K4WarpSmem {
 
 struct __align__(128) K4Smem {
     K4WarpSmem w[K4_WARPS];
+#if K_QMODE == 0
+    QuantSmem q;
+#endif
 };
 
 // K1Params with mcus_x / mcus_y = blocks per row / block rows, units_x = units per block row
@@ -768,6 +843,12 @@ k_jpeg_444(const __grid_constant__ K1Params P, const __grid_constant__ QPairTab 
     K4Smem &S = *reinterpret_cast<K4Smem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     K4WarpSmem &WS = S.w[warp];
+#if K_QMODE == 0
+    for (int i = tid; i < 64; i += K4_THREADS) S.q.t[i >> 5][i & 31] = qp.t[i >> 5][i & 31];
+    const QuantSmem *QS = &S.q;
+#else
+    const QuantSmem *QS = nullptr;
+#endif
     if (lane == 0) {
         mbar_init(&WS.bar[0], 1);
         mbar_init(&WS.bar[1], 1);
@@ -776,21 +857,22 @@ k_jpeg_444(const __grid_constant__ K1Params P, const __grid_constant__ QPairTab 
     __syncthreads();
 
     const f2 zero2 = pk(P.zero[0], P.zero[1]);
-    const uint64_t units_per_img = (uint64_t)P.mcus_y * P.units_x;
-    const uint64_t nunits = units_per_img * P.n_images;
-    const uint64_t stride = (uint64_t)gridDim.x * K4_WARPS;
+    const uint32_t units_per_img = P.mcus_y * P.units_x;   // no division in the loop: see k_jpeg_420
+    const uint64_t nunits = (uint64_t)units_per_img * P.n_images;
+    const uint32_t stride = gridDim.x * K4_WARPS;
+    const uint32_t d_ux = stride % P.units_x, d_t = stride / P.units_x;
+    const uint32_t d_by = d_t % P.mcus_y, d_img = d_t / P.mcus_y;
     uint32_t phase = 0;  // bit b = parity to wait for on bar[b]
 
-    auto decode = [&](uint64_t u, uint32_t &img, uint32_t &by, uint32_t &ux) {
-        img = (uint32_t)(u / units_per_img);
-        const uint32_t rem = (uint32_t)(u - (uint64_t)img * units_per_img);
-        by = rem / P.units_x;
-        ux = rem - by * P.units_x;
+    auto advance = [&](uint32_t &img, uint32_t &by, uint32_t &ux) {
+        ux += d_ux;
+        if (ux >= P.units_x) { ux -= P.units_x; ++by; }
+        by += d_by;
+        if (by >= P.mcus_y) { by -= P.mcus_y; ++img; }
+        img += d_img;
     };
     auto unit_by_tma = [&](uint32_t by) { return P.use_tma && (by * 8 + 8 <= P.h); };
-    auto issue_tma = [&](uint64_t u_, int b) {
-        uint32_t img_, by_, ux_;
-        decode(u_, img_, by_, ux_);
+    auto issue_tma = [&](uint32_t img_, uint32_t by_, uint32_t ux_, int b) {
         if (unit_by_tma(by_)) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&WS.bar[b], K4_TILE_BYTES);
@@ -799,12 +881,20 @@ k_jpeg_444(const __grid_constant__ K1Params P, const __grid_constant__ QPairTab 
     };
 
     uint64_t u = (uint64_t)blockIdx.x * K4_WARPS + warp;
+    uint32_t img, by, ux;
+    {
+        const uint32_t u0 = blockIdx.x * K4_WARPS + warp;
+        img = u0 / units_per_img;
+        const uint32_t rem = u0 - img * units_per_img;
+        by = rem / P.units_x;
+        ux = rem - by * P.units_x;
+    }
     int b = 0;
-    if (u < nunits && lane == 0) issue_tma(u, 0);
+    if (u < nunits && lane == 0) issue_tma(img, by, ux, 0);
     for (; u < nunits; u += stride, b ^= 1) {
-        uint32_t img, by, ux;
-        decode(u, img, by, ux);
-        if (lane == 0 && u + stride < nunits) issue_tma(u + stride, b ^ 1);  // that buffer was released below
+        uint32_t img_n = img, by_n = by, ux_n = ux;
+        advance(img_n, by_n, ux_n);
+        if (lane == 0 && u + stride < nunits) issue_tma(img_n, by_n, ux_n, b ^ 1);  // that buffer was released below
         if (unit_by_tma(by)) {
             mbar_wait(&WS.bar[b], (phase >> b) & 1u);
             phase ^= 1u << b;
@@ -829,37 +919,38 @@ k_jpeg_444(const __grid_constant__ K1Params P, const __grid_constant__ QPairTab 
                 WS.stage, lane, [](int s) { return s & 7; },
                 [&](int s) -> uint4 * { return bx0 + s < P.mcus_x ? dbase + s * 8 : nullptr; });
         };
-        {   // the component is decided once per pass, not per pixel: straight-line fills
-            f2 R[4][8];
-#pragma unroll
-            for (int rp = 0; rp < 4; ++rp) {
-                float v0[8], v1[8];
-                uint32_t wa[6], wb[6];
-                row_words(rp * 2, wa); row_words(rp * 2 + 1, wb);
-                y_row8(wa, v0); y_row8(wb, v1);
-#pragma unroll
-                for (int x = 0; x < 8; ++x) R[rp][x] = pk(v0[x], v1[x]);
-            }
-            dct_quant_store_x2<ZIGZAG, 0>(R, qp, WS.stage + lane * 8, lane & 7, zero2);
-            flush(P.y + (size_t)img * P.y_stride);
-        }
 #pragma unroll 1
-        for (int comp = 1; comp < 3; ++comp) {
+        for (int comp = 0; comp < 3; ++comp) {
+            const bool chroma_u = __ballot_sync(0xffffffffu, comp != 0) != 0u;   // uniform, and ptxas can tell
             f2 R[4][8];
-            const uint32_t wgt = comp == 1 ? 0x0080552Bu : 0x00156B80u;
+            // the component is decided once per pass, not per pixel: straight-line fills
+            if (!chroma_u) {
 #pragma unroll
-            for (int rp = 0; rp < 4; ++rp) {
-                float v0[8], v1[8];
-                uint32_t wa[6], wb[6];
-                row_words(rp * 2, wa); row_words(rp * 2 + 1, wb);
-                c_row8(wa, wgt, v0); c_row8(wb, wgt, v1);
+                for (int rp = 0; rp < 4; ++rp) {
+                    float v0[8], v1[8];
+                    uint32_t wa[6], wb[6];
+                    row_words(rp * 2, wa); row_words(rp * 2 + 1, wb);
+                    y_row8(wa, v0); y_row8(wb, v1);
 #pragma unroll
-                for (int x = 0; x < 8; ++x) R[rp][x] = pk(v0[x], v1[x]);
+                    for (int x = 0; x < 8; ++x) R[rp][x] = pk(v0[x], v1[x]);
+                }
+            } else {
+                const uint32_t wgt = comp == 1 ? 0x0080552Bu : 0x00156B80u;
+#pragma unroll
+                for (int rp = 0; rp < 4; ++rp) {
+                    float v0[8], v1[8];
+                    uint32_t wa[6], wb[6];
+                    row_words(rp * 2, wa); row_words(rp * 2 + 1, wb);
+                    c_row8(wa, wgt, v0); c_row8(wb, wgt, v1);
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) R[rp][x] = pk(v0[x], v1[x]);
+                }
             }
-            dct_quant_store_x2<ZIGZAG, 1>(R, qp, WS.stage + lane * 8, lane & 7, zero2);
-            flush((comp == 1 ? P.cb : P.cr) + (size_t)img * P.c_stride);
+            dct_quant_store_x2<ZIGZAG>(R, qp, QS, chroma_u, WS.stage + lane * 8, lane & 7, zero2);
+            flush(comp == 0 ? P.y + (size_t)img * P.y_stride : (comp == 1 ? P.cb : P.cr) + (size_t)img * P.c_stride);
         }
         __syncwarp();  // every lane is done with tile[b]: the TMA issued next iteration may refill it
+        img = img_n; by = by_n; ux = ux_n;
     }
 }
 
@@ -872,6 +963,13 @@ k_jpeg_gray(const uint8_t *__restrict__ pixels, size_t pixel_stride, uint32_t w,
     constexpr int TB = K2_BLOCKS * 8;  // 512
     __shared__ __align__(16) uint8_t tile[8 * TB];
     __shared__ __align__(16) uint4 stage[2][256];
+#if K_QMODE == 0
+    __shared__ QuantSmem qsm;
+    for (int i = threadIdx.x; i < 64; i += 64) qsm.t[i >> 5][i & 31] = qp.t[i >> 5][i & 31];
+    const QuantSmem *QS = &qsm;
+#else
+    const QuantSmem *QS = nullptr;
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tx = blockIdx.x % tiles_x;
     const uint32_t brow = blockIdx.x / tiles_x;
@@ -897,7 +995,7 @@ k_jpeg_gray(const uint8_t *__restrict__ pixels, size_t pixel_stride, uint32_t w,
                 R[rp][x] = sub2(pk(f0, f1), K2(8388736.0f));
             }
         }
-        dct_quant_store_x2<ZIGZAG, 0>(R, qp, stage[warp] + lane * 8, lane & 7, zero2);
+        dct_quant_store_x2<ZIGZAG>(R, qp, QS, false, stage[warp] + lane * 8, lane & 7, zero2);
     }
     const uint32_t first = b0 + warp * 32;
     uint4 *dbase = reinterpret_cast<uint4 *>(yout + (size_t)img * y_stride + ((size_t)brow * blocks_x + first) * 64);
@@ -1128,8 +1226,12 @@ int launch_jpeg_transform(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pi
             return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT,
                              "quantisation table entries must be integers in 1..255");
     }
-    for (uint32_t i0 = 0; i0 < n_images; i0 += 65535) {
-        const uint32_t nb = n_images - i0 < 65535 ? n_images - i0 : 65535;
+    // frames per launch: grid.y of the gray kernel and the 32-bit unit coordinates of K1 / K2 (a
+    // frame has fewer than 2^24 units: 65 535^2 px / (256 x 8))
+    const uint64_t units_max = (uint64_t)((w + 7) / 8 + 31) / 32 * ((h + 7) / 8);   // K2's units; K1 has fewer
+    const uint32_t per_launch = (uint32_t)std::min<uint64_t>(65535, 0xFFFFFFFFull / (units_max ? units_max : 1));
+    for (uint32_t i0 = 0; i0 < n_images; i0 += per_launch) {
+        const uint32_t nb = n_images - i0 < per_launch ? n_images - i0 : per_launch;
         const uint8_t *px = d_pixels + (size_t)i0 * pixel_stride;
         int16_t *y = d_y + (size_t)i0 * y_stride;
         int16_t *cb = d_cb ? d_cb + (size_t)i0 * c_stride : nullptr;

@@ -103,6 +103,7 @@ class DeviceBandCoder:
         self.ny, self.nc = int(ny), int(nc)
         self.dev = d_y.device
         self.raw = None
+        self.out = None
 
     def _p(self, t):
         return None if t is None else int(t.data_ptr())
@@ -132,7 +133,9 @@ class DeviceBandCoder:
         s = (C.c_int32 * 3)(*[int(v) for v in seed])
         hp = None if hist is None else np.ascontiguousarray(hist, np.uint64).ctypes.data_as(_lib.u64p)
         for _ in range(2):
-            self.raw = self.torch.empty(cap, dtype=self.torch.uint8, device=self.dev)
+            if self.raw is None or self.raw.numel() < cap:
+                self.raw = self.torch.empty(cap, dtype=self.torch.uint8, device=self.dev)
+            cap = self.raw.numel() // 16 * 16
             nbits, tail = C.c_uint64(), C.c_uint32()
             rc = self.lib.pixo_b200_jpeg_band_entropy_dev(
                 self.ctx.handle, self._p(self.d_y), self._p(self.d_cb), self._p(self.d_cr), *self.geo, s, hp,
@@ -147,12 +150,13 @@ class DeviceBandCoder:
     def splice(self, nbits, start_bit, tail_in, is_last):
         """-> uint8 tensor (device) of this band's finished scan bytes."""
         cap = (nbits + 7) // 8 * 2 + 64     # worst case: every byte stuffed
-        out = self.torch.empty(cap, dtype=self.torch.uint8, device=self.dev)
+        if self.out is None or self.out.numel() < cap:
+            self.out = self.torch.empty(cap, dtype=self.torch.uint8, device=self.dev)
         n = C.c_uint64()
         _lib.check(self.ctx.handle, self.lib.pixo_b200_jpeg_band_splice_dev(
             self.ctx.handle, self._p(self.raw) if self.raw is not None else None, nbits, start_bit, tail_in,
-            int(is_last), int(out.data_ptr()), cap, C.byref(n)))
-        return out[: n.value]
+            int(is_last), int(self.out.data_ptr()), self.out.numel(), C.byref(n)))
+        return self.out[: n.value]
 
 
 class HostBandCoder:
@@ -222,11 +226,27 @@ def write_headers(width, height, color_type, quality, subsampling, hist=None) ->
 
 
 def encode_tiled(coder, width: int, height: int, color_type: int, quality: int, subsampling: int,
-                 optimize_huffman: bool, rank: int, world: int, dst: int = 0, timings: dict | None = None):
-    """Distributed entropy stage of one tiled frame.  `coder` holds this rank's band (coefficients
-    already computed).  Returns the complete JPEG on `dst`, None elsewhere.  Collectives: all_gather
-    of 4 ints (DC predictors), [all_reduce of 536 counters], all_gather of 2 ints (bits, tail),
-    all_gather of 1 int (byte counts), gather of the scan bytes."""
+                 optimize_huffman: bool, rank: int, world: int, dst: int = 0):
+    """Distributed entropy stage of one tiled frame: the complete JPEG on `dst`, None elsewhere."""
+    parts, hist = tiled_scan_parts(coder, optimize_huffman, rank, world, dst)
+    if rank != dst:
+        return None
+    return assemble_tiled(parts, hist, width, height, color_type, quality, subsampling)
+
+
+def assemble_tiled(parts, hist, width, height, color_type, quality, subsampling) -> bytes:
+    """Host side of the last step: headers + the bands' scan bytes (device or host tensors) + EOI."""
+    import torch
+    scan = torch.cat([p.cpu() for p in parts]).numpy().tobytes() if parts else b""
+    return write_headers(width, height, color_type, quality, subsampling, hist) + scan + b"\xff\xd9"
+
+
+def tiled_scan_parts(coder, optimize_huffman: bool, rank: int, world: int, dst: int = 0):
+    """The device part of `encode_tiled`.  `coder` holds this rank's band (coefficients already
+    computed).  Returns (the bands' finished scan bytes in band order as tensors on dst's device -
+    None on the other ranks -, the summed histogram or None).  Collectives: all_gather of 4 ints (DC
+    predictors), [all_reduce of 536 counters], all_gather of 2 ints (bits, tail), all_gather of 1 int
+    (byte counts), gather of the scan bytes (only dst receives)."""
     import torch
     import torch.distributed as dist
     dev = coder.dev
@@ -261,18 +281,10 @@ def encode_tiled(coder, width: int, height: int, color_type: int, quality: int, 
         mx = int(max(sizes.max(), 1))
         pad = torch.zeros(mx, dtype=torch.uint8, device=dev)
         pad[: body.numel()] = body
-        if dist.get_backend() == "nccl":
-            # NCCL gather: every rank sends its (padded) bytes, only dst receives
-            bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
-            dist.gather(pad, bufs, dst=dst)
-        else:
-            bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
-            dist.gather(pad, bufs, dst=dst)
+        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+        dist.gather(pad, bufs, dst=dst)      # every rank sends its (padded) bytes, only dst receives
         parts = [bufs[r][: int(sizes[r])] for r in range(world)] if rank == dst else None
-    if rank != dst:
-        return None
-    scan = torch.cat(parts).cpu().numpy().tobytes()
-    return write_headers(width, height, color_type, quality, subsampling, hist) + scan + b"\xff\xd9"
+    return (parts if rank == dst else None), hist
 
 
 def encode_tiled_local(coders: list, width: int, height: int, color_type: int, quality: int, subsampling: int,
@@ -280,6 +292,11 @@ def encode_tiled_local(coders: list, width: int, height: int, color_type: int, q
     """The same stage sequence with every band in THIS process (one GPU context, or the host
     twins): what `encode_tiled` does across ranks, minus the collectives.  Used at world size 1
     (bench.py's C4 line on one GPU, the single-device tests)."""
+    parts, hist = tiled_scan_parts_local(coders, optimize_huffman)
+    return assemble_tiled(parts, hist, width, height, color_type, quality, subsampling)
+
+
+def tiled_scan_parts_local(coders: list, optimize_huffman: bool = False):
     import torch
     world = len(coders)
     last = np.stack([c.last_dc() for c in coders])
@@ -296,9 +313,8 @@ def encode_tiled_local(coders: list, width: int, height: int, color_type: int, q
         if not nbits[r]:
             continue
         start, tail_in, is_last = bit_offsets(nbits, tails, r)
-        parts.append(c.splice(nbits[r], start, tail_in, is_last).cpu())
-    scan = torch.cat(parts).numpy().tobytes() if parts else b""
-    return write_headers(width, height, color_type, quality, subsampling, hist) + scan + b"\xff\xd9"
+        parts.append(c.splice(nbits[r], start, tail_in, is_last))
+    return parts, hist
 
 
 # ---- Adler-32 of a stream held in pieces (PNG filter stage in row bands) ----------------------------

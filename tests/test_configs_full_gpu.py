@@ -43,7 +43,7 @@ def test_c5_full_batch_64x4k_rgba(po, gpu_ctx):
         if k in (0, 1, 31, 62, 63):
             hosts[k] = f
         d_in[k] = torch.from_numpy(f).to(dev)
-    assert d_in.numel() > 1 << 31
+    assert d_in.numel() > 1 << 30
     out_stride = h * (rb + 1)
     d_out = torch.empty((n, out_stride), dtype=torch.uint8, device=dev)
     d_ad = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -67,3 +67,55 @@ def test_default_preset_444_q75_on_4k(po, gpu_ctx):
     for img in (synthetic.noise(w, h, 3, 3), synthetic.gradient_rgb(w, h)):
         o = JpegOptions.fast(w, h, 75)
         assert jpeg.encode(img, o, ctx=gpu_ctx) == po.jpeg_encode(img, w, h, 2, 75, 0)
+
+
+def test_offsets_beyond_4_gib(po, gpu_ctx):
+    """One call over more than 2^32 bytes of input AND output: 180 4K RGB frames through the JPEG
+    device path (4.48 GB in) and 132 4K RGBA frames through the PNG filter (4.38 GB in/out); the last
+    frames - whose byte offsets do not fit 32 bits - must match the oracle."""
+    import torch
+    from pixo_b200 import _lib, synthetic
+    lib = _lib.load()
+    dev = torch.device("cuda", gpu_ctx.device)
+    w, h = 3840, 2160
+    base = [synthetic.noise(w, h, 3, 5), synthetic.gradient_rgb(w, h)]
+    n = 180
+    d_px = torch.empty((n, w * h * 3), dtype=torch.uint8, device=dev)
+    d_base = [torch.from_numpy(b).to(dev).reshape(h, -1) for b in base]
+    for k in range(n):
+        d_px[k] = torch.roll(d_base[k % 2], k, 0).reshape(-1)
+    assert d_px.numel() > 1 << 32
+    cap = (w * h * 3 // 2 + 65536) // 256 * 256
+    d_scan = torch.empty((n, cap), dtype=torch.uint8, device=dev)
+    d_len = torch.zeros(n, dtype=torch.int64, device=dev)
+    d_ovf = torch.zeros(n, dtype=torch.int32, device=dev)
+    _lib.check(gpu_ctx.handle, lib.pixo_b200_jpeg_encode_dev(gpu_ctx.handle, d_px.data_ptr(), w * h * 3, n, w, h, 2, 80, 1,
+                                                             d_scan.data_ptr(), cap, d_len.data_ptr(), d_ovf.data_ptr()))
+    gpu_ctx.sync()
+    assert int(d_ovf.sum()) == 0
+    lens = d_len.cpu().numpy()
+    for k in (0, 178, 179):
+        ref = po.jpeg_encode(np.roll(base[k % 2].reshape(h, -1), k, axis=0).reshape(-1), w, h, 2, 80, 1)
+        got = d_scan[k, : int(lens[k])].cpu().numpy().tobytes()
+        assert got == ref[ref.index(b"\xff\xda") + 14:-2], k
+    del d_px, d_scan
+    torch.cuda.empty_cache()
+    n, bpp = 132, 4
+    rb = w * bpp
+    rgba = [synthetic.noise(w, h, 4, 8), np.concatenate([synthetic.gradient_rgb(w, h).reshape(h, w, 3),
+                                                         np.full((h, w, 1), 200, np.uint8)], -1).reshape(-1)]
+    d_base = [torch.from_numpy(b).to(dev).reshape(h, rb) for b in rgba]
+    d_in = torch.empty((n, h * rb), dtype=torch.uint8, device=dev)
+    for k in range(n):
+        d_in[k] = torch.roll(d_base[k % 2], k, 0).reshape(-1)
+    assert d_in.numel() > 1 << 32
+    d_out = torch.empty((n, h * (rb + 1)), dtype=torch.uint8, device=dev)
+    d_ad = torch.zeros(n, dtype=torch.int32, device=dev)
+    _lib.check(gpu_ctx.handle, lib.pixo_b200_png_filter_dev(gpu_ctx.handle, d_in.data_ptr(), h * rb, n, w, h, rb, bpp,
+                                                            po.F_ADAPTIVE, d_out.data_ptr(), h * (rb + 1), d_ad.data_ptr()))
+    gpu_ctx.sync()
+    ad = d_ad.cpu().numpy().view(np.uint32)
+    for k in (0, 130, 131):
+        ref = po.apply_filters(np.roll(rgba[k % 2].reshape(h, rb), k, axis=0).reshape(-1), w, h, bpp, po.F_ADAPTIVE)
+        assert hashlib.sha256(d_out[k].cpu().numpy().tobytes()).digest() == hashlib.sha256(ref.tobytes()).digest(), k
+        assert int(ad[k]) == po.adler32(ref), k
