@@ -62,22 +62,95 @@ int ensure_pinned(pixo_b200_ctx *ctx, Scratch &s, size_t bytes)
     return 0;
 }
 
-// Host -> device copy that does not depend on the caller's buffer being page-locked.  pixo's
-// callers hand over ordinary (pageable) memory; the driver's own pageable path slows down to
-// ~11 GB/s on large sources.  Here up to four host threads copy 4 MB pieces into a ring of pinned slots and queue
-// the DMA of each piece as soon as it is staged, so copy and DMA overlap and the link runs near
-// its pinned rate.  Page-locked sources (and small ones) go straight to cudaMemcpyAsync.
-static int h2d_copy(pixo_b200_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st)
+HostPool::HostPool(int nthreads)
 {
-    constexpr size_t SLOT = (size_t)4 << 20;
-    constexpr int NSLOT = 4;
+    for (int i = 0; i < nthreads; ++i) threads_.emplace_back([this] { worker(); });
+}
+
+HostPool::~HostPool()
+{
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        stop_ = true;
+    }
+    cv_work_.notify_all();
+    for (auto &t : threads_) t.join();
+}
+
+void HostPool::worker()
+{
+    uint64_t seen = 0;
+    for (;;) {
+        const std::function<void(int)> *fn;
+        int n;
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_work_.wait(lk, [&] { return stop_ || generation_ != seen; });
+            if (stop_) return;
+            seen = generation_;
+            fn = fn_;
+            n = njobs_;
+            ++active_;
+        }
+        for (int j; (j = next_.fetch_add(1)) < n;) (*fn)(j);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            if (--active_ == 0) cv_done_.notify_all();
+        }
+    }
+}
+
+void HostPool::run(int njobs, const std::function<void(int)> &fn)
+{
+    if (njobs <= 0) return;
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        fn_ = &fn;
+        njobs_ = njobs;
+        next_.store(0);
+        ++generation_;
+    }
+    if (njobs > 1) cv_work_.notify_all();
+    for (int j; (j = next_.fetch_add(1)) < njobs;) fn(j);
+    // every job has been claimed; wait for the workers that are still inside one (a worker that
+    // wakes up late finds nothing to claim and leaves at once)
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [&] { return active_ == 0; });
+    fn_ = nullptr;
+    njobs_ = 0;
+}
+
+static HostPool *host_pool(pixo_b200_ctx *ctx)
+{
+    if (!ctx->pool) {
+        int n = ctx->host_threads - 1;
+        n = n < 1 ? 1 : (n > 5 ? 5 : n);   // five helpers + the caller saturate a socket's copy bandwidth
+        ctx->pool = new HostPool(n);
+    }
+    return ctx->pool;
+}
+
+static bool is_page_locked(const void *p)
+{
     cudaPointerAttributes at;
-    const bool locked = cudaPointerGetAttributes(&at, src) == cudaSuccess &&
+    const bool locked = cudaPointerGetAttributes(&at, p) == cudaSuccess &&
                         (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
     cudaGetLastError();  // an unregistered pointer is not an error here
-    // measured on the B200 box: a 25 MB frame takes 1.4 ms either way, a 201 MB frame 18 ms through
-    // the driver's pageable path and 7.5 ms through the slots, so only large sources are staged
-    if (locked || bytes < ((size_t)64 << 20)) {
+    return locked;
+}
+
+// Host -> device copy that does not depend on the caller's buffer being page-locked.  pixo's
+// callers hand over ordinary (pageable) memory, and the driver's own pageable path moves it at
+// 11-18 GB/s (one staging thread).  Here the context's host threads copy 1 MB pieces into a ring of
+// pinned slots and each queues the DMA of its piece as soon as it is staged, so the host copies run
+// in parallel with each other and with the DMA engine, and the link runs near its pinned rate
+// (measured on the B200 box: a pageable 25 MB 4K frame 1.4 ms -> see DESIGN.md section 5).
+// Page-locked sources, and small ones, go straight to cudaMemcpyAsync.
+static int h2d_copy(pixo_b200_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    constexpr size_t SLOT = (size_t)1 << 20;
+    constexpr int NSLOT = 32;
+    if (bytes < 4 * SLOT || is_page_locked(src)) {
         PIXO_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
         return 0;
     }
@@ -88,27 +161,59 @@ static int h2d_copy(pixo_b200_ctx *ctx, void *dst, const void *src, size_t bytes
         PIXO_CUDA(ctx, cudaEventRecord(ev, st));
         ctx->stage_events.push_back(ev);
     }
-    const size_t nchunks = (bytes + SLOT - 1) / SLOT;
-    const int nthreads = (int)std::min<size_t>(NSLOT, nchunks);
-    cudaError_t errs[NSLOT];
-    auto worker = [&](int t) {   // thread t owns slot t and the pieces t, t + nthreads, ...
-        cudaError_t e = cudaSetDevice(ctx->device);
-        uint8_t *slot = reinterpret_cast<uint8_t *>(ctx->h_in.ptr) + (size_t)t * SLOT;
-        for (size_t c = (size_t)t; c < nchunks && e == cudaSuccess; c += (size_t)nthreads) {
-            const size_t off = c * SLOT, n = std::min(SLOT, bytes - off);
-            e = cudaEventSynchronize(ctx->stage_events[t]);  // the slot's previous DMA has drained
-            if (e != cudaSuccess) break;
+    const int nchunks = (int)((bytes + SLOT - 1) / SLOT);
+    std::atomic<int> first_error{(int)cudaSuccess};
+    const int device = ctx->device;
+    // piece c uses slot c % NSLOT; pieces are claimed in order, so a slot's previous user is always
+    // NSLOT pieces back and its DMA has normally drained long before the slot comes round again
+    auto piece = [&](int c) {
+        if (first_error.load() != (int)cudaSuccess) return;
+        cudaError_t e = cudaSetDevice(device);
+        const int slot_i = c % NSLOT;
+        uint8_t *slot = reinterpret_cast<uint8_t *>(ctx->h_in.ptr) + (size_t)slot_i * SLOT;
+        const size_t off = (size_t)c * SLOT, n = std::min(SLOT, bytes - off);
+        if (e == cudaSuccess) e = cudaEventSynchronize(ctx->stage_events[slot_i]);   // the slot's previous DMA (this call's or the last one's) has drained
+        if (e == cudaSuccess) {
             memcpy(slot, reinterpret_cast<const uint8_t *>(src) + off, n);
             e = cudaMemcpyAsync(reinterpret_cast<uint8_t *>(dst) + off, slot, n, cudaMemcpyHostToDevice, st);
-            if (e == cudaSuccess) e = cudaEventRecord(ctx->stage_events[t], st);
         }
-        errs[t] = e;
+        if (e == cudaSuccess && c + NSLOT < nchunks) e = cudaEventRecord(ctx->stage_events[slot_i], st);
+        if (e != cudaSuccess) { int ok = (int)cudaSuccess; first_error.compare_exchange_strong(ok, (int)e); }
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nthreads; ++t) th.emplace_back(worker, t);
-    worker(0);
-    for (auto &x : th) x.join();
-    for (int t = 0; t < nthreads; ++t) PIXO_CUDA(ctx, errs[t]);
+    if (nchunks > NSLOT) {
+        // a slot is reused: its event must be recorded by the piece that used it before.  Run the
+        // pieces in rounds of NSLOT so that "previous user" is always in an earlier round.
+        for (int r0 = 0; r0 < nchunks; r0 += NSLOT) {
+            const int cnt = std::min(NSLOT, nchunks - r0);
+            host_pool(ctx)->run(cnt, [&](int j) { piece(r0 + j); });
+        }
+    } else {
+        host_pool(ctx)->run(nchunks, piece);
+    }
+    // the slots may be rewritten by the next call: make that call wait for this one's DMAs
+    PIXO_CUDA(ctx, (cudaError_t)first_error.load());
+    for (int s_i = 0; s_i < std::min(nchunks, NSLOT); ++s_i) PIXO_CUDA(ctx, cudaEventRecord(ctx->stage_events[s_i], st));
+    return 0;
+}
+
+// Device -> pageable host: through the pinned ring with the pool copying out, for results big
+// enough to matter (a 4K JPEG is ~3 MB).  Synchronous: returns when `dst` holds the bytes.
+static int d2h_copy_sync(pixo_b200_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    constexpr size_t PIECE = (size_t)512 << 10;
+    if (bytes < 2 * PIECE || is_page_locked(dst)) {
+        PIXO_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        PIXO_CUDA(ctx, cudaStreamSynchronize(st));
+        return 0;
+    }
+    PIXO_TRY(ensure_pinned(ctx, ctx->h_out, bytes));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(ctx->h_out.ptr, src, bytes, cudaMemcpyDeviceToHost, st));
+    PIXO_CUDA(ctx, cudaStreamSynchronize(st));
+    const int n = (int)((bytes + PIECE - 1) / PIECE);
+    host_pool(ctx)->run(n, [&](int j) {
+        const size_t off = (size_t)j * PIECE, len = std::min(PIECE, bytes - off);
+        memcpy(reinterpret_cast<uint8_t *>(dst) + off, reinterpret_cast<const uint8_t *>(ctx->h_out.ptr) + off, len);
+    });
     return 0;
 }
 
@@ -200,6 +305,7 @@ void pixo_b200_ctx_destroy(pixo_b200_ctx *ctx)
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    delete ctx->pool;
     delete ctx;
 }
 
@@ -526,6 +632,7 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
                     reinterpret_cast<int16_t *>(base + yb + cbb)};
     };
     std::vector<HuffTables> tables[2];
+    const bool out_locked = is_page_locked(out);
     DrainOnError drain(ctx);
 
     auto upload = [&](uint32_t gi) -> int {
@@ -610,8 +717,11 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
             if (hdr[k] + body + 2 > out_cap_each)
                 return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small (need %zu)",
                                  out_cap_each, hdr[k] + body + 2);
-            PIXO_CUDA(ctx, cudaMemcpyAsync(o + hdr[k], scan + (size_t)k * scan_cap, body, cudaMemcpyDeviceToHost,
-                                           ctx->d2h_stream));
+            if (out_locked)
+                PIXO_CUDA(ctx, cudaMemcpyAsync(o + hdr[k], scan + (size_t)k * scan_cap, body, cudaMemcpyDeviceToHost,
+                                               ctx->d2h_stream));
+            else   // ordinary caller memory: through the pinned ring, copied out by the host pool
+                PIXO_TRY(d2h_copy_sync(ctx, o + hdr[k], scan + (size_t)k * scan_cap, body, ctx->d2h_stream));
             o[hdr[k] + body] = 0xFF;
             o[hdr[k] + body + 1] = 0xD9;
             out_lens[img] = hdr[k] + body + 2;

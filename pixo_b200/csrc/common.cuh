@@ -5,8 +5,12 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pixo_b200.h"
@@ -26,6 +30,29 @@ struct QuantTab {
 struct Scratch {
     void *ptr = nullptr;
     size_t cap = 0;
+};
+
+// A few persistent host threads per context for the one host-side job that is worth spreading:
+// copying a caller's ordinary (pageable) memory into / out of the pinned staging ring while the DMA
+// engine drains it.  Created on first use; the threads sleep on a condition variable between calls.
+class HostPool {
+public:
+    explicit HostPool(int nthreads);
+    ~HostPool();
+    // fn(job) for job in [0, njobs), on the pool's threads and the caller; returns when all are done
+    void run(int njobs, const std::function<void(int)> &fn);
+    int size() const { return (int)threads_.size(); }
+
+private:
+    void worker();
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int njobs_ = 0, active_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
 };
 
 }  // namespace pixo
@@ -48,6 +75,7 @@ struct pixo_b200_ctx {
     pixo::Scratch h_in, h_out, h_misc;
     std::vector<cudaEvent_t> events;
     std::vector<cudaEvent_t> stage_events;  // one per pinned staging slot of h2d_copy
+    pixo::HostPool *pool = nullptr;         // see HostPool
 };
 
 namespace pixo {

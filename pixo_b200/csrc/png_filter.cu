@@ -38,20 +38,48 @@ __device__ __forceinline__ uint32_t sum_abs_s8x4(uint32_t v)
     return (uint32_t)__dp4a((int)v, (int)sgn, 0);
 }
 
-__device__ __forceinline__ uint32_t paeth4(uint32_t a, uint32_t b, uint32_t c)
+__device__ __forceinline__ uint32_t sel4(uint32_t mask, uint32_t x, uint32_t y)
 {
-    // fallback_paeth_predictor, src/simd/fallback.rs:143-159, per byte lane
-    uint32_t r = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int aa = (a >> (8 * j)) & 0xFF, bb = (b >> (8 * j)) & 0xFF, cc = (c >> (8 * j)) & 0xFF;
-        const int t1 = bb - cc, t2 = aa - cc;
-        const int pa = abs(t1), pb = abs(t2), pc = abs(t1 + t2);
-        const int pred = (pa <= pb && pa <= pc) ? aa : (pb <= pc ? bb : cc);
-        r |= (uint32_t)pred << (8 * j);
-    }
+    return (x & mask) | (y & ~mask);
+}
+// every byte -> 0xFF if its bit 7 is set, else 0 (PRMT sign replication: one instruction)
+__device__ __forceinline__ uint32_t signrep4(uint32_t v)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(0u), "r"(0xBA98u));
     return r;
 }
+// bit 7 of every byte = (y >= x), unsigned per byte; the other bits are garbage.  (y | H) - (x & ~H)
+// is 128 + y7 - x7 per byte (y7, x7 = low seven bits), so it never borrows across bytes and its bit
+// 7 says y7 >= x7; the top bits decide unless they are equal.  Two LOP3, one IADD, one LOP3.
+__device__ __forceinline__ uint32_t ge7(uint32_t y, uint32_t x)
+{
+    const uint32_t t = (y | 0x80808080u) - (x & 0x7F7F7F7Fu);
+    return (y & ~x) | (~(y ^ x) & t);
+}
+
+// fallback_paeth_predictor (src/simd/fallback.rs:143-159) for four byte lanes at once.
+// With pa=|b-c|, pb=|a-c|, dab=|a-b|:  c lies within [min(a,b), max(a,b)]  <=>  max(pa,pb) <= dab,
+// in which case pc = |pa-pb|, otherwise pc = pa+pb >= max(pa,pb).  The reference's ladder
+// (a if pa<=pb && pa<=pc, else b if pb<=pc, else c) therefore reduces to: take the nearer of a/b
+// (a on ties) unless c is within the range and that nearer distance exceeds |pa-pb|, then c.
+// The three byte-wise comparisons are carried in bit 7 only (ge7) and widened to byte masks with
+// two PRMTs: 23 instructions for four bytes (the __vcmp* intrinsics version took 29).
+// Checked against the scalar definition for all 2^24 (a, b, c): tools/verify_paeth.c.
+__device__ __forceinline__ uint32_t paeth_pred4(uint32_t a, uint32_t b, uint32_t c)
+{
+    const uint32_t pa = __vabsdiffu4(b, c), pb = __vabsdiffu4(a, c), dab = __vabsdiffu4(a, b);
+    const uint32_t m1 = signrep4(ge7(pb, pa));       // 0xFF where pa <= pb: a is the nearer endpoint
+    const uint32_t near = sel4(m1, a, b);
+    const uint32_t mn = sel4(m1, pa, pb), mx = sel4(m1, pb, pa);
+    const uint32_t adiff = mx - mn;                  // per byte, mx >= mn: no borrow
+    // c wins iff it lies within the range (dab >= mx) and the nearer endpoint does not beat it
+    // (NOT adiff >= mn)
+    const uint32_t cw = signrep4(ge7(dab, mx) & ~ge7(adiff, mn));
+    return sel4(cw, c, near);
+}
+
+__device__ __forceinline__ uint32_t paeth4(uint32_t a, uint32_t b, uint32_t c) { return paeth_pred4(a, b, c); }
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
 {
@@ -433,28 +461,6 @@ __global__ void __launch_bounds__(PNG_THREADS) k_png_filter(const PngParams P)
 #endif
 constexpr int BAND_ROWS = PNG_BAND_ROWS;
 
-__device__ __forceinline__ uint32_t sel4(uint32_t mask, uint32_t x, uint32_t y)
-{
-    return (x & mask) | (y & ~mask);
-}
-
-// fallback_paeth_predictor (src/simd/fallback.rs:143-159) for four byte lanes at once.
-// With pa=|b-c|, pb=|a-c|, dab=|a-b|:  c lies within [min(a,b), max(a,b)]  <=>  max(pa,pb) <= dab,
-// in which case pc = |pa-pb|, otherwise pc = pa+pb >= max(pa,pb).  The reference's ladder
-// (a if pa<=pb && pa<=pc, else b if pb<=pc, else c) therefore reduces to: take the nearer of a/b
-// (a on ties) unless c is within the range and that nearer distance exceeds |pa-pb|, then c.
-__device__ __forceinline__ uint32_t paeth_pred4(uint32_t a, uint32_t b, uint32_t c)
-{
-    const uint32_t pa = __vabsdiffu4(b, c), pb = __vabsdiffu4(a, c), dab = __vabsdiffu4(a, b);
-    const uint32_t m1 = __vcmpleu4(pa, pb);          // 0xFF where pa <= pb
-    const uint32_t cand = sel4(m1, a, b);
-    const uint32_t mn = sel4(m1, pa, pb), mx = sel4(m1, pb, pa);
-    const uint32_t adiff = __vabsdiffu4(pa, pb);
-    const uint32_t within = __vcmpleu4(mx, dab);
-    const uint32_t keep = __vcmpleu4(mn, adiff);     // nearer endpoint still beats c
-    return sel4(within & ~keep, c, cand);
-}
-
 struct BandParams {
     const uint8_t *data;
     size_t in_stride;
@@ -571,18 +577,57 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
                 T[2] += __vsadu4(__vabsdiffu4(x, b) & mask, 0x80808080u);
                 T[4] += __vsadu4(__vabsdiffu4(x, paeth_pred4(a, b, c)) & mask, 0x80808080u);
             };
+            // Four consecutive words per thread (one LDS.128 per row buffer): the left neighbours of
+            // words 1-3 are already in registers, word 0's comes from the previous lane by shuffle,
+            // so a word costs half a shared-memory load instead of four; pixels of four bytes need
+            // no funnel shift at all (left = the previous word).
+            const uint32_t nv = full >> 2;
+            auto score4 = [&](auto a0tag, auto fivetag) {
+                constexpr bool A0 = decltype(a0tag)::value, FIVE = decltype(fivetag)::value;
+                const uint4 *c4 = reinterpret_cast<const uint4 *>(c32), *p4 = reinterpret_cast<const uint4 *>(p32);
+                for (uint32_t vb = (uint32_t)tid & ~31u; vb < nv; vb += PNG_THREADS) {
+                    const uint32_t v = vb + lane;
+                    const bool valid = v < nv;
+                    const uint32_t vv = valid ? v : nv - 1;
+                    const uint4 X4 = c4[vv], B4 = p4[vv];
+                    uint32_t x[5] = {0, X4.x, X4.y, X4.z, X4.w}, b[5] = {0, B4.x, B4.y, B4.z, B4.w};
+                    x[0] = __shfl_up_sync(0xffffffffu, X4.w, 1);
+                    b[0] = __shfl_up_sync(0xffffffffu, B4.w, 1);
+                    if (lane == 0) { x[0] = c32[4 * (int)vv - 1]; b[0] = p32[4 * (int)vv - 1]; }
+                    if (OA) {
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) { x[i] = zero_transparent<OA ? OA : 4>(x[i]); b[i] = zero_transparent<OA ? OA : 4>(b[i]); }
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int i = 1; i < 5; ++i) {
+                            const uint32_t a = A0 ? x[i - 1] : __funnelshift_r(x[i - 1], x[i], ashift);
+                            const uint32_t c = A0 ? b[i - 1] : __funnelshift_r(b[i - 1], b[i], ashift);
+                            if (FIVE) {
+                                T[0] += __vsadu4(x[i], 0x80808080u);
+                                T[3] += __vsadu4(__vabsdiffu4(x[i], __vhaddu4(a, b[i])), 0x80808080u);
+                            }
+                            T[1] += __vsadu4(__vabsdiffu4(x[i], a), 0x80808080u);
+                            T[2] += __vsadu4(__vabsdiffu4(x[i], b[i]), 0x80808080u);
+                            T[4] += __vsadu4(__vabsdiffu4(x[i], paeth_pred4(a, b[i], c)), 0x80808080u);
+                        }
+                    }
+                }
+            };
+            using std::true_type; using std::false_type;
+            if (ashift == 0) { if (fast) score4(true_type{}, false_type{}); else score4(true_type{}, true_type{}); }
+            else { if (fast) score4(false_type{}, false_type{}); else score4(false_type{}, true_type{}); }
+            // the up-to-three whole words after the last vector, and the ragged last word
             if (fast) {
-                for (uint32_t k = tid; k < full; k += PNG_THREADS) score(k, 0xFFFFFFFFu, false);
+                for (uint32_t k = nv * 4 + tid; k < full; k += PNG_THREADS) score(k, 0xFFFFFFFFu, false);
                 if (full < nw && tid == (int)(full % PNG_THREADS)) score(full, tailmask, false);
             } else {
-                for (uint32_t k = tid; k < full; k += PNG_THREADS) score(k, 0xFFFFFFFFu, true);
+                for (uint32_t k = nv * 4 + tid; k < full; k += PNG_THREADS) score(k, 0xFFFFFFFFu, true);
                 if (full < nw && tid == (int)(full % PNG_THREADS)) score(full, tailmask, true);
             }
 #pragma unroll
             for (int f = 0; f < 5; ++f) {
-                uint32_t v = T[f];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                const uint32_t v = __reduce_add_sync(0xffffffffu, T[f]);   // REDUX: one instruction per score
                 if (lane == 0) red[f][warp] = v;
             }
             __syncthreads();
