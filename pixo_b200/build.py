@@ -2,8 +2,10 @@
 
 The library is compiled for exactly one target: -gencode arch=compute_100a,code=sm_100a.
 `-fmad=false` keeps the compiler from contracting the reference's separate multiply/add steps
-into FMAs (the DCT must round after every operation); the few FMAs the quantiser needs are
-written explicitly with __fmaf_rn.
+into FMAs (the DCT must round after every operation); the FMAs the quantiser's exact division
+needs are written explicitly as PTX `fma.rn.f32x2` (and products that feed an add as
+`fma(x, c, +0)`, because ptxas contracts `mul.f32x2` + `add.f32x2` even under --fmad=false: see
+DESIGN.md section 3).
 """
 from __future__ import annotations
 

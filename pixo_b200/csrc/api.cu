@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -787,15 +788,24 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
     PIXO_CUDA(ctx, cudaEventRecord(ev_out[0], ctx->stream));
     PIXO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev_out[0], 0));
     PIXO_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ev_out[0], 0));
+    const bool dbg = getenv("PIXO_B200_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = dbg ? now() : 0;
     PIXO_TRY(upload(0));
+    const double t1 = dbg ? now() : 0;
     for (uint32_t gi = 0; gi < ngroups; ++gi) {
         if (gi + 1 < ngroups) PIXO_TRY(upload(gi + 1));
         PIXO_TRY(compute(gi));
         if (gi > 0) PIXO_TRY(finish(gi - 1));
     }
+    const double t2 = dbg ? now() : 0;
     PIXO_TRY(finish(ngroups - 1));
+    const double t3 = dbg ? now() : 0;
     PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
     PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (dbg)
+        fprintf(stderr, "encode_frames n=%u: upload(0) queued %.0f us, compute queued %.0f us, last finish %.0f us, drain %.0f us\n",
+                n_images, t1 - t0, t2 - t1, t3 - t2, now() - t3);
     drain.armed = false;
     return 0;
 }

@@ -80,6 +80,14 @@ struct EntParams {
     uint32_t *overflow;            // [n] bit 0: out_cap was exceeded (out_len = the size needed); bit 1: a chain timed out
 };
 
+#ifndef HUFF_EMIT_V
+#define HUFF_EMIT_V 1      // 0: byte stores (round 1); 1: aligned word stores
+#endif
+#ifndef HUFF_ZRL_SPLIT
+#define HUFF_ZRL_SPLIT 0   // 1: a second copy of the symbol loop without the ZRL test for warps that need none
+                           // (measured: 706 -> 727 us per 32 4K frames - the mask test and the larger code cost more than the
+                           // four instructions per symbol save)
+#endif
 constexpr int CB = 32;             // blocks per chunk == one warp
 static_assert(CB * 4 == 128, "the slot word stride is spelled out in code_block's PTX");
 constexpr int HUFF_WARPS = 4;      // warps per CTA (they only share the tables)
@@ -457,18 +465,27 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             diff = (int)(int16_t)(dc - prev_dc);
             // does a non-zero coefficient follow 16 or more zeros (a ZRL symbol)?  position 0 (DC)
             // bounds the first run; a8 bit i = positions i..i+15 all zero
+#if HUFF_ZRL_SPLIT
             const unsigned long long N = ((unsigned long long)M1 << 32) | M0 | 1ull;
             unsigned long long a = ~N & (~N >> 1);
             a &= a >> 2; a &= a >> 4; a &= a >> 8;
             zrl_here = ((a << 16) & N) != 0;
+#endif
         }
+#if HUFF_ZRL_SPLIT
         const bool any_zrl = __any_sync(0xffffffffu, zrl_here);   // uniform: which symbol loop the warp runs
+#endif
+        (void)zrl_here;
         if (s < iend) {
             const uint32_t sa_ac = (uint32_t)__cvta_generic_to_shared(&T.ac[tbl][0]);
             const uint32_t sa_slot = (uint32_t)__cvta_generic_to_shared(slot) + 4u * lane;
             uint32_t acc;
+#if HUFF_ZRL_SPLIT
             if (any_zrl) L = code_block<false, true>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill[buf], &acc);
             else L = code_block<false, false>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill[buf], &acc);
+#else
+            L = code_block<false, true>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill[buf], &acc);
+#endif
             if (L > SLOT_W * 32u)  // long block: run again, keeping the words past the slot in local memory
                 L = code_block<true, true>(M0, M1, diff, T.dc[tbl], sa_ac, sa_stage, sa_slot, spill[buf], &acc);
             asm volatile("" ::: "memory");  // slot words were written through st.shared
@@ -522,40 +539,20 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         // range land outside the part of sbuf that is copied out); sbuf index 16 + shb is
         // the chunk's first owned byte of this window.
         if (32 * lane < b) {
-            // The lane's 32 bytes go to sbuf at an arbitrary byte offset.  Words without a 0xFF are
-            // written as whole, ALIGNED words: up to 3 head bytes, then each word merged with the
-            // unwritten tail of its predecessor by one funnel shift (pend = the last `np` bytes not
-            // yet stored, kept in the top of `prev`); a word holding 0xFF first drains the pending
-            // bytes and is expanded byte by byte (0xFF -> 0xFF 0x00).  7 word + ~4 byte stores per
-            // lane instead of 32 byte stores (which were 25 % of the kernel's shared-memory wavefronts).
             uint32_t dst = 16u + shb + (uint32_t)(32 * lane) - (uint32_t)a + ffb;
-            uint32_t prev = 0, np = 0;   // prev: previous little-endian word; its top np bytes are pending at dst
+#if HUFF_EMIT_V == 0
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const uint32_t w = wv[j];
                 if (ff_bytes(w) == 0) {
-                    const uint32_t m = __byte_perm(w, 0, 0x0123);   // memory order
-                    if (np == 0) {
-                        const uint32_t al = dst & 3u;
-                        if (al == 0) {
-                            *reinterpret_cast<uint32_t *>(sbuf + dst) = m;
-                            dst += 4;
-                        } else {             // head: 4 - al bytes singly, the other al bytes wait in prev
-                            sbuf[dst] = (uint8_t)m;
-                            if (al < 3) sbuf[dst + 1] = (uint8_t)(m >> 8);
-                            if (al < 2) sbuf[dst + 2] = (uint8_t)(m >> 16);
-                            dst += 4u - al;
-                            np = al;
-                            prev = m;
-                        }
-                    } else {                 // dst is aligned: np pending bytes + 4 - np new ones
-                        *reinterpret_cast<uint32_t *>(sbuf + dst) = __funnelshift_r(prev, m, 32u - 8u * np);
-                        dst += 4;
-                        prev = m;
+                    if ((dst & 3u) == 0) {
+                        *reinterpret_cast<uint32_t *>(sbuf + dst) = __byte_perm(w, 0, 0x0123);
+                    } else {
+                        sbuf[dst] = (uint8_t)(w >> 24); sbuf[dst + 1] = (uint8_t)(w >> 16);
+                        sbuf[dst + 2] = (uint8_t)(w >> 8); sbuf[dst + 3] = (uint8_t)w;
                     }
+                    dst += 4;
                 } else {
-                    for (uint32_t i = 0; i < np; ++i) sbuf[dst++] = (uint8_t)(prev >> (8u * (4u - np + i)));
-                    np = 0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t byte = (w >> (24 - 8 * i)) & 0xFFu;
@@ -564,7 +561,50 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
                     }
                 }
             }
-            for (uint32_t i = 0; i < np; ++i) sbuf[dst + i] = (uint8_t)(prev >> (8u * (4u - np + i)));
+#else
+            // A lane without a 0xFF among its 32 bytes (all of them on smooth content, ~7 of 8 on
+            // noise) writes them as ALIGNED words whatever its byte offset: word k = the tail of
+            // little-endian word k-1 and the head of word k (one funnel shift), plus at most three
+            // single bytes at either end - all predicated, the same instruction sequence in every
+            // lane.  7 word + <= 6 byte stores instead of 32 byte stores (which were 25 % of the
+            // kernel's shared-memory wavefronts).  A lane that holds a 0xFF goes byte by byte.
+            uint32_t anyff = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) anyff |= ff_bytes(wv[j]);
+            if (anyff == 0) {
+                uint32_t m[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = __byte_perm(wv[j], 0, 0x0123);   // memory order
+                const uint32_t al = dst & 3u, sh8 = 8u * al;
+                uint8_t *base = sbuf + (dst - al);                 // aligned
+                uint32_t *wbase = reinterpret_cast<uint32_t *>(base);
+#pragma unroll
+                for (int k = 1; k < 8; ++k) wbase[k] = __funnelshift_l(m[k - 1], m[k], sh8);
+                if (al == 0) {
+                    wbase[0] = m[0];
+                } else {
+                    // head: bytes al..3 of word 0 <- the low 4 - al bytes of m[0]
+                    base[3] = (uint8_t)(m[0] >> (24u - sh8));
+                    if (al < 3) base[2] = (uint8_t)(m[0] >> (16u - sh8));
+                    if (al < 2) base[1] = (uint8_t)m[0];
+                    // tail: bytes 0..al-1 of word 8 <- the top al bytes of m[7]
+                    base[32] = (uint8_t)(m[7] >> (32u - sh8));
+                    if (al > 1) base[33] = (uint8_t)(m[7] >> (40u - sh8));
+                    if (al > 2) base[34] = (uint8_t)(m[7] >> 24);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t w = wv[j];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t byte = (w >> (24 - 8 * i)) & 0xFFu;
+                        sbuf[dst++] = (uint8_t)byte;
+                        if (byte == 0xFFu) sbuf[dst++] = 0;
+                    }
+                }
+            }
+#endif
         }
         __syncwarp();
         if (mk) {  // 0xFF 0xDn, not subject to stuffing; after the barrier: the last lane's spare bytes land here too

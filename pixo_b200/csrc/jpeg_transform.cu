@@ -322,7 +322,7 @@ struct QPairTab {
 // (A warp-uniform run-time index into the constant bank is no alternative: ptxas then emits
 // per-thread LDC.64 c[0x0][R+imm] into vector registers, even when the index comes from a vote.)
 #ifndef K_QMODE
-#define K_QMODE 2
+#define K_QMODE 0   // measured (32 x 4K, us per launch): mode 0 371, mode 2 378, mode 1 388
 #endif
 struct QuantSmem {
     QPair t[2][32];

@@ -10,14 +10,22 @@
 //   filter_row / apply_filters*     src/png/filter.rs:64-206,529-608
 //   adler32                         src/compress/adler32.rs:26-47
 //
-// Design (B200): one CTA per image row.  The raw row and the raw previous row are staged in
-// shared memory with 128-bit loads (previous row comes from L2: it is the neighbouring CTA's
-// current row, so HBM sees each raw byte once); every thread evaluates all candidate filters on
-// 4-byte words (SWAR + dp4a scoring), the CTA reduces the five scores, replays the reference's
-// decision ladder, re-derives only the winning filter from the staged rows and writes
-// `type byte + row` with aligned word stores.  The row's Adler-32 contribution
-// (A = sum d, B = sum (n-i) d, position-weighted to the end of the image) is accumulated in the
-// same pass; the last CTA of an image folds the accumulators into the checksum.
+// Design (B200): two kernels.
+//   k_png_band (the default): a CTA walks a band of 16 consecutive rows with a 3-deep ring of row
+//     buffers in shared memory (previous / current / next, filled by 16-byte cp.async), so every
+//     raw byte is read from HBM once and the next row streams in under the current row's
+//     arithmetic.  Candidates are scored on 4-byte words, four consecutive words per thread
+//     (|i8(x - pred)| = 128 - ||x - pred| - 128|: two VABSDIFF4 per candidate; Paeth is a
+//     23-instruction byte-SIMD predictor), the five scores are reduced (REDUX + one shared-memory
+//     step), the reference's decision ladder is replayed, only the winner is re-derived, shifted to
+//     the output stream's byte phase and written as aligned words.  The row's Adler-32 contribution
+//     (A = sum d, B = sum (n-i) d, position-weighted to the end of the image) rides along; the last
+//     CTA of an image folds the accumulators into the checksum.
+//   k_png_filter (one CTA per row, rows staged in 32 KB segments): Bigrams (65 536-bit "seen"
+//     bitmaps per candidate), the sticky small-image AdaptiveFast rule, and rows too long for three
+//     shared-memory buffers.
+// A band of rows of a taller image (one image over several GPUs) takes the raw row above it as an
+// extra input (`above`); nothing else crosses a band.
 #include <type_traits>
 
 #include "common.cuh"

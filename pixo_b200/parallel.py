@@ -116,7 +116,10 @@ class DeviceBandCoder:
 
     def histogram(self, seed: np.ndarray):
         """536 counters of this band (torch int64 on the device, ready for all_reduce)."""
-        hist = self.torch.zeros(536, dtype=self.torch.int64, device=self.dev)
+        # (the library clears the counters itself, on ITS stream: a torch-side fill could land after it)
+        hist = self.torch.empty(536, dtype=self.torch.int64, device=self.dev)
+        if not self.ny:
+            hist.zero_()
         if self.ny:
             s = (C.c_int32 * 3)(*[int(v) for v in seed])
             _lib.check(self.ctx.handle, self.lib.pixo_b200_jpeg_band_histogram_dev(

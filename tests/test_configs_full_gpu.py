@@ -47,6 +47,7 @@ def test_c5_full_batch_64x4k_rgba(po, gpu_ctx):
     out_stride = h * (rb + 1)
     d_out = torch.empty((n, out_stride), dtype=torch.uint8, device=dev)
     d_ad = torch.zeros(n, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()   # torch fills ran on torch's stream; the library has its own
     for strat, code in (("adaptive", po.F_ADAPTIVE), ("fast", po.F_ADAPTIVE_FAST)):
         rc = lib.pixo_b200_png_filter_dev(gpu_ctx.handle, d_in.data_ptr(), h * rb, n, w, h, rb, bpp, code,
                                           d_out.data_ptr(), out_stride, d_ad.data_ptr())
@@ -89,6 +90,7 @@ def test_offsets_beyond_4_gib(po, gpu_ctx):
     d_scan = torch.empty((n, cap), dtype=torch.uint8, device=dev)
     d_len = torch.zeros(n, dtype=torch.int64, device=dev)
     d_ovf = torch.zeros(n, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()   # torch fills ran on torch's stream; the library has its own
     _lib.check(gpu_ctx.handle, lib.pixo_b200_jpeg_encode_dev(gpu_ctx.handle, d_px.data_ptr(), w * h * 3, n, w, h, 2, 80, 1,
                                                              d_scan.data_ptr(), cap, d_len.data_ptr(), d_ovf.data_ptr()))
     gpu_ctx.sync()
@@ -111,6 +113,7 @@ def test_offsets_beyond_4_gib(po, gpu_ctx):
     assert d_in.numel() > 1 << 32
     d_out = torch.empty((n, h * (rb + 1)), dtype=torch.uint8, device=dev)
     d_ad = torch.zeros(n, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
     _lib.check(gpu_ctx.handle, lib.pixo_b200_png_filter_dev(gpu_ctx.handle, d_in.data_ptr(), h * rb, n, w, h, rb, bpp,
                                                             po.F_ADAPTIVE, d_out.data_ptr(), h * (rb + 1), d_ad.data_ptr()))
     gpu_ctx.sync()

@@ -31,6 +31,7 @@ def _device_coders(ctx, frame, w, h, ct, ss, q, world):
         if bh:
             px = torch.from_numpy(np.ascontiguousarray(parallel.band_pixels(frame, w, h, ch, b)).reshape(-1)).to(dev)
             keep.append(px)
+            torch.cuda.synchronize(dev)   # torch's stream is not the context's
             rc = lib.pixo_b200_jpeg_coefficients_dev(ctx.handle, px.data_ptr(), px.numel(), 1, w, bh, ct, ss,
                                                      lq.ctypes.data_as(_lib.f32p), cq.ctypes.data_as(_lib.f32p),
                                                      d_y.data_ptr(), ny * 64, d_cb.data_ptr(), d_cr.data_ptr(), nc * 64, 0, None)
@@ -137,6 +138,7 @@ def test_png_rows_in_bands_with_adler_combine(po, gpu_ctx, strategy):
         above = d_img[r0 - 1].contiguous() if r0 else None
         d_out = torch.empty((r1 - r0) * (rb + 1), dtype=torch.uint8, device=dev)
         d_ad = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
         png.apply_filters_rows_dev(rows, above, w, h, r1 - r0, rb, bpp, strat, d_out, d_ad, ctx=gpu_ctx)
         gpu_ctx.sync()
         outs.append(d_out.cpu().numpy())
