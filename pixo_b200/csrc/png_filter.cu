@@ -484,6 +484,21 @@ struct BandParams {
 };
 
 
+// explicit shared-space loads with 32-bit addresses: the ring's row buffers are picked by r % 3, and
+// through generic pointers the compiler emits LD.E with 64-bit address arithmetic for every operand
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+
 __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
@@ -503,6 +518,7 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
     const uint32_t rb = P.row_bytes;
     const uint32_t pitch = 16 + ((rb + 15) & ~15u) + 16;   // [16 B zero halo][row][slack]
     uint8_t *bufs[3] = {smem, smem + pitch, smem + 2 * pitch};
+    const uint32_t smem_u = (uint32_t)__cvta_generic_to_shared(smem);
     const uint8_t *image = P.data + (size_t)img * P.in_stride;
     const uint8_t *lo_b = image, *hi_b = image + (size_t)P.height * rb;
     const uint32_t r0 = blockIdx.x * BAND_ROWS;
@@ -550,15 +566,15 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the newest group
         __syncthreads();
-        const uint32_t *c32 = reinterpret_cast<const uint32_t *>(bufs[r % 3]) + 4;
-        const uint32_t *p32 = reinterpret_cast<const uint32_t *>(bufs[(r + 2) % 3]) + 4;
+        const uint32_t cs = smem_u + (r % 3) * pitch + 16u;          // shared address of the row's word 0
+        const uint32_t ps = smem_u + ((r + 2) % 3) * pitch + 16u;    // ... of the row above
 
         // words before `full` hold four row bytes; the last word's missing bytes are masked off
         const uint32_t full = rb >> 2;
         const uint32_t tailmask = (rb & 3u) ? (0xFFFFFFFFu >> (8 * (4 - (rb & 3u)))) : 0u;
         auto operands = [&](uint32_t k, uint32_t &x, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &mask) {
-            x = c32[k]; b = p32[k];
-            uint32_t xl = c32[(int)k - 1], bl = p32[(int)k - 1];
+            x = lds32(cs + 4u * k); b = lds32(ps + 4u * k);
+            uint32_t xl = lds32(cs + 4u * k - 4u), bl = lds32(ps + 4u * k - 4u);
             if (OA) {
                 x = zero_transparent<OA ? OA : 4>(x); b = zero_transparent<OA ? OA : 4>(b);
                 xl = zero_transparent<OA ? OA : 4>(xl); bl = zero_transparent<OA ? OA : 4>(bl);
@@ -592,16 +608,15 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
             const uint32_t nv = full >> 2;
             auto score4 = [&](auto a0tag, auto fivetag) {
                 constexpr bool A0 = decltype(a0tag)::value, FIVE = decltype(fivetag)::value;
-                const uint4 *c4 = reinterpret_cast<const uint4 *>(c32), *p4 = reinterpret_cast<const uint4 *>(p32);
                 for (uint32_t vb = (uint32_t)tid & ~31u; vb < nv; vb += PNG_THREADS) {
                     const uint32_t v = vb + lane;
                     const bool valid = v < nv;
                     const uint32_t vv = valid ? v : nv - 1;
-                    const uint4 X4 = c4[vv], B4 = p4[vv];
+                    const uint4 X4 = lds128(cs + 16u * vv), B4 = lds128(ps + 16u * vv);
                     uint32_t x[5] = {0, X4.x, X4.y, X4.z, X4.w}, b[5] = {0, B4.x, B4.y, B4.z, B4.w};
                     x[0] = __shfl_up_sync(0xffffffffu, X4.w, 1);
                     b[0] = __shfl_up_sync(0xffffffffu, B4.w, 1);
-                    if (lane == 0) { x[0] = c32[4 * (int)vv - 1]; b[0] = p32[4 * (int)vv - 1]; }
+                    if (lane == 0) { x[0] = lds32(cs + 16u * vv - 4u); b[0] = lds32(ps + 16u * vv - 4u); }
                     if (OA) {
 #pragma unroll
                         for (int i = 0; i < 5; ++i) { x[i] = zero_transparent<OA ? OA : 4>(x[i]); b[i] = zero_transparent<OA ? OA : 4>(b[i]); }
