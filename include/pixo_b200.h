@@ -166,8 +166,10 @@ int pixo_b200_jpeg_encode_batch(pixo_b200_ctx *ctx, const uint8_t *pixels, size_
 /* Device-resident variant of the whole hot path (asynchronous on the context's stream):
  * frame i at d_pixels + i*pixel_stride -> entropy-coded scan bytes (what encode_scan appends
  * between the SOS header and EOI, src/jpeg/mod.rs:1408-1563) at d_scan + i*scan_cap_each, byte
- * count in d_scan_len[i] (the size needed, also when it did not fit); d_overflow[i] != 0 when
- * scan_cap_each was too small.  Baseline, standard Huffman tables, no restart interval.
+ * count in d_scan_len[i] (the size needed, also when it did not fit); d_overflow[i] != 0 when the
+ * frame was not finished: bit 0 scan_cap_each was too small, bit 1 a device fault (spin limit), bit 2 a
+ * segment of a frame that is coded in segments (few large frames) outgrew its internal buffer - does
+ * not happen for JPEGs smaller than their raw pixels; pixo_b200_jpeg_encode* handle all three.  Baseline, standard Huffman tables, no restart interval.
  * Headers/EOI are the caller's (pixo_b200_jpeg_encode* add them). */
 int pixo_b200_jpeg_encode_dev(pixo_b200_ctx *ctx, const uint8_t *d_pixels, size_t pixel_stride,
                               uint32_t n_images, uint32_t width, uint32_t height,

@@ -333,7 +333,7 @@ void pixo_b200_ctx_destroy(pixo_b200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    Scratch *dev[] = {&ctx->d_in, &ctx->d_y, &ctx->d_cb, &ctx->d_cr, &ctx->d_misc, &ctx->d_out, &ctx->d_ent, &ctx->d_coef, &ctx->d_retry};
+    Scratch *dev[] = {&ctx->d_in, &ctx->d_y, &ctx->d_cb, &ctx->d_cr, &ctx->d_misc, &ctx->d_out, &ctx->d_ent, &ctx->d_coef, &ctx->d_retry, &ctx->d_raw};
     for (Scratch *s : dev) if (s->ptr) cudaFree(s->ptr);
     Scratch *host[] = {&ctx->h_in, &ctx->h_out, &ctx->h_misc};
     for (Scratch *s : host) if (s->ptr) cudaFreeHost(s->ptr);
@@ -777,30 +777,41 @@ static int encode_frames(pixo_b200_ctx *ctx, const uint8_t *pixels, size_t len_e
             uint8_t *o = out + (size_t)img * out_cap_each;
             const HuffTables &t = tb[optimize ? k : 0];
             bool done = false;
-            if (h_ovf[k] == 1 && ctx->gpu_retry) {  // capacity only: the kernel reported the size it needs
-                const size_t need = (size_t)h_len[k];
-                if (hdr[k] + need + 2 > out_cap_each)
-                    return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small (need %zu)",
-                                     out_cap_each, hdr[k] + need + 2);
-                const uint64_t cap2 = align_up(need + 64, 256);
-                PIXO_TRY(ensure_dev(ctx, ctx->d_retry, cap2 + ent_one + 256));
-                auto *rbuf = reinterpret_cast<uint8_t *>(ctx->d_retry.ptr);
-                uint64_t *d_len = nullptr;
-                uint32_t *d_ovf = nullptr;
-                PIXO_TRY(launch_jpeg_entropy(ctx, c.y + (size_t)k * cstride, cstride, c.cb + (size_t)k * cstride,
-                                             c.cr + (size_t)k * cstride, cstride, 1, g, t, restart_interval,
-                                             rbuf + cap2, rbuf, cap2, &d_len, &d_ovf));
-                uint64_t len2 = 0;
-                uint32_t ovf2 = 0;
-                PIXO_CUDA(ctx, cudaMemcpyAsync(&len2, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
-                PIXO_CUDA(ctx, cudaMemcpyAsync(&ovf2, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
-                PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                if (!ovf2 && len2 == need) {
-                    PIXO_CUDA(ctx, cudaMemcpyAsync(o + hdr[k], rbuf, need, cudaMemcpyDeviceToHost, ctx->stream));
+            // bit 0: the scan did not fit (the kernel reported the size it needs); bit 2: a segment's raw
+            // string did not fit its share - either way code the frame again on the GPU, unsegmented, with
+            // enough room.  Bit 1 (a faulted chain) goes to the host coder.
+            if (!(h_ovf[k] & 2u) && ctx->gpu_retry) {
+                size_t need = (h_ovf[k] & 4u) ? (size_t)scan_cap * 2 : (size_t)h_len[k];
+                for (int attempt = 0; attempt < 3 && !done; ++attempt) {
+                    if (hdr[k] + need + 2 > out_cap_each && !(h_ovf[k] & 4u))
+                        return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small (need %zu)",
+                                         out_cap_each, hdr[k] + need + 2);
+                    const uint64_t cap2 = align_up(need + 64, 256);
+                    PIXO_TRY(ensure_dev(ctx, ctx->d_retry, cap2 + ent_one + 256));
+                    auto *rbuf = reinterpret_cast<uint8_t *>(ctx->d_retry.ptr);
+                    uint64_t *d_len = nullptr;
+                    uint32_t *d_ovf = nullptr;
+                    ctx->no_segments = true;
+                    const int rc = launch_jpeg_entropy(ctx, c.y + (size_t)k * cstride, cstride, c.cb + (size_t)k * cstride,
+                                                       c.cr + (size_t)k * cstride, cstride, 1, g, t, restart_interval,
+                                                       rbuf + cap2, rbuf, cap2, &d_len, &d_ovf);
+                    ctx->no_segments = false;
+                    PIXO_TRY(rc);
+                    uint64_t len2 = 0;
+                    uint32_t ovf2 = 0;
+                    PIXO_CUDA(ctx, cudaMemcpyAsync(&len2, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                    PIXO_CUDA(ctx, cudaMemcpyAsync(&ovf2, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
                     PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                    o[hdr[k] + need] = 0xFF;
-                    o[hdr[k] + need + 1] = 0xD9;
-                    out_lens[img] = hdr[k] + need + 2;
+                    if (ovf2 & 2u) break;
+                    if (ovf2) { need = (size_t)len2; continue; }
+                    if (hdr[k] + (size_t)len2 + 2 > out_cap_each)
+                        return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small (need %zu)",
+                                         out_cap_each, hdr[k] + (size_t)len2 + 2);
+                    PIXO_CUDA(ctx, cudaMemcpyAsync(o + hdr[k], rbuf, (size_t)len2, cudaMemcpyDeviceToHost, ctx->stream));
+                    PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                    o[hdr[k] + len2] = 0xFF;
+                    o[hdr[k] + len2 + 1] = 0xD9;
+                    out_lens[img] = hdr[k] + (size_t)len2 + 2;
                     done = true;
                 }
             }
@@ -1010,9 +1021,14 @@ int pixo_b200_jpeg_entropy_encode_dev(pixo_b200_ctx *ctx, const int16_t *d_y, co
         PIXO_CUDA(ctx, cudaMemcpyAsync(h_len, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
         PIXO_CUDA(ctx, cudaMemcpyAsync(h_ovf, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
         PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->no_segments = false;
         if (!*h_ovf) break;
-        if (*h_ovf != 1 || attempt)
+        if ((*h_ovf & 2u) || attempt >= 2)
             return set_error(ctx, PIXO_B200_ERR_CUDA, "device entropy stage did not finish (flags %u)", *h_ovf);
+        if (*h_ovf & 4u) {   // a segment outgrew its share: once more, unsegmented
+            ctx->no_segments = true;
+            continue;
+        }
         if (hdr + (size_t)*h_len + 2 > out_cap)
             return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "output capacity %zu too small (need %zu)", out_cap,
                              hdr + (size_t)*h_len + 2);
@@ -1080,19 +1096,29 @@ int pixo_b200_jpeg_band_entropy_dev(pixo_b200_ctx *ctx, const int16_t *d_y, cons
     tables_from(hist, g.has_chroma, t);
     PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
     PIXO_TRY(ensure_dev(ctx, ctx->d_ent, entropy_scratch_bytes(1, g, 0)));
-    PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, 256));
     uint64_t *d_len = nullptr, *d_tail = nullptr;
     uint32_t *d_ovf = nullptr;
     PIXO_TRY(launch_jpeg_entropy(ctx, d_y, 0, d_cb, d_cr, 0, 1, g, t, 0, reinterpret_cast<uint8_t *>(ctx->d_ent.ptr),
                                  d_raw, raw_cap, &d_len, &d_ovf, dc_seed, &d_tail));
+    // (a long band is coded as several segments - see k_seg_* -: their bit counts add up, the band's
+    // tail is its last non-empty segment's)
+    const uint32_t S = ctx->band_segments;
+    PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, (size_t)S * 20 + 256));
     auto *h = reinterpret_cast<uint64_t *>(ctx->h_misc.ptr);
-    PIXO_CUDA(ctx, cudaMemcpyAsync(h, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    PIXO_CUDA(ctx, cudaMemcpyAsync(h + 1, d_tail, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    PIXO_CUDA(ctx, cudaMemcpyAsync(h + 2, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(h, d_len, (size_t)S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(h + S, d_tail, (size_t)S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PIXO_CUDA(ctx, cudaMemcpyAsync(h + 2 * S, d_ovf, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
     PIXO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const uint32_t ovf = *reinterpret_cast<uint32_t *>(h + 2);
-    *nbits = h[0];
-    *tail7 = (uint32_t)h[1] & 0x7Fu;
+    uint32_t ovf = 0;
+    uint64_t total = 0, tail = 0;
+    for (uint32_t q = 0; q < S; ++q) {
+        ovf |= reinterpret_cast<uint32_t *>(h + 2 * S)[q];
+        total += h[q];
+        if (h[q]) tail = h[S + q];
+    }
+    h[0] = total;
+    *nbits = total;
+    *tail7 = (uint32_t)tail & 0x7Fu;
     if (ovf & 2) return set_error(ctx, PIXO_B200_ERR_CUDA, "device entropy stage did not finish (flags %u)", ovf);
     if (ovf) return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "raw capacity %zu too small (need %llu)", raw_cap,
                               (unsigned long long)((h[0] + 7) / 8));
@@ -1110,8 +1136,12 @@ int pixo_b200_jpeg_band_splice_dev(pixo_b200_ctx *ctx, const uint8_t *d_raw, uin
     PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, 256));
     uint64_t *d_len = nullptr;
     uint32_t *d_ovf = nullptr;
-    PIXO_TRY(launch_splice(ctx, d_raw, nbits, (uint32_t)(start_bit & 7), tail_in, is_last_band != 0,
-                           reinterpret_cast<uint8_t *>(ctx->d_misc.ptr), d_out, out_cap, &d_len, &d_ovf));
+    if (ctx->band_segments > 1)   // the band was coded in segments; their raw strings are in the context
+        PIXO_TRY(launch_band_splice_segments(ctx, start_bit, tail_in, is_last_band != 0,
+                                             reinterpret_cast<uint8_t *>(ctx->d_misc.ptr), d_out, out_cap, &d_len, &d_ovf));
+    else
+        PIXO_TRY(launch_splice(ctx, d_raw, nbits, (uint32_t)(start_bit & 7), tail_in, is_last_band != 0,
+                               reinterpret_cast<uint8_t *>(ctx->d_misc.ptr), d_out, out_cap, &d_len, &d_ovf));
     auto *h = reinterpret_cast<uint64_t *>(ctx->h_misc.ptr);
     PIXO_CUDA(ctx, cudaMemcpyAsync(h, d_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
     PIXO_CUDA(ctx, cudaMemcpyAsync(h + 1, d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -71,11 +71,16 @@ struct pixo_b200_ctx {
     bool gpu_retry = true;         // re-run k_huff with the exact size when the heuristic was too small
     std::string err;
     // reusable scratch (device + pinned host)
-    pixo::Scratch d_in, d_y, d_cb, d_cr, d_misc, d_out, d_ent, d_coef, d_retry;
+    pixo::Scratch d_in, d_y, d_cb, d_cr, d_misc, d_out, d_ent, d_coef, d_retry, d_raw;
     pixo::Scratch h_in, h_out, h_misc;
     std::vector<cudaEvent_t> events;
     std::vector<cudaEvent_t> stage_events;  // one per pinned staging slot of h2d_copy
     pixo::HostPool *pool = nullptr;         // see HostPool
+    bool no_segments = false;               // entropy stage: never cut images into segments (retry path)
+    // the segmentation of the band coded last by pixo_b200_jpeg_band_entropy_dev (its raw strings sit in d_raw)
+    uint32_t band_segments = 1, band_bpm = 0, band_geo_y_per_mcu = 1;
+    bool band_has_chroma = true;
+    uint64_t band_cap = 0, band_mcus = 0;
 };
 
 namespace pixo {
@@ -127,6 +132,9 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
                         uint64_t out_cap, uint64_t **d_out_len, uint32_t **d_overflow,
                         const int *dc_seed = nullptr, uint64_t **d_raw_tail = nullptr);
 size_t splice_scratch_bytes(uint64_t nbits);
+int launch_band_splice_segments(pixo_b200_ctx *ctx, uint64_t base_bit, uint32_t base_tail, bool last,
+                                uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap, uint64_t **d_out_len,
+                                uint32_t **d_overflow);
 int launch_splice(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t nbits, uint32_t phase, uint32_t tail_in,
                   bool last, uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap, uint64_t **d_out_len,
                   uint32_t **d_overflow);

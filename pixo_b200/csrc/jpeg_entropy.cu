@@ -74,6 +74,12 @@ struct EntParams {
     uint8_t *out;                  // [n][out_cap]
     uint64_t out_cap;
     uint64_t *out_len;             // [n] final byte count
+    // RAW + segments: every image is cut into seg_per_img runs of whole MCUs, each coded as a bit
+    // string of its own ("pseudo image" q = image * seg_per_img + segment: status words, raw buffer,
+    // bit count and tail are all indexed by q); k_seg_* splice them afterwards.  0/1 = not segmented.
+    uint32_t seg_per_img;
+    uint32_t nblocks_last;         // blocks of an image's last segment (the others have nblocks)
+    size_t seg_y_stride, seg_c_stride;   // int16 elements between the segments of an image
     int dc_seed[3];                // DC predictors (Y, Cb, Cr) before block 0: 0 for a whole image, the previous
                                    // band's last DCs when the arrays are one band of a frame tiled over several GPUs
     unsigned long long *out_tail;  // RAW only: [n] the stream's last 7 bits
@@ -352,6 +358,7 @@ struct ChunkState {
     uint32_t ffb;          // 0xFF bytes before this lane's piece of the kept window
     bool kept;             // uniform: phase A left the assembled (single) window in the slot buffer
     bool fault;
+    bool skip;             // uniform: the chunk lies past the end of a short last segment: nothing to do
 };
 
 // Persistent kernel; every WARP works on its own: it draws chunks of 32 blocks from the ticket
@@ -398,19 +405,31 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         // the chunk's place: with a restart interval every interval is its own bit stream
         // (handle_restart, src/jpeg/mod.rs:1423-1445) and is cut into chunks separately
         uint32_t s0, iend, interval = 0;
+        uint32_t nblk = P.nblocks;
+        size_t y_off = (size_t)C.img * P.y_stride, c_off = (size_t)C.img * P.c_stride;
+        bool seg_prev = false;     // block 0 continues the previous segment's DC chain
+        if (RAW && P.seg_per_img > 1) {
+            const uint32_t ii = C.img / P.seg_per_img, seg = C.img - ii * P.seg_per_img;
+            y_off = (size_t)ii * P.y_stride + (size_t)seg * P.seg_y_stride;
+            c_off = (size_t)ii * P.c_stride + (size_t)seg * P.seg_c_stride;
+            if (seg == P.seg_per_img - 1) nblk = P.nblocks_last;
+            seg_prev = seg != 0;
+        }
+        C.skip = false;
         if (P.rst_blocks) {
             interval = C.chunk / P.cpi;
             const uint32_t sub = C.chunk - interval * P.cpi;
             s0 = interval * P.rst_blocks + sub * CB;
-            iend = (uint32_t)min((unsigned long long)(interval + 1) * P.rst_blocks, (unsigned long long)P.nblocks);
+            iend = (uint32_t)min((unsigned long long)(interval + 1) * P.rst_blocks, (unsigned long long)nblk);
             C.first = sub == 0;
         } else {
             s0 = C.chunk * CB;
-            iend = P.nblocks;
+            iend = nblk;
             C.first = C.chunk == 0;
         }
+        if (s0 >= iend) { C.skip = true; return; }   // short last segment: no such chunk
         C.last = s0 + CB >= iend;
-        C.final_ = C.last && iend == P.nblocks;
+        C.final_ = C.last && iend == nblk;
         C.marker = (C.last && !C.final_) ? 0xD0u + (interval & 7u) : 0u;
         const uint32_t s = s0 + lane;
         const int nv = (int)min((uint32_t)CB, iend - s0);
@@ -426,12 +445,13 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             const int16_t *arr;
             size_t idx;
             int seed;
-            if (k < P.y_per_mcu) { arr = P.y + (size_t)C.img * P.y_stride; idx = (size_t)m * P.y_per_mcu + k; tbl = 0; seed = P.dc_seed[0]; }
-            else if (k == P.y_per_mcu) { arr = P.cb + (size_t)C.img * P.c_stride; idx = m; tbl = 1; seed = P.dc_seed[1]; }
-            else { arr = P.cr + (size_t)C.img * P.c_stride; idx = m; tbl = 1; seed = P.dc_seed[2]; }
+            if (k < P.y_per_mcu) { arr = P.y + y_off; idx = (size_t)m * P.y_per_mcu + k; tbl = 0; seed = P.dc_seed[0]; }
+            else if (k == P.y_per_mcu) { arr = P.cb + c_off; idx = m; tbl = 1; seed = P.dc_seed[1]; }
+            else { arr = P.cr + c_off; idx = m; tbl = 1; seed = P.dc_seed[2]; }
             // DC predictors restart with the interval (src/jpeg/mod.rs:1433-1443)
             const bool dc_reset = P.rst_mcus && m % P.rst_mcus == 0 && (k == 0 || k >= P.y_per_mcu);
-            const int prev_dc = dc_reset ? 0 : (idx ? arr[(idx - 1) * 64] : seed);
+            // (a later segment's first block follows the previous segment's last one in the same array)
+            const int prev_dc = dc_reset ? 0 : ((idx || seg_prev) ? arr[((long long)idx - 1) * 64] : seed);
             const uint4 *src = reinterpret_cast<const uint4 *>(arr + idx * 64);
             uint32_t e0 = 0, e1 = 0;
             int dc;
@@ -749,6 +769,7 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
 
     // ---- A: bit offset from chain 1, then the chunk's 0xFF count into chain 2 ------------------------
     auto phase_a = [&](ChunkState &C) {
+        if (C.skip) return;
         unsigned long long *st1 = P.st_bits + (size_t)C.img * P.nchunks;
         unsigned long long *st2 = P.st_ff + (size_t)C.img * P.nchunks;
         if (!C.first) {
@@ -772,7 +793,7 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
     };
     // ---- B: stuffed-byte offset from chain 2, then the bytes ------------------------------------------
     auto phase_b = [&](ChunkState &C) {
-        if (RAW) return;
+        if (RAW || C.skip) return;
         unsigned long long *st2 = P.st_ff + (size_t)C.img * P.nchunks;
         unsigned long long ffx = 0;
         if (C.chunk) {
@@ -854,75 +875,6 @@ size_t entropy_scratch_bytes(uint32_t n, const FrameGeometry &g, uint32_t restar
 {
     const uint64_t bpm = g.y_per_mcu + (g.has_chroma ? 2 : 0);
     return plan_entropy(n, g.ny + 2 * g.nc, (uint64_t)restart_interval * bpm).total;
-}
-
-// Enqueue the entropy stage for n images (natural-order coefficient arrays) on ctx->stream.
-// d_scratch: entropy_scratch_bytes.  d_out: n * out_cap bytes of scan data; *d_out_len /
-// *d_overflow point into the scratch.
-int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride, const int16_t *d_cb,
-                        const int16_t *d_cr, size_t c_stride, uint32_t n, const FrameGeometry &g,
-                        const HuffTables &t, uint32_t restart_interval, uint8_t *d_scratch, uint8_t *d_out,
-                        uint64_t out_cap, uint64_t **d_out_len, uint32_t **d_overflow, const int *dc_seed,
-                        uint64_t **d_raw_tail)
-{
-    const bool raw = d_raw_tail != nullptr;
-    if (raw && restart_interval)
-        return set_error(ctx, PIXO_B200_ERR_UNSUPPORTED, "band-local raw coding does not take a restart interval");
-    if (raw && (out_cap & 3))
-        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "raw buffer capacity must be a multiple of 4");
-    const uint64_t nblocks = g.ny + 2 * g.nc;
-    const uint64_t bpm_ = g.y_per_mcu + (g.has_chroma ? 2 : 0);
-    uint64_t rst_blocks = (uint64_t)restart_interval * bpm_;
-    if (rst_blocks >= nblocks) rst_blocks = 0;  // a single interval: no marker is ever written
-    const EntropyPlan pl = plan_entropy(n, nblocks, rst_blocks);
-    if (nblocks > 0xFFFFFFFFull || (uint64_t)n * pl.nchunks > 0x7FFFFFFFull)
-        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "entropy stage: too many blocks per call");
-    EntParams P;
-    P.y = d_y; P.cb = d_cb; P.cr = d_cr; P.y_stride = y_stride; P.c_stride = c_stride;
-    P.bpm = g.y_per_mcu + (g.has_chroma ? 2 : 0);
-    P.y_per_mcu = g.y_per_mcu;
-    P.nblocks = (uint32_t)nblocks;
-    P.nchunks = (uint32_t)pl.nchunks;
-    P.rst_blocks = (uint32_t)rst_blocks;
-    P.rst_mcus = rst_blocks ? restart_interval : 0u;
-    P.cpi = rst_blocks ? (uint32_t)((rst_blocks + CB - 1) / CB) : 0u;
-    P.nimages = n;
-    P.st_bits = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_st1);
-    P.st_ff = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_st2);
-    P.ticket = reinterpret_cast<uint32_t *>(d_scratch + pl.off_ticket);
-    P.overflow = reinterpret_cast<uint32_t *>(d_scratch + pl.off_ovf);
-    P.out_len = reinterpret_cast<uint64_t *>(d_scratch + pl.off_outlen);
-    P.out = d_out; P.out_cap = out_cap;
-    P.out_tail = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_tail);
-    for (int k = 0; k < 3; ++k) P.dc_seed[k] = dc_seed ? dc_seed[k] : 0;
-    *d_out_len = P.out_len;
-    *d_overflow = P.overflow;
-    if (raw) *d_raw_tail = reinterpret_cast<uint64_t *>(P.out_tail);
-
-    HuffDev T;
-    memset(&T, 0, sizeof T);
-    for (int k = 0; k < 2; ++k) {
-        for (int cat = 0; cat < 12; ++cat)
-            if (t.len[k][cat])
-                T.dc[k][cat] = ((uint32_t)t.code[k][cat] << (32 - t.len[k][cat])) | (uint32_t)(t.len[k][cat] + cat);
-        for (int rs = 0; rs < 256; ++rs) {
-            const int cat = rs & 15, run = rs >> 4;
-            if (!t.len[2 + k][rs] || cat > 10) continue;
-            const uint32_t e = ((uint32_t)t.code[2 + k][rs] << (32 - t.len[2 + k][rs])) | (uint32_t)(t.len[2 + k][rs] + cat);
-            if (rs == 0x00) T.ac[k][AC_EOB] = e;
-            else if (rs == 0xF0) T.ac[k][AC_ZRL] = e;
-            else if (cat >= 1) T.ac[k][run * AC_STRIDE + cat - 1] = e;
-        }
-    }
-    cudaStream_t st = ctx->stream;
-    PIXO_CUDA(ctx, cudaMemsetAsync(d_scratch, 0, pl.zero_bytes, st));
-    const size_t want = ((size_t)n * pl.nchunks + HUFF_WARPS - 1) / HUFF_WARPS;
-    const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)ctx->sm_count * HUFF_CTAS_PER_SM);
-    if (raw) k_huff<true><<<grid, 32 * HUFF_WARPS, 0, st>>>(P, T);
-    else k_huff<false><<<grid, 32 * HUFF_WARPS, 0, st>>>(P, T);
-    ctx->launches += 1;
-    PIXO_CUDA(ctx, cudaGetLastError());
-    return 0;
 }
 
 // ---- splicing a band's raw bit string into the frame's scan ------------------------------------
@@ -1027,6 +979,193 @@ __global__ void __launch_bounds__(SPL_THREADS) k_splice_emit(const __grid_consta
 
 }  // namespace
 
+// ---- segmented coding: many short chains instead of one long one ------------------------------------
+// One image (or a handful) gives the single-pass kernel only one look-back chain per image: with
+// ~3500 warps in flight on the same chain a chunk has to look back over thousands of predecessors
+// (a 16 384^2 frame took 1.95 ms in k_huff against 0.39 ms for its transform).  Instead the image is
+// cut into S runs of whole MCUs, each coded by k_huff<RAW> as a bit string of its own - S independent,
+// short chains advancing side by side - and four small kernels splice the strings: per-segment bit
+// offsets (k_seg_prefix), 0xFF counts per 4 KB tile of the shifted stream (k_seg_count), their prefix
+// (k_seg_scan), and the stuffed bytes (k_seg_emit).  No host round trip in between.  The same
+// machinery splices a band of a frame tiled over several GPUs (base bit offset and inherited bits
+// come from the other ranks).
+namespace {
+
+struct SegRec {
+    unsigned long long nbits, byte_off, nbytes;   // byte_off: T-bytes of the image's earlier segments
+    uint32_t phase, tail_in, tile_off, last;
+};
+
+struct SegParams {
+    const uint8_t *raw;             // [n * S][raw_cap]
+    unsigned long long raw_cap;
+    const unsigned long long *bits; // [n * S] from k_huff<RAW>
+    const unsigned long long *tails;
+    uint32_t S, max_tiles;
+    unsigned long long base_bit;    // bits of the stream before segment 0 (a band of a tiled frame; 0 otherwise)
+    uint32_t base_tail, last_band;  // the stream's last base_bit % 8 bits; 1: the last segment ends the stream (1-pad)
+    SegRec *rec;                    // [n * S]
+    uint32_t *ntiles;               // [n]
+    uint32_t *cnt;                  // [n][max_tiles] 0xFF counts, then their exclusive prefix
+    uint8_t *out;                   // [n][out_cap]
+    unsigned long long out_cap;
+    unsigned long long *out_len;    // [n]
+    uint32_t *overflow;             // [n]
+    const uint32_t *raw_overflow;   // [n * S] flags of the coding kernel
+};
+
+__device__ __forceinline__ uint32_t seg_byte(const uint8_t *raw, const SegRec &r, unsigned long long m)
+{
+    const unsigned long long rb = (r.nbits + 7) >> 3;
+    const uint32_t cur = m < rb ? raw[m] : 0u;
+    const uint32_t prev = m ? raw[m - 1] : r.tail_in;
+    uint32_t v = (((prev << 8) | cur) >> r.phase) & 0xFFu;
+    const unsigned long long tbits = r.phase + r.nbits;
+    if (m == (tbits >> 3)) v |= 0xFFu >> (uint32_t)(tbits & 7);   // reached only by the padded last byte
+    return v;
+}
+
+__global__ void k_seg_prefix(const __grid_constant__ SegParams P)
+{
+    if (threadIdx.x) return;
+    const uint32_t i = blockIdx.x;
+    unsigned long long start = P.base_bit, byte_off = 0;
+    uint32_t tail_prev = P.base_tail, tile_off = 0, bad = 0;
+    for (uint32_t s = 0; s < P.S; ++s) {
+        const uint32_t q = i * P.S + s;
+        SegRec r;
+        r.nbits = P.bits[q];
+        r.phase = (uint32_t)(start & 7);
+        r.tail_in = tail_prev & ((1u << r.phase) - 1u);
+        r.last = (s == P.S - 1 && P.last_band) ? 1u : 0u;
+        const unsigned long long tbits = r.phase + r.nbits;
+        r.nbytes = (tbits >> 3) + ((r.last && (tbits & 7)) ? 1 : 0);
+        r.byte_off = byte_off;
+        r.tile_off = tile_off;
+        P.rec[q] = r;
+        byte_off += r.nbytes;
+        tile_off += (uint32_t)((r.nbytes + SPL_TILE - 1) / SPL_TILE);
+        start += r.nbits;
+        if (r.nbits) tail_prev = (uint32_t)P.tails[q];
+        bad |= P.raw_overflow[q];
+    }
+    P.ntiles[i] = tile_off;
+    // a raw segment that did not fit (or a faulted chain): the caller codes the image again unsegmented
+    if (bad || tile_off > P.max_tiles) { P.overflow[i] = 4u | (bad & 2u); P.ntiles[i] = 0; P.out_len[i] = 0; }
+    else if (tile_off == 0) P.out_len[i] = 0;
+}
+
+__device__ __forceinline__ uint32_t seg_of_tile(const SegParams &P, uint32_t i, uint32_t t)
+{
+    uint32_t s = 0;
+    while (s + 1 < P.S && P.rec[i * P.S + s + 1].tile_off <= t) ++s;   // S <= 64; the records sit in L1/L2
+    return s;
+}
+
+__global__ void __launch_bounds__(SPL_THREADS) k_seg_count(const __grid_constant__ SegParams P)
+{
+    __shared__ uint32_t red[SPL_THREADS / 32];
+    const uint32_t i = blockIdx.y, t = blockIdx.x;
+    if (t >= P.ntiles[i]) return;
+    const uint32_t s = seg_of_tile(P, i, t);
+    const SegRec r = P.rec[i * P.S + s];
+    const uint8_t *raw = P.raw + (size_t)(i * P.S + s) * P.raw_cap;
+    const unsigned long long m0 = (unsigned long long)(t - r.tile_off) * SPL_TILE + threadIdx.x * 16;
+    uint32_t c = 0;
+    for (int k = 0; k < 16; ++k)
+        if (m0 + k < r.nbytes) c += seg_byte(raw, r, m0 + k) == 0xFFu;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int k = 0; k < SPL_THREADS / 32; ++k) tot += red[k];
+        P.cnt[(size_t)i * P.max_tiles + t] = tot;
+    }
+}
+
+// exclusive prefix of an image's tile counts, in place (one CTA per image)
+__global__ void __launch_bounds__(1024) k_seg_scan(const __grid_constant__ SegParams P)
+{
+    __shared__ uint32_t part[1024];
+    const uint32_t i = blockIdx.x, n = P.ntiles[i];
+    uint32_t *c = P.cnt + (size_t)i * P.max_tiles;
+    const uint32_t per = (n + 1023) / 1024, lo = threadIdx.x * per, hi = min(n, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t k = lo; k < hi; ++k) sum += c[k];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {   // Hillis-Steele over the 1024 partial sums
+        const uint32_t v = threadIdx.x >= (unsigned)o ? part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
+    for (uint32_t k = lo; k < hi; ++k) { const uint32_t v = c[k]; c[k] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(SPL_THREADS) k_seg_emit(const __grid_constant__ SegParams P)
+{
+    __shared__ uint32_t wsum[SPL_THREADS / 32];
+    __shared__ __align__(16) uint8_t sb[2 * SPL_TILE];
+    const uint32_t i = blockIdx.y, t = blockIdx.x, nt = P.ntiles[i];
+    if (t >= nt) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s = seg_of_tile(P, i, t);
+    const SegRec r = P.rec[i * P.S + s];
+    const uint8_t *raw = P.raw + (size_t)(i * P.S + s) * P.raw_cap;
+    const unsigned long long tile_first = (unsigned long long)(t - r.tile_off) * SPL_TILE;
+    const unsigned long long m0 = tile_first + tid * 16;
+    uint32_t v[16], c = 0;
+    for (int k = 0; k < 16; ++k) {
+        v[k] = m0 + k < r.nbytes ? seg_byte(raw, r, m0 + k) : 0x100u;
+        c += v[k] == 0xFFu;
+    }
+    uint32_t inc = c;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t nb = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += nb;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+    for (int k = 0; k < SPL_THREADS / 32; ++k) { if (k < warp) woff += wsum[k]; total += wsum[k]; }
+    uint32_t dst = tid * 16 + woff + inc - c;
+    for (int k = 0; k < 16; ++k) {
+        if (v[k] > 0xFFu) break;
+        sb[dst++] = (uint8_t)v[k];
+        if (v[k] == 0xFFu) sb[dst++] = 0;
+    }
+    __syncthreads();
+    const unsigned long long tile_n = min((unsigned long long)SPL_TILE, r.nbytes - tile_first);
+    const unsigned long long g0 = r.byte_off + tile_first + P.cnt[(size_t)i * P.max_tiles + t];
+    const uint32_t nout = (uint32_t)tile_n + total;
+    uint8_t *outp = P.out + (size_t)i * P.out_cap;
+    if (g0 + nout <= P.out_cap) {
+        // 16-byte stores where source and destination allow, bytes at the ragged ends
+        const uint32_t head = (uint32_t)((16 - ((reinterpret_cast<uintptr_t>(outp) + g0) & 15)) & 15);
+        for (uint32_t k = tid; k < min(head, nout); k += SPL_THREADS) outp[g0 + k] = sb[k];
+        if (nout > head) {
+            const uint32_t nv = (nout - head) >> 4;
+            if ((head & 3) == 0) {
+                for (uint32_t k = tid; k < nv; k += SPL_THREADS) {
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(sb + head + 16 * k);
+                    *reinterpret_cast<uint4 *>(outp + g0 + head + 16 * (size_t)k) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            } else {
+                for (uint32_t k = tid; k < nv * 16; k += SPL_THREADS) outp[g0 + head + k] = sb[head + k];
+            }
+            for (uint32_t k = head + nv * 16 + tid; k < nout; k += SPL_THREADS) outp[g0 + k] = sb[k];
+        }
+    } else if (tid == 0) {
+        atomicOr(&P.overflow[i], 1u);
+    }
+    if (tid == 0 && t == nt - 1) P.out_len[i] = g0 + nout;   // the size needed, also when it did not fit
+}
+
+}  // namespace
+
 size_t splice_scratch_bytes(uint64_t nbits) { return a256(((nbits + 16) / 8 / SPL_TILE + 2) * 4) + 256; }
 
 // d_scratch: splice_scratch_bytes(nbits).  *d_out_len / *d_overflow point into it.
@@ -1054,5 +1193,226 @@ int launch_splice(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t nbits, uint
     PIXO_CUDA(ctx, cudaGetLastError());
     return 0;
 }
+
+// How many segments per image: enough chains to keep a look-back short (~64 chains in flight), none
+// shorter than 48 chunks.  1 = do not segment.
+static uint32_t segments_for(uint32_t n, uint64_t total_mcus, uint64_t bpm)
+{
+    if (const char *e = getenv("PIXO_B200_SEGMENTS")) return (uint32_t)std::max(1, atoi(e));
+    if (n > 8) return 1;
+    uint32_t S = 64 / n;
+    const uint64_t chunks = total_mcus * bpm / CB;
+    while (S > 1 && chunks / S < 48) S >>= 1;
+    if (S > total_mcus) S = (uint32_t)total_mcus;
+    return S < 2 ? 1 : S;
+}
+
+struct SegPlan {
+    uint32_t S;
+    uint64_t seg_mcus, last_mcus;
+    size_t raw_cap;                 // bytes per segment
+    uint32_t max_tiles;             // per image
+    EntropyPlan ent;                // status words etc. for n * S pseudo images
+    size_t off_ent, off_raw, off_rec, off_ntiles, off_cnt, total;
+};
+
+static SegPlan plan_segments(uint32_t n, uint32_t S, uint64_t total_mcus, uint64_t bpm, uint64_t mcu_raw_bytes)
+{
+    SegPlan p;
+    p.seg_mcus = (total_mcus + S - 1) / S;
+    S = (uint32_t)((total_mcus + p.seg_mcus - 1) / p.seg_mcus);   // no empty last segment
+    p.S = S;
+    p.last_mcus = total_mcus - p.seg_mcus * (S - 1);
+    // room for a segment's raw string: as many bytes as its pixels take (q=100 noise stays below 0.7 of
+    // that), at most what its blocks can possibly need (64 x 26 bits + DC < 216 bytes per block).  It
+    // does not depend on the caller's output capacity, so an output that is too small is still measured.
+    const uint64_t fair = p.seg_mcus * mcu_raw_bytes + 4096, worst = p.seg_mcus * bpm * 216 + 64;
+    p.raw_cap = (size_t)a256(std::min(fair, worst));
+    p.max_tiles = (uint32_t)(S * (p.raw_cap / SPL_TILE + 2));
+    p.ent = plan_entropy(n * S, p.seg_mcus * bpm, 0);
+    size_t o = 0;
+    p.off_ent = o; o += a256(p.ent.total);
+    p.off_raw = o; o += a256((size_t)n * S * p.raw_cap);
+    p.off_rec = o; o += a256((size_t)n * S * sizeof(SegRec));
+    p.off_ntiles = o; o += a256((size_t)n * 4);
+    p.off_cnt = o; o += a256((size_t)n * p.max_tiles * 4);
+    p.total = o;
+    return p;
+}
+
+// k_huff<RAW> over n * S segments + the four splice kernels; final bytes in d_out, lengths / flags in
+// the caller's scratch (same contract as the unsegmented launch).  base_bit / base_tail / last_stream:
+// see SegParams (a band of a tiled frame passes its offset; a whole image passes 0, 0, true).
+static int launch_segmented(pixo_b200_ctx *ctx, EntParams P, const HuffDev &T, uint32_t n, const FrameGeometry &g,
+                            const SegPlan &sp, uint8_t *seg_scratch, uint8_t *d_out, uint64_t out_cap,
+                            uint64_t *d_out_len, uint32_t *d_overflow, uint64_t base_bit, uint32_t base_tail,
+                            bool last_stream, bool code, bool splice)
+{
+    cudaStream_t st = ctx->stream;
+    const uint64_t bpm = g.y_per_mcu + (g.has_chroma ? 2 : 0);
+    uint8_t *ent = seg_scratch + sp.off_ent;
+    P.nimages = n * sp.S;
+    P.seg_per_img = sp.S;
+    P.nblocks = (uint32_t)(sp.seg_mcus * bpm);
+    P.nblocks_last = (uint32_t)(sp.last_mcus * bpm);
+    P.nchunks = (uint32_t)sp.ent.nchunks;
+    P.seg_y_stride = (size_t)sp.seg_mcus * g.y_per_mcu * 64;
+    P.seg_c_stride = (size_t)sp.seg_mcus * 64;
+    P.rst_blocks = P.rst_mcus = P.cpi = 0;
+    P.st_bits = reinterpret_cast<unsigned long long *>(ent + sp.ent.off_st1);
+    P.st_ff = reinterpret_cast<unsigned long long *>(ent + sp.ent.off_st2);
+    P.ticket = reinterpret_cast<uint32_t *>(ent + sp.ent.off_ticket);
+    P.overflow = reinterpret_cast<uint32_t *>(ent + sp.ent.off_ovf);
+    P.out_len = reinterpret_cast<uint64_t *>(ent + sp.ent.off_outlen);
+    P.out_tail = reinterpret_cast<unsigned long long *>(ent + sp.ent.off_tail);
+    P.out = seg_scratch + sp.off_raw;
+    P.out_cap = sp.raw_cap;
+    if (code) {
+        PIXO_CUDA(ctx, cudaMemsetAsync(ent, 0, sp.ent.zero_bytes, st));
+        const size_t want = ((size_t)P.nimages * P.nchunks + HUFF_WARPS - 1) / HUFF_WARPS;
+        const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)ctx->sm_count * HUFF_CTAS_PER_SM);
+        k_huff<true><<<grid, 32 * HUFF_WARPS, 0, st>>>(P, T);
+        ctx->launches += 1;
+        PIXO_CUDA(ctx, cudaGetLastError());
+    }
+    if (!splice) return 0;
+    SegParams Q;
+    Q.raw = P.out; Q.raw_cap = sp.raw_cap;
+    Q.bits = reinterpret_cast<const unsigned long long *>(P.out_len);
+    Q.tails = P.out_tail;
+    Q.S = sp.S; Q.max_tiles = sp.max_tiles;
+    Q.base_bit = base_bit; Q.base_tail = base_tail; Q.last_band = last_stream ? 1u : 0u;
+    Q.rec = reinterpret_cast<SegRec *>(seg_scratch + sp.off_rec);
+    Q.ntiles = reinterpret_cast<uint32_t *>(seg_scratch + sp.off_ntiles);
+    Q.cnt = reinterpret_cast<uint32_t *>(seg_scratch + sp.off_cnt);
+    Q.out = d_out; Q.out_cap = out_cap;
+    Q.out_len = reinterpret_cast<unsigned long long *>(d_out_len);
+    Q.overflow = d_overflow;
+    Q.raw_overflow = P.overflow;
+    k_seg_prefix<<<n, 32, 0, st>>>(Q);
+    k_seg_count<<<dim3(sp.max_tiles, n), SPL_THREADS, 0, st>>>(Q);
+    k_seg_scan<<<n, 1024, 0, st>>>(Q);
+    k_seg_emit<<<dim3(sp.max_tiles, n), SPL_THREADS, 0, st>>>(Q);
+    ctx->launches += 4;
+    PIXO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+// Enqueue the entropy stage for n images (natural-order coefficient arrays) on ctx->stream.
+// d_scratch: entropy_scratch_bytes.  d_out: n * out_cap bytes of scan data; *d_out_len /
+// *d_overflow point into the scratch.
+int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride, const int16_t *d_cb,
+                        const int16_t *d_cr, size_t c_stride, uint32_t n, const FrameGeometry &g,
+                        const HuffTables &t, uint32_t restart_interval, uint8_t *d_scratch, uint8_t *d_out,
+                        uint64_t out_cap, uint64_t **d_out_len, uint32_t **d_overflow, const int *dc_seed,
+                        uint64_t **d_raw_tail)
+{
+    const bool raw = d_raw_tail != nullptr;
+    if (raw && restart_interval)
+        return set_error(ctx, PIXO_B200_ERR_UNSUPPORTED, "band-local raw coding does not take a restart interval");
+    if (raw && (out_cap & 3))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "raw buffer capacity must be a multiple of 4");
+    const uint64_t nblocks = g.ny + 2 * g.nc;
+    const uint64_t bpm_ = g.y_per_mcu + (g.has_chroma ? 2 : 0);
+    uint64_t rst_blocks = (uint64_t)restart_interval * bpm_;
+    if (rst_blocks >= nblocks) rst_blocks = 0;  // a single interval: no marker is ever written
+    const EntropyPlan pl = plan_entropy(n, nblocks, rst_blocks);
+    if (nblocks > 0xFFFFFFFFull || (uint64_t)n * pl.nchunks > 0x7FFFFFFFull)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "entropy stage: too many blocks per call");
+    EntParams P;
+    P.y = d_y; P.cb = d_cb; P.cr = d_cr; P.y_stride = y_stride; P.c_stride = c_stride;
+    P.bpm = g.y_per_mcu + (g.has_chroma ? 2 : 0);
+    P.y_per_mcu = g.y_per_mcu;
+    P.nblocks = (uint32_t)nblocks;
+    P.nchunks = (uint32_t)pl.nchunks;
+    P.rst_blocks = (uint32_t)rst_blocks;
+    P.rst_mcus = rst_blocks ? restart_interval : 0u;
+    P.cpi = rst_blocks ? (uint32_t)((rst_blocks + CB - 1) / CB) : 0u;
+    P.nimages = n;
+    P.st_bits = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_st1);
+    P.st_ff = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_st2);
+    P.ticket = reinterpret_cast<uint32_t *>(d_scratch + pl.off_ticket);
+    P.overflow = reinterpret_cast<uint32_t *>(d_scratch + pl.off_ovf);
+    P.out_len = reinterpret_cast<uint64_t *>(d_scratch + pl.off_outlen);
+    P.out = d_out; P.out_cap = out_cap;
+    P.out_tail = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_tail);
+    for (int k = 0; k < 3; ++k) P.dc_seed[k] = dc_seed ? dc_seed[k] : 0;
+    *d_out_len = P.out_len;
+    *d_overflow = P.overflow;
+    if (raw) *d_raw_tail = reinterpret_cast<uint64_t *>(P.out_tail);
+
+    HuffDev T;
+    memset(&T, 0, sizeof T);
+    for (int k = 0; k < 2; ++k) {
+        for (int cat = 0; cat < 12; ++cat)
+            if (t.len[k][cat])
+                T.dc[k][cat] = ((uint32_t)t.code[k][cat] << (32 - t.len[k][cat])) | (uint32_t)(t.len[k][cat] + cat);
+        for (int rs = 0; rs < 256; ++rs) {
+            const int cat = rs & 15, run = rs >> 4;
+            if (!t.len[2 + k][rs] || cat > 10) continue;
+            const uint32_t e = ((uint32_t)t.code[2 + k][rs] << (32 - t.len[2 + k][rs])) | (uint32_t)(t.len[2 + k][rs] + cat);
+            if (rs == 0x00) T.ac[k][AC_EOB] = e;
+            else if (rs == 0xF0) T.ac[k][AC_ZRL] = e;
+            else if (cat >= 1) T.ac[k][run * AC_STRIDE + cat - 1] = e;
+        }
+    }
+    cudaStream_t st = ctx->stream;
+    PIXO_CUDA(ctx, cudaMemsetAsync(d_scratch, 0, pl.zero_bytes, st));
+    P.seg_per_img = 1; P.nblocks_last = P.nblocks; P.seg_y_stride = P.seg_c_stride = 0;
+    // few images: cut each into segments (short look-back chains) and splice - see k_seg_*
+    const uint32_t S = (rst_blocks == 0 && !ctx->no_segments) ? segments_for(n, g.total_mcus(), bpm_) : 1;
+    const uint64_t mcu_raw = (uint64_t)g.y_per_mcu * 64 * (g.has_chroma ? 3 : 1);
+    const SegPlan sp = plan_segments(n, S, g.total_mcus(), bpm_, mcu_raw);
+    if (sp.S > 1) {
+        PIXO_TRY(ensure_dev(ctx, ctx->d_raw, sp.total));
+        auto *seg_scratch = reinterpret_cast<uint8_t *>(ctx->d_raw.ptr);
+        if (!raw)
+            return launch_segmented(ctx, P, T, n, g, sp, seg_scratch, d_out, out_cap, P.out_len, P.overflow, 0, 0, true,
+                                    true, true);
+        // a band of a tiled frame: code now, splice when the bit offset is known (launch_band_splice);
+        // the per-segment bit counts and tails are summed up by the caller
+        ctx->band_segments = sp.S;
+        ctx->band_cap = mcu_raw;
+        ctx->band_mcus = g.total_mcus();
+        ctx->band_bpm = (uint32_t)bpm_;
+        ctx->band_geo_y_per_mcu = g.y_per_mcu;
+        ctx->band_has_chroma = g.has_chroma;
+        PIXO_TRY(launch_segmented(ctx, P, T, n, g, sp, seg_scratch, nullptr, 0, nullptr, nullptr, 0, 0, false, true, false));
+        *d_out_len = reinterpret_cast<uint64_t *>(seg_scratch + sp.off_ent + sp.ent.off_outlen);
+        *d_overflow = reinterpret_cast<uint32_t *>(seg_scratch + sp.off_ent + sp.ent.off_ovf);
+        *d_raw_tail = reinterpret_cast<uint64_t *>(seg_scratch + sp.off_ent + sp.ent.off_tail);
+        return 0;
+    }
+    ctx->band_segments = 1;
+    const size_t want = ((size_t)n * pl.nchunks + HUFF_WARPS - 1) / HUFF_WARPS;
+    const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)ctx->sm_count * HUFF_CTAS_PER_SM);
+    if (raw) k_huff<true><<<grid, 32 * HUFF_WARPS, 0, st>>>(P, T);
+    else k_huff<false><<<grid, 32 * HUFF_WARPS, 0, st>>>(P, T);
+    ctx->launches += 1;
+    PIXO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+
+// Splice the S raw segments the last launch_jpeg_entropy(raw) left in ctx->d_raw into the band's scan bytes.
+int launch_band_splice_segments(pixo_b200_ctx *ctx, uint64_t base_bit, uint32_t base_tail, bool last,
+                                uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap, uint64_t **d_out_len,
+                                uint32_t **d_overflow)
+{
+    const uint32_t S = ctx->band_segments;
+    const SegPlan sp = plan_segments(1, S, ctx->band_mcus, ctx->band_bpm, ctx->band_cap);
+    FrameGeometry g;
+    g.y_per_mcu = ctx->band_geo_y_per_mcu; g.has_chroma = ctx->band_has_chroma;
+    EntParams P;
+    memset(&P, 0, sizeof P);
+    HuffDev T;
+    memset(&T, 0, sizeof T);
+    PIXO_CUDA(ctx, cudaMemsetAsync(d_scratch, 0, 256, ctx->stream));
+    *d_out_len = reinterpret_cast<uint64_t *>(d_scratch);
+    *d_overflow = reinterpret_cast<uint32_t *>(d_scratch + 8);
+    return launch_segmented(ctx, P, T, 1, g, sp, reinterpret_cast<uint8_t *>(ctx->d_raw.ptr), d_out, out_cap, *d_out_len,
+                            *d_overflow, base_bit, base_tail, last, false, true);
+}
+
 
 }  // namespace pixo

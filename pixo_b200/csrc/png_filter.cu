@@ -513,6 +513,7 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
     __shared__ uint32_t red[5][PNG_THREADS / 32];
     __shared__ unsigned long long red64[3][PNG_THREADS / 32];
     __shared__ int s_filter;
+    __shared__ uint4 vstage[PNG_THREADS / 32][33];   // emit_vec: a warp's filtered vectors, slot l + 1 = lane l, slot 0 = carry
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t img = blockIdx.y;
     const uint32_t rb = P.row_bytes;
@@ -725,12 +726,127 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
                 }
             }
         };
-        switch (filter) {
-        case 0: emit_row(std::integral_constant<int, 0>{}); break;
-        case 1: emit_row(std::integral_constant<int, 1>{}); break;
-        case 2: emit_row(std::integral_constant<int, 2>{}); break;
-        case 3: emit_row(std::integral_constant<int, 3>{}); break;
-        default: emit_row(std::integral_constant<int, 4>{}); break;
+        // ---- the same, 16 filtered bytes per thread (rows of at least VEC_MIN_VECS vectors) ---------
+        // Thread = vector v (four consecutive words, one LDS.128 per row buffer as in score4).  The
+        // output stream is byte-shifted against the row (type bytes: row r starts at r * (rb + 1) + 1), so
+        // the ALIGNED 16-byte chunk v of the output holds the last sh16 bytes of vector v-1 and the
+        // first 16 - sh16 of vector v: the previous vector comes through a per-warp shared staging
+        // array (the warp's first one is recomputed), eight words are funnel-shifted into four, and
+        // the chunk leaves as one 16-byte store, 512 contiguous bytes per warp instruction.  Up to 15
+        // bytes at either end of the row go out singly.  Adler: two dp4a chains per vector.
+        uint32_t SWv = 0, SVv = 0;   // sum v * (byte sum of vector v); sum of (index within the vector) * byte
+        auto emit_vec = [&](auto ftag, auto a0tag) {
+            constexpr int F = decltype(ftag)::value;
+            constexpr bool A0 = decltype(a0tag)::value;
+            const uint32_t nv = (rb >> 2) >> 2;                       // whole 16-byte vectors in the row
+            const uint32_t sh16 = (uint32_t)(reinterpret_cast<uintptr_t>(orow + 1) & 15);
+            uint8_t *abase = orow + 1 - sh16;                          // 16-byte aligned; chunk v at abase + 16 v
+            auto fvec = [&](uint32_t v, bool shfl, uint32_t (&f)[4]) {
+                const uint4 X4 = lds128(cs + 16u * v), B4 = lds128(ps + 16u * v);
+                uint32_t x[5] = {0, X4.x, X4.y, X4.z, X4.w}, b[5] = {0, B4.x, B4.y, B4.z, B4.w};
+                if (shfl) {
+                    x[0] = __shfl_up_sync(0xffffffffu, X4.w, 1);
+                    b[0] = __shfl_up_sync(0xffffffffu, B4.w, 1);
+                }
+                if (!shfl || lane == 0) { x[0] = lds32(cs + 16u * v - 4u); b[0] = lds32(ps + 16u * v - 4u); }
+                if (OA) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) { x[i] = zero_transparent<OA ? OA : 4>(x[i]); b[i] = zero_transparent<OA ? OA : 4>(b[i]); }
+                }
+#pragma unroll
+                for (int i = 1; i < 5; ++i) {
+                    const uint32_t a = A0 ? x[i - 1] : __funnelshift_r(x[i - 1], x[i], ashift);
+                    const uint32_t c = A0 ? b[i - 1] : __funnelshift_r(b[i - 1], b[i], ashift);
+                    const uint32_t pred = F == 0 ? 0u : F == 1 ? a : F == 2 ? b[i] : F == 3 ? __vhaddu4(a, b[i]) : paeth_pred4(a, b[i], c);
+                    f[i - 1] = F == 0 ? x[i] : __vsub4(x[i], pred);
+                }
+            };
+            const uint32_t per = (((nv + PNG_THREADS / 32 - 1) / (PNG_THREADS / 32)) + 31) & ~31u;   // vectors per warp
+            const uint32_t v_lo = warp * per, v_hi = min(nv, v_lo + per);
+            uint4 *stg = vstage[warp];
+            if (v_lo < v_hi) {
+                if (lane == 0) {
+                    uint32_t f[4] = {0, 0, 0, 0};
+                    if (v_lo > 0 && sh16) fvec(v_lo - 1, false, f);
+                    stg[0] = make_uint4(f[0], f[1], f[2], f[3]);
+                }
+                for (uint32_t vb = v_lo; vb < v_hi; vb += 32) {
+                    const uint32_t v = vb + lane;
+                    const bool valid = v < v_hi;
+                    uint32_t f[4];
+                    fvec(valid ? v : v_hi - 1, true, f);
+                    if (valid) {
+                        const uint32_t ssum = __dp4a(f[0], 0x01010101u, __dp4a(f[1], 0x01010101u, __dp4a(f[2], 0x01010101u, __dp4a(f[3], 0x01010101u, 0u))));
+                        S1 += ssum;
+                        SWv += v * ssum;
+                        SVv += __dp4a(f[0], 0x03020100u, __dp4a(f[1], 0x07060504u, __dp4a(f[2], 0x0B0A0908u, __dp4a(f[3], 0x0F0E0D0Cu, 0u))));
+                    }
+                    stg[lane + 1] = make_uint4(f[0], f[1], f[2], f[3]);
+                    __syncwarp();
+                    const uint4 pv = stg[lane];                          // vector v - 1
+                    __syncwarp();
+                    if (lane == 31) stg[0] = make_uint4(f[0], f[1], f[2], f[3]);   // carry into the next round
+                    if (valid) {
+                        if (v > 0 || sh16 == 0) {
+                            const uint32_t W[9] = {pv.x, pv.y, pv.z, pv.w, f[0], f[1], f[2], f[3], 0u};
+                            const uint32_t o = 16u - sh16, bs = (o & 3u) * 8u;
+                            uint4 q;
+                            switch (o >> 2) {   // uniform: the row's byte phase
+                            case 0: q = make_uint4(__funnelshift_r(W[0], W[1], bs), __funnelshift_r(W[1], W[2], bs), __funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs)); break;
+                            case 1: q = make_uint4(__funnelshift_r(W[1], W[2], bs), __funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs)); break;
+                            case 2: q = make_uint4(__funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs), __funnelshift_r(W[5], W[6], bs)); break;
+                            case 3: q = make_uint4(__funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs), __funnelshift_r(W[5], W[6], bs), __funnelshift_r(W[6], W[7], bs)); break;
+                            default: q = make_uint4(W[4], W[5], W[6], W[7]); break;
+                            }
+                            *reinterpret_cast<uint4 *>(abase + 16 * (size_t)v) = q;
+                        } else {   // v == 0, sh16 > 0: the row's first 16 - sh16 bytes share chunk 0 with the row before
+                            for (uint32_t i = 0; i < 16u - sh16; ++i) orow[1 + i] = (uint8_t)(f[i >> 2] >> (8 * (i & 3)));
+                        }
+                        if (v == nv - 1 && sh16)   // the last sh16 bytes of the last vector start the next chunk
+                            for (uint32_t i = 16u - sh16; i < 16u; ++i) orow[1 + 16 * (size_t)v + i] = (uint8_t)(f[i >> 2] >> (8 * (i & 3)));
+                    }
+                    __syncwarp();
+                }
+            }
+            // what is left of the row after the last whole vector: up to three words and a ragged one
+            for (uint32_t k = nv * 4 + tid; k < nw; k += PNG_THREADS) {
+                uint32_t x, a, b, c, mask;
+                operands(k, x, a, b, c, mask);
+                const uint32_t pred = F == 0 ? 0u : F == 1 ? a : F == 2 ? b : F == 3 ? __vhaddu4(a, b) : paeth_pred4(a, b, c);
+                const uint32_t f = __vsub4(x, pred) & mask;
+                const uint32_t s4 = __dp4a(f, 0x01010101u, 0u);
+                S1 += s4; S2 += k * s4; S3 += __dp4a(f, 0x03020100u, 0u);
+                for (uint32_t t = 0; t < 4 && 4 * k + t < rb; ++t) orow[1 + 4 * (size_t)k + t] = (uint8_t)(f >> (8 * t));
+            }
+        };
+        const bool use_vec = (rb >> 4) >= 64;   // at least 64 vectors (1 KB rows)
+        using std::integral_constant;
+        if (use_vec) {
+            if (ashift == 0) {
+                switch (filter) {
+                case 0: emit_vec(integral_constant<int, 0>{}, std::true_type{}); break;
+                case 1: emit_vec(integral_constant<int, 1>{}, std::true_type{}); break;
+                case 2: emit_vec(integral_constant<int, 2>{}, std::true_type{}); break;
+                case 3: emit_vec(integral_constant<int, 3>{}, std::true_type{}); break;
+                default: emit_vec(integral_constant<int, 4>{}, std::true_type{}); break;
+                }
+            } else {
+                switch (filter) {
+                case 0: emit_vec(integral_constant<int, 0>{}, std::false_type{}); break;
+                case 1: emit_vec(integral_constant<int, 1>{}, std::false_type{}); break;
+                case 2: emit_vec(integral_constant<int, 2>{}, std::false_type{}); break;
+                case 3: emit_vec(integral_constant<int, 3>{}, std::false_type{}); break;
+                default: emit_vec(integral_constant<int, 4>{}, std::false_type{}); break;
+                }
+            }
+        } else {
+            switch (filter) {
+            case 0: emit_row(std::integral_constant<int, 0>{}); break;
+            case 1: emit_row(std::integral_constant<int, 1>{}); break;
+            case 2: emit_row(std::integral_constant<int, 2>{}); break;
+            case 3: emit_row(std::integral_constant<int, 3>{}); break;
+            default: emit_row(std::integral_constant<int, 4>{}); break;
+            }
         }
         if (tid == 0) orow[0] = (uint8_t)filter;
         if (P.acc) {
@@ -738,7 +854,7 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
             const unsigned long long Wr = (Ntot - (unsigned long long)r * n_out - 1) % ADLER_MOD;
             accA += S1;
             accBpos += Wr * S1;
-            accBneg += 4ull * S2 + S3;
+            accBneg += 4ull * S2 + S3 + 16ull * SWv + SVv;
             if (tid == 0) { accA += (unsigned)filter; accBpos += ((Wr + 1) % ADLER_MOD) * (unsigned)filter; }
         }
         __syncthreads();   // all reads of this row's buffers are done before the ring advances
