@@ -225,7 +225,10 @@ int pixo_b200_jpeg_band_histogram_dev(pixo_b200_ctx *ctx, const int16_t *d_y, co
                                       uint32_t color_type, uint32_t subsampling,
                                       const int32_t dc_seed[3], uint64_t *d_hist /* 536, device */);
 /* hist (host, optional): the frame's summed statistics -> optimised tables (standard when NULL or
- * when they cannot be built, as the reference's unwrap_or_default does). */
+ * when they cannot be built, as the reference's unwrap_or_default does).  d_raw: 16-byte aligned,
+ * raw_cap a multiple of 4; it must stay untouched until the band has been spliced.  A raw_cap of at
+ * least the band's pixel bytes + 1 MiB lets a long band be coded as several independent segments
+ * (shorter look-back chains); with less room the band is coded as one string. */
 int pixo_b200_jpeg_band_entropy_dev(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb,
                                     const int16_t *d_cr, uint32_t width, uint32_t band_height,
                                     uint32_t color_type, uint32_t subsampling,

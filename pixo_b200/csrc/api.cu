@@ -1102,7 +1102,7 @@ int pixo_b200_jpeg_band_entropy_dev(pixo_b200_ctx *ctx, const int16_t *d_y, cons
                                  d_raw, raw_cap, &d_len, &d_ovf, dc_seed, &d_tail));
     // (a long band is coded as several segments - see k_seg_* -: their bit counts add up, the band's
     // tail is its last non-empty segment's)
-    const uint32_t S = ctx->band_segments;
+    const uint32_t S = ctx->last_band_segments;
     PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, (size_t)S * 20 + 256));
     auto *h = reinterpret_cast<uint64_t *>(ctx->h_misc.ptr);
     PIXO_CUDA(ctx, cudaMemcpyAsync(h, d_len, (size_t)S * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1136,8 +1136,8 @@ int pixo_b200_jpeg_band_splice_dev(pixo_b200_ctx *ctx, const uint8_t *d_raw, uin
     PIXO_TRY(ensure_pinned(ctx, ctx->h_misc, 256));
     uint64_t *d_len = nullptr;
     uint32_t *d_ovf = nullptr;
-    if (ctx->band_segments > 1)   // the band was coded in segments; their raw strings are in the context
-        PIXO_TRY(launch_band_splice_segments(ctx, start_bit, tail_in, is_last_band != 0,
+    if (ctx->bands.count(d_raw))   // the band was coded in segments (strings, bit counts and tails are in d_raw)
+        PIXO_TRY(launch_band_splice_segments(ctx, d_raw, start_bit, tail_in, is_last_band != 0,
                                              reinterpret_cast<uint8_t *>(ctx->d_misc.ptr), d_out, out_cap, &d_len, &d_ovf));
     else
         PIXO_TRY(launch_splice(ctx, d_raw, nbits, (uint32_t)(start_bit & 7), tail_in, is_last_band != 0,

@@ -11,6 +11,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/pixo_b200.h"
@@ -77,10 +78,15 @@ struct pixo_b200_ctx {
     std::vector<cudaEvent_t> stage_events;  // one per pinned staging slot of h2d_copy
     pixo::HostPool *pool = nullptr;         // see HostPool
     bool no_segments = false;               // entropy stage: never cut images into segments (retry path)
-    // the segmentation of the band coded last by pixo_b200_jpeg_band_entropy_dev (its raw strings sit in d_raw)
-    uint32_t band_segments = 1, band_bpm = 0, band_geo_y_per_mcu = 1;
-    bool band_has_chroma = true;
-    uint64_t band_cap = 0, band_mcus = 0;
+    // How the bands coded by pixo_b200_jpeg_band_entropy_dev were cut into segments, keyed by the
+    // caller's raw buffer (which holds the segments' strings, bit counts and tails until the splice).
+    struct BandInfo {
+        uint32_t segments = 1, bpm = 0, y_per_mcu = 1;
+        bool has_chroma = true;
+        uint64_t mcus = 0;
+    };
+    std::unordered_map<const void *, BandInfo> bands;
+    uint32_t last_band_segments = 1;        // of the latest launch_jpeg_entropy(raw) call
 };
 
 namespace pixo {
@@ -132,9 +138,11 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
                         uint64_t out_cap, uint64_t **d_out_len, uint32_t **d_overflow,
                         const int *dc_seed = nullptr, uint64_t **d_raw_tail = nullptr);
 size_t splice_scratch_bytes(uint64_t nbits);
-int launch_band_splice_segments(pixo_b200_ctx *ctx, uint64_t base_bit, uint32_t base_tail, bool last,
-                                uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap, uint64_t **d_out_len,
-                                uint32_t **d_overflow);
+int launch_band_splice_segments(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t base_bit, uint32_t base_tail,
+                                bool last, uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap,
+                                uint64_t **d_out_len, uint32_t **d_overflow);
+// bytes a band's raw buffer needs so that the band can be coded in segments (0: never segmented)
+size_t band_raw_bytes_segmented(const FrameGeometry &g);
 int launch_splice(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t nbits, uint32_t phase, uint32_t tail_in,
                   bool last, uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap, uint64_t **d_out_len,
                   uint32_t **d_overflow);

@@ -1047,7 +1047,7 @@ __global__ void k_seg_prefix(const __grid_constant__ SegParams P)
         tile_off += (uint32_t)((r.nbytes + SPL_TILE - 1) / SPL_TILE);
         start += r.nbits;
         if (r.nbits) tail_prev = (uint32_t)P.tails[q];
-        bad |= P.raw_overflow[q];
+        if (P.raw_overflow) bad |= P.raw_overflow[q];
     }
     P.ntiles[i] = tile_off;
     // a raw segment that did not fit (or a faulted chain): the caller codes the image again unsegmented
@@ -1199,11 +1199,13 @@ int launch_splice(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t nbits, uint
 static uint32_t segments_for(uint32_t n, uint64_t total_mcus, uint64_t bpm)
 {
     if (const char *e = getenv("PIXO_B200_SEGMENTS")) return (uint32_t)std::max(1, atoi(e));
-    if (n > 8) return 1;
-    uint32_t S = 64 / n;
+    // Measured on B200: for 4K frames (6 075 chunks) the four extra launches cost more than the
+    // shorter chains save (k_huff 72 -> 111 us for one frame, 715 -> 1110 us for 32); a 16 384^2 frame
+    // (196 608 chunks on ONE chain) is where the look-back distance hurts.  So: few images, each long.
     const uint64_t chunks = total_mcus * bpm / CB;
-    while (S > 1 && chunks / S < 48) S >>= 1;
-    if (S > total_mcus) S = (uint32_t)total_mcus;
+    if (n > 8 || chunks < 16384) return 1;
+    uint32_t S = 64 / n;
+    while (S > 1 && chunks / S < 1024) S >>= 1;
     return S < 2 ? 1 : S;
 }
 
@@ -1213,7 +1215,8 @@ struct SegPlan {
     size_t raw_cap;                 // bytes per segment
     uint32_t max_tiles;             // per image
     EntropyPlan ent;                // status words etc. for n * S pseudo images
-    size_t off_ent, off_raw, off_rec, off_ntiles, off_cnt, total;
+    size_t off_ent, off_rec, off_ntiles, off_cnt, total;   // offsets into the context's segment scratch
+    size_t raw_bytes, off_bits, off_tails, raw_total;      // layout of the raw area: strings, then the segments' bit counts and tails
 };
 
 static SegPlan plan_segments(uint32_t n, uint32_t S, uint64_t total_mcus, uint64_t bpm, uint64_t mcu_raw_bytes)
@@ -1232,7 +1235,10 @@ static SegPlan plan_segments(uint32_t n, uint32_t S, uint64_t total_mcus, uint64
     p.ent = plan_entropy(n * S, p.seg_mcus * bpm, 0);
     size_t o = 0;
     p.off_ent = o; o += a256(p.ent.total);
-    p.off_raw = o; o += a256((size_t)n * S * p.raw_cap);
+    p.raw_bytes = a256((size_t)n * S * p.raw_cap);
+    p.off_bits = p.raw_bytes;
+    p.off_tails = p.off_bits + a256((size_t)n * S * 8);
+    p.raw_total = p.off_tails + a256((size_t)n * S * 8);
     p.off_rec = o; o += a256((size_t)n * S * sizeof(SegRec));
     p.off_ntiles = o; o += a256((size_t)n * 4);
     p.off_cnt = o; o += a256((size_t)n * p.max_tiles * 4);
@@ -1244,7 +1250,7 @@ static SegPlan plan_segments(uint32_t n, uint32_t S, uint64_t total_mcus, uint64
 // the caller's scratch (same contract as the unsegmented launch).  base_bit / base_tail / last_stream:
 // see SegParams (a band of a tiled frame passes its offset; a whole image passes 0, 0, true).
 static int launch_segmented(pixo_b200_ctx *ctx, EntParams P, const HuffDev &T, uint32_t n, const FrameGeometry &g,
-                            const SegPlan &sp, uint8_t *seg_scratch, uint8_t *d_out, uint64_t out_cap,
+                            const SegPlan &sp, uint8_t *seg_scratch, uint8_t *raw_area, uint8_t *d_out, uint64_t out_cap,
                             uint64_t *d_out_len, uint32_t *d_overflow, uint64_t base_bit, uint32_t base_tail,
                             bool last_stream, bool code, bool splice)
 {
@@ -1265,7 +1271,7 @@ static int launch_segmented(pixo_b200_ctx *ctx, EntParams P, const HuffDev &T, u
     P.overflow = reinterpret_cast<uint32_t *>(ent + sp.ent.off_ovf);
     P.out_len = reinterpret_cast<uint64_t *>(ent + sp.ent.off_outlen);
     P.out_tail = reinterpret_cast<unsigned long long *>(ent + sp.ent.off_tail);
-    P.out = seg_scratch + sp.off_raw;
+    P.out = raw_area;
     P.out_cap = sp.raw_cap;
     if (code) {
         PIXO_CUDA(ctx, cudaMemsetAsync(ent, 0, sp.ent.zero_bytes, st));
@@ -1274,12 +1280,15 @@ static int launch_segmented(pixo_b200_ctx *ctx, EntParams P, const HuffDev &T, u
         k_huff<true><<<grid, 32 * HUFF_WARPS, 0, st>>>(P, T);
         ctx->launches += 1;
         PIXO_CUDA(ctx, cudaGetLastError());
+        // the segments' bit counts and tails travel with the strings (a band is spliced by a later call)
+        PIXO_CUDA(ctx, cudaMemcpyAsync(raw_area + sp.off_bits, P.out_len, (size_t)n * sp.S * 8, cudaMemcpyDeviceToDevice, st));
+        PIXO_CUDA(ctx, cudaMemcpyAsync(raw_area + sp.off_tails, P.out_tail, (size_t)n * sp.S * 8, cudaMemcpyDeviceToDevice, st));
     }
     if (!splice) return 0;
     SegParams Q;
     Q.raw = P.out; Q.raw_cap = sp.raw_cap;
-    Q.bits = reinterpret_cast<const unsigned long long *>(P.out_len);
-    Q.tails = P.out_tail;
+    Q.bits = reinterpret_cast<const unsigned long long *>(raw_area + sp.off_bits);
+    Q.tails = reinterpret_cast<const unsigned long long *>(raw_area + sp.off_tails);
     Q.S = sp.S; Q.max_tiles = sp.max_tiles;
     Q.base_bit = base_bit; Q.base_tail = base_tail; Q.last_band = last_stream ? 1u : 0u;
     Q.rec = reinterpret_cast<SegRec *>(seg_scratch + sp.off_rec);
@@ -1288,7 +1297,7 @@ static int launch_segmented(pixo_b200_ctx *ctx, EntParams P, const HuffDev &T, u
     Q.out = d_out; Q.out_cap = out_cap;
     Q.out_len = reinterpret_cast<unsigned long long *>(d_out_len);
     Q.overflow = d_overflow;
-    Q.raw_overflow = P.overflow;
+    Q.raw_overflow = code ? P.overflow : nullptr;   // a band's flags were checked by the host when it was coded
     k_seg_prefix<<<n, 32, 0, st>>>(Q);
     k_seg_count<<<dim3(sp.max_tiles, n), SPL_THREADS, 0, st>>>(Q);
     k_seg_scan<<<n, 1024, 0, st>>>(Q);
@@ -1362,28 +1371,29 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
     // few images: cut each into segments (short look-back chains) and splice - see k_seg_*
     const uint32_t S = (rst_blocks == 0 && !ctx->no_segments) ? segments_for(n, g.total_mcus(), bpm_) : 1;
     const uint64_t mcu_raw = (uint64_t)g.y_per_mcu * 64 * (g.has_chroma ? 3 : 1);
-    const SegPlan sp = plan_segments(n, S, g.total_mcus(), bpm_, mcu_raw);
+    SegPlan sp = plan_segments(n, S, g.total_mcus(), bpm_, mcu_raw);
+    if (raw && sp.S > 1 && sp.raw_total > out_cap) sp.S = 1;   // the caller's band buffer has no room for segments
+    ctx->last_band_segments = 1;
     if (sp.S > 1) {
-        PIXO_TRY(ensure_dev(ctx, ctx->d_raw, sp.total));
+        PIXO_TRY(ensure_dev(ctx, ctx->d_raw, sp.total + (raw ? 0 : sp.raw_total)));
         auto *seg_scratch = reinterpret_cast<uint8_t *>(ctx->d_raw.ptr);
         if (!raw)
-            return launch_segmented(ctx, P, T, n, g, sp, seg_scratch, d_out, out_cap, P.out_len, P.overflow, 0, 0, true,
-                                    true, true);
-        // a band of a tiled frame: code now, splice when the bit offset is known (launch_band_splice);
-        // the per-segment bit counts and tails are summed up by the caller
-        ctx->band_segments = sp.S;
-        ctx->band_cap = mcu_raw;
-        ctx->band_mcus = g.total_mcus();
-        ctx->band_bpm = (uint32_t)bpm_;
-        ctx->band_geo_y_per_mcu = g.y_per_mcu;
-        ctx->band_has_chroma = g.has_chroma;
-        PIXO_TRY(launch_segmented(ctx, P, T, n, g, sp, seg_scratch, nullptr, 0, nullptr, nullptr, 0, 0, false, true, false));
+            return launch_segmented(ctx, P, T, n, g, sp, seg_scratch, seg_scratch + sp.total, d_out, out_cap, P.out_len,
+                                    P.overflow, 0, 0, true, true, true);
+        // a band of a tiled frame: code now into the CALLER's raw buffer, splice when the bit offset is
+        // known (launch_band_splice_segments); the per-segment bit counts and tails are summed up by the caller
+        pixo_b200_ctx::BandInfo bi;
+        bi.segments = sp.S; bi.bpm = (uint32_t)bpm_; bi.y_per_mcu = g.y_per_mcu; bi.has_chroma = g.has_chroma;
+        bi.mcus = g.total_mcus();
+        ctx->bands[d_out] = bi;
+        ctx->last_band_segments = sp.S;
+        PIXO_TRY(launch_segmented(ctx, P, T, n, g, sp, seg_scratch, d_out, nullptr, 0, nullptr, nullptr, 0, 0, false, true, false));
         *d_out_len = reinterpret_cast<uint64_t *>(seg_scratch + sp.off_ent + sp.ent.off_outlen);
         *d_overflow = reinterpret_cast<uint32_t *>(seg_scratch + sp.off_ent + sp.ent.off_ovf);
         *d_raw_tail = reinterpret_cast<uint64_t *>(seg_scratch + sp.off_ent + sp.ent.off_tail);
         return 0;
     }
-    ctx->band_segments = 1;
+    if (raw) ctx->bands.erase(d_out);
     const size_t want = ((size_t)n * pl.nchunks + HUFF_WARPS - 1) / HUFF_WARPS;
     const unsigned grid = (unsigned)std::min<size_t>(want, (size_t)ctx->sm_count * HUFF_CTAS_PER_SM);
     if (raw) k_huff<true><<<grid, 32 * HUFF_WARPS, 0, st>>>(P, T);
@@ -1394,15 +1404,18 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
 }
 
 
-// Splice the S raw segments the last launch_jpeg_entropy(raw) left in ctx->d_raw into the band's scan bytes.
-int launch_band_splice_segments(pixo_b200_ctx *ctx, uint64_t base_bit, uint32_t base_tail, bool last,
-                                uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap, uint64_t **d_out_len,
-                                uint32_t **d_overflow)
+// Splice the raw segments pixo_b200_jpeg_band_entropy_dev left in the caller's buffer d_raw into the
+// band's scan bytes.  (Call only when the context knows d_raw as a segmented band.)
+int launch_band_splice_segments(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t base_bit, uint32_t base_tail,
+                                bool last, uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap,
+                                uint64_t **d_out_len, uint32_t **d_overflow)
 {
-    const uint32_t S = ctx->band_segments;
-    const SegPlan sp = plan_segments(1, S, ctx->band_mcus, ctx->band_bpm, ctx->band_cap);
+    const pixo_b200_ctx::BandInfo bi = ctx->bands.at(d_raw);
     FrameGeometry g;
-    g.y_per_mcu = ctx->band_geo_y_per_mcu; g.has_chroma = ctx->band_has_chroma;
+    g.y_per_mcu = bi.y_per_mcu; g.has_chroma = bi.has_chroma;
+    const uint64_t mcu_raw = (uint64_t)g.y_per_mcu * 64 * (g.has_chroma ? 3 : 1);
+    const SegPlan sp = plan_segments(1, bi.segments, bi.mcus, bi.bpm, mcu_raw);
+    PIXO_TRY(ensure_dev(ctx, ctx->d_raw, sp.total));
     EntParams P;
     memset(&P, 0, sizeof P);
     HuffDev T;
@@ -1410,9 +1423,16 @@ int launch_band_splice_segments(pixo_b200_ctx *ctx, uint64_t base_bit, uint32_t 
     PIXO_CUDA(ctx, cudaMemsetAsync(d_scratch, 0, 256, ctx->stream));
     *d_out_len = reinterpret_cast<uint64_t *>(d_scratch);
     *d_overflow = reinterpret_cast<uint32_t *>(d_scratch + 8);
-    return launch_segmented(ctx, P, T, 1, g, sp, reinterpret_cast<uint8_t *>(ctx->d_raw.ptr), d_out, out_cap, *d_out_len,
-                            *d_overflow, base_bit, base_tail, last, false, true);
+    return launch_segmented(ctx, P, T, 1, g, sp, reinterpret_cast<uint8_t *>(ctx->d_raw.ptr), const_cast<uint8_t *>(d_raw),
+                            d_out, out_cap, *d_out_len, *d_overflow, base_bit, base_tail, last, false, true);
 }
 
+size_t band_raw_bytes_segmented(const FrameGeometry &g)
+{
+    const uint64_t bpm = g.y_per_mcu + (g.has_chroma ? 2 : 0);
+    const uint32_t S = segments_for(1, g.total_mcus(), bpm);
+    if (S < 2) return 0;
+    return plan_segments(1, S, g.total_mcus(), bpm, (uint64_t)g.y_per_mcu * 64 * (g.has_chroma ? 3 : 1)).raw_total;
+}
 
 }  // namespace pixo

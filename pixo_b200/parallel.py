@@ -132,7 +132,9 @@ class DeviceBandCoder:
         if not self.ny:
             return 0, 0
         w, bh = self.geo[0], self.geo[1]
-        cap = (w * bh * 3 // 2 + 65536) // 16 * 16     # a JPEG band is far below half its raw size; grown on demand
+        # as many bytes as the band's pixels + 1 MiB: lets a long band be coded in segments (short
+        # look-back chains), whose raw strings need more room than the finished JPEG; grown on demand
+        cap = (w * bh * 3 + (1 << 20)) // 16 * 16
         s = (C.c_int32 * 3)(*[int(v) for v in seed])
         hp = None if hist is None else np.ascontiguousarray(hist, np.uint64).ctypes.data_as(_lib.u64p)
         for _ in range(2):

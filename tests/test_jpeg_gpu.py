@@ -310,3 +310,22 @@ def test_restart_intervals_on_the_gpu_coder(po, gpu_ctx, w, h, ss, ri):
     g = po.gen_noise(w, h, 1, 5)
     o = JpegOptions(w, h, ColorType.Gray, 85, Subsampling.S444, ri)
     assert jpeg.encode(g, o, ctx=gpu_ctx) == po.jpeg_encode(g, w, h, 0, 85, 0, ri, False)
+
+
+@pytest.mark.parametrize("segments", [2, 5, 64])
+def test_segmented_entropy_coding_forced(po, gpu_ctx, monkeypatch, segments):
+    """Large single frames are cut into runs of MCUs that are Huffman-coded as independent bit
+    strings and spliced on the device (k_huff<RAW> + k_seg_*).  The size threshold keeps small frames
+    on the single-pass kernel, so force the segment count here: ragged last segments, segments
+    shorter than a chunk, DC prediction across segment borders, optimised tables, dense q=100 noise
+    (0xFF stuffing across the borders), gray / 4:4:4 / 4:2:0."""
+    monkeypatch.setenv("PIXO_B200_SEGMENTS", str(segments))
+    for (w, h, ct, ss) in ((640, 480, 2, 1), (333, 222, 2, 0), (257, 129, 0, 0), (48, 32, 2, 1)):
+        img = po.gen_noise(w, h, 3 if ct == 2 else 1, 7)
+        for q, opt in ((80, False), (100, False), (55, True)):
+            o = JpegOptions(w, h, ColorType(ct), q, Subsampling(ss), None, opt)
+            assert jpeg.encode(img, o, ctx=gpu_ctx) == po.jpeg_encode(img, w, h, ct, q, ss, 0, opt), (w, h, q, opt)
+    frames = np.stack([po.gen_noise(512, 256, 3, s) for s in (1, 2, 3)])
+    got = jpeg.encode_batch(frames, JpegOptions(512, 256, ColorType.Rgb, 90, Subsampling.S420), ctx=gpu_ctx)
+    for k in range(3):
+        assert got[k] == po.jpeg_encode(frames[k], 512, 256, 2, 90, 1), k

@@ -54,6 +54,18 @@ def test_tiled_frame_bands_on_one_gpu(po, gpu_ctx, w, h, world, ct, ss):
     assert gpu_ctx.host_fallbacks == 0
 
 
+def test_tiled_frame_bands_coded_in_segments(po, gpu_ctx, monkeypatch):
+    """Long bands are themselves cut into segments (a 16 384^2 frame on 8 GPUs: 16 per band); force
+    it on a small frame."""
+    from pixo_b200 import parallel, synthetic
+    monkeypatch.setenv("PIXO_B200_SEGMENTS", "3")
+    w, h = 640, 400
+    frame = synthetic.noise(w, h, 3, 11)
+    for q, opt in ((85, False), (100, True)):
+        coders, _keep = _device_coders(gpu_ctx, frame, w, h, 2, 1, q, 4)
+        assert parallel.encode_tiled_local(coders, w, h, 2, q, 1, opt) == po.jpeg_encode(frame, w, h, 2, q, 1, 0, opt)
+
+
 def test_c4_full_size_16384_tiled_and_whole(po, gpu_ctx):
     """BASELINE config C4 at its stated size: one 16 384 x 16 384 RGB frame (805 MB, 6.3 M blocks),
     q=80 4:2:0 - eight bands with the distributed entropy stage AND the plain single-context encode,
