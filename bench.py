@@ -411,6 +411,7 @@ def c4_config(env: Env, steps: int) -> dict:
 
     coders = [parallel.DeviceBandCoder(env.ctx, dy, dcb, dcr, w, b.px_row1 - b.px_row0, 2, 1, b.y_blocks, b.c_blocks)
               for b, (dy, dcb, dcr) in zip(my_bands, coefs)]
+    nonempty = [b.y_blocks > 0 for b in bands]
 
     def tiled_once():
         # transform of every band this rank owns, then the distributed entropy stage; the timed region
@@ -422,17 +423,17 @@ def c4_config(env: Env, steps: int) -> dict:
                                                           b.c_blocks * 64, 0, None))
         if env.world == 1:
             out["parts"], out["hist"] = parallel.tiled_scan_parts_local(coders, False)
-        else:
-            out["parts"], out["hist"] = parallel.tiled_scan_parts(coders[0], False, env.rank, env.world)
+        else:   # stream-ordered: predictors, bit counts and offsets never leave the devices
+            out["parts"], out["hist"] = parallel.tiled_scan_parts_async(coders[0], nonempty, env.rank, env.world)
 
     ms_tiled = env.timed(tiled_once, max(2, steps // 2), warm=2)
     if env.rank == 0:
         out["jpg"] = parallel.assemble_tiled(out["parts"], out["hist"], w, h, 2, q, 1)
     res = {"geometry": "16384x16384", "quality": q, "bands": nbands,
            "tiled": {"mpix_s": w * h / (ms_tiled * 1e-3) / 1e6, "ms": ms_tiled,
-                     "what": ("band r on rank r: transform + k_huff<RAW> + splice per GPU; all-gather of DC predictors and of "
-                              "(bits, tail), gather of scan bytes to rank 0 over NCCL; timed until the scan bytes are on rank "
-                              "0's device" if env.world > 1 else
+                     "what": ("band r on rank r: transform + k_huff<RAW> + splice per GPU, stream-ordered (predictors, bit counts "
+                              "and offsets stay in device memory); all-gathers of 3+2+2 words and a gather of the scan bytes to "
+                              "rank 0 over NCCL; one host wait (byte counts); timed until the scan bytes are on rank 0's device" if env.world > 1 else
                               "8 bands, every stage of the distributed path, run one after the other in ONE context"),
                      "nccl_ranks": env.world}}
     tiled_sha = sha(out["jpg"]) if env.rank == 0 else None

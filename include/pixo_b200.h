@@ -238,6 +238,22 @@ int pixo_b200_jpeg_band_entropy_dev(pixo_b200_ctx *ctx, const int16_t *d_y, cons
 int pixo_b200_jpeg_band_splice_dev(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t nbits,
                                    uint64_t start_bit, uint32_t tail_in, uint32_t is_last_band,
                                    uint8_t *d_out, size_t out_cap, uint64_t *out_len);
+/* Stream-ordered variants: everything that crosses a band boundary stays in DEVICE memory, so a
+ * rank can queue transform -> (NCCL all-gather of predictors) -> coding -> (all-gather of bits) ->
+ * splice without a single host synchronisation; only the final byte count is read back.
+ *   d_dc_seed:   int32[3] in device memory (written by an earlier operation on the stream)
+ *   d_bits_tail: uint64[2] out, {bit count, last 7 bits}
+ *   d_offset:    uint64[3] in, {start_bit, the last 7 bits of the stream before this band, is_last_band}
+ *   d_flags:     uint32, OR-ed: bit 0 a capacity was too small, bit 1 device fault (caller zeroes it)
+ * raw_cap must be at least the band's pixel bytes + 1 MiB. */
+int pixo_b200_jpeg_band_entropy_dev_async(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb,
+                                          const int16_t *d_cr, uint32_t width, uint32_t band_height,
+                                          uint32_t color_type, uint32_t subsampling,
+                                          const int32_t *d_dc_seed, const uint64_t *hist, uint8_t *d_raw,
+                                          size_t raw_cap, uint64_t *d_bits_tail, uint32_t *d_flags);
+int pixo_b200_jpeg_band_splice_dev_async(pixo_b200_ctx *ctx, const uint8_t *d_raw, const uint64_t *d_offset,
+                                         uint8_t *d_out, size_t out_cap, uint64_t *d_out_len,
+                                         uint32_t *d_flags);
 int pixo_b200_jpeg_band_entropy(const int16_t *y, const int16_t *cb, const int16_t *cr, uint32_t width,
                                 uint32_t band_height, uint32_t color_type, uint32_t subsampling,
                                 const int32_t dc_seed[3], const uint64_t *hist, uint8_t *raw,

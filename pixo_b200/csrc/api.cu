@@ -1152,6 +1152,35 @@ int pixo_b200_jpeg_band_splice_dev(pixo_b200_ctx *ctx, const uint8_t *d_raw, uin
     return 0;
 }
 
+int pixo_b200_jpeg_band_entropy_dev_async(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb,
+                                          const int16_t *d_cr, uint32_t width, uint32_t band_height,
+                                          uint32_t color_type, uint32_t subsampling,
+                                          const int32_t *d_dc_seed, const uint64_t *hist, uint8_t *d_raw,
+                                          size_t raw_cap, uint64_t *d_bits_tail, uint32_t *d_flags)
+{
+    if (!ctx) return set_error(nullptr, PIXO_B200_ERR_INVALID_ARGUMENT, "ctx is null");
+    PIXO_TRY(validate_jpeg(ctx, width, band_height, color_type, subsampling));
+    if (!d_y || !d_raw || !d_dc_seed || !d_bits_tail || !d_flags || (color_type != PIXO_B200_GRAY && (!d_cb || !d_cr)))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null buffer");
+    if ((raw_cap & 3) || (reinterpret_cast<uintptr_t>(d_raw) & 15))
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "raw buffer must be 16-byte aligned, capacity multiple of 4");
+    const FrameGeometry g = make_geometry(width, band_height, color_type, subsampling);
+    HuffTables t;
+    tables_from(hist, g.has_chroma, t);
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_band_entropy_async(ctx, d_y, d_cb, d_cr, g, t, d_dc_seed, d_raw, raw_cap, d_bits_tail, d_flags);
+}
+
+int pixo_b200_jpeg_band_splice_dev_async(pixo_b200_ctx *ctx, const uint8_t *d_raw, const uint64_t *d_offset,
+                                         uint8_t *d_out, size_t out_cap, uint64_t *d_out_len,
+                                         uint32_t *d_flags)
+{
+    if (!ctx || !d_raw || !d_offset || !d_out || !d_out_len || !d_flags)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "null argument");
+    PIXO_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_band_splice_async(ctx, d_raw, d_offset, d_out, out_cap, d_out_len, d_flags);
+}
+
 int pixo_b200_jpeg_band_entropy(const int16_t *y, const int16_t *cb, const int16_t *cr, uint32_t width,
                                 uint32_t band_height, uint32_t color_type, uint32_t subsampling,
                                 const int32_t dc_seed[3], const uint64_t *hist, uint8_t *raw,

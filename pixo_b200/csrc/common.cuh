@@ -141,6 +141,11 @@ size_t splice_scratch_bytes(uint64_t nbits);
 int launch_band_splice_segments(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t base_bit, uint32_t base_tail,
                                 bool last, uint8_t *d_scratch, uint8_t *d_out, uint64_t out_cap,
                                 uint64_t **d_out_len, uint32_t **d_overflow);
+int launch_band_entropy_async(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb, const int16_t *d_cr,
+                              const FrameGeometry &g, const HuffTables &t, const int *d_seed, uint8_t *d_raw,
+                              uint64_t raw_cap, uint64_t *d_bits_tail, uint32_t *d_flags);
+int launch_band_splice_async(pixo_b200_ctx *ctx, const uint8_t *d_raw, const uint64_t *d_offset, uint8_t *d_out,
+                             uint64_t out_cap, uint64_t *d_out_len, uint32_t *d_flags);
 // bytes a band's raw buffer needs so that the band can be coded in segments (0: never segmented)
 size_t band_raw_bytes_segmented(const FrameGeometry &g);
 int launch_splice(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t nbits, uint32_t phase, uint32_t tail_in,

@@ -80,6 +80,7 @@ struct EntParams {
     uint32_t seg_per_img;
     uint32_t nblocks_last;         // blocks of an image's last segment (the others have nblocks)
     size_t seg_y_stride, seg_c_stride;   // int16 elements between the segments of an image
+    const int *dc_seed_dev;        // the same three predictors in device memory (stream-ordered callers), or null
     int dc_seed[3];                // DC predictors (Y, Cb, Cr) before block 0: 0 for a whole image, the previous
                                    // band's last DCs when the arrays are one band of a frame tiled over several GPUs
     unsigned long long *out_tail;  // RAW only: [n] the stream's last 7 bits
@@ -97,8 +98,14 @@ struct EntParams {
 constexpr int CB = 32;             // blocks per chunk == one warp
 static_assert(CB * 4 == 128, "the slot word stride is spelled out in code_block's PTX");
 constexpr int HUFF_WARPS = 4;      // warps per CTA (they only share the tables)
-constexpr int HUFF_CTAS_PER_SM = 6;
-constexpr int SLOT_W = 16;         // words of a block's code kept in shared memory (512 bits)
+#ifndef HUFF_CTAS_N
+#define HUFF_CTAS_N 6
+#endif
+constexpr int HUFF_CTAS_PER_SM = HUFF_CTAS_N;
+#ifndef HUFF_SLOT_W
+#define HUFF_SLOT_W 16
+#endif
+constexpr int SLOT_W = HUFF_SLOT_W;  // words of a block's code kept in shared memory (16: 512 bits)
 constexpr int MAX_W = 54;          // worst case: 27 + 63 * 26 = 1665 bits
 constexpr int WIN_W = 256;         // stream words assembled per round (32 bytes per lane)
 constexpr int WIN_B = WIN_W * 4;
@@ -451,6 +458,7 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
             // DC predictors restart with the interval (src/jpeg/mod.rs:1433-1443)
             const bool dc_reset = P.rst_mcus && m % P.rst_mcus == 0 && (k == 0 || k >= P.y_per_mcu);
             // (a later segment's first block follows the previous segment's last one in the same array)
+            if (P.dc_seed_dev && idx == 0 && !seg_prev) seed = P.dc_seed_dev[k < P.y_per_mcu ? 0 : (k == P.y_per_mcu ? 1 : 2)];
             const int prev_dc = dc_reset ? 0 : ((idx || seg_prev) ? arr[((long long)idx - 1) * 64] : seed);
             const uint4 *src = reinterpret_cast<const uint4 *>(arr + idx * 64);
             uint32_t e0 = 0, e1 = 0;
@@ -1004,6 +1012,7 @@ struct SegParams {
     uint32_t S, max_tiles;
     unsigned long long base_bit;    // bits of the stream before segment 0 (a band of a tiled frame; 0 otherwise)
     uint32_t base_tail, last_band;  // the stream's last base_bit % 8 bits; 1: the last segment ends the stream (1-pad)
+    const unsigned long long *base_dev;   // {base_bit, the previous band's last 7 bits, last_band} in device memory, or null
     SegRec *rec;                    // [n * S]
     uint32_t *ntiles;               // [n]
     uint32_t *cnt;                  // [n][max_tiles] 0xFF counts, then their exclusive prefix
@@ -1025,19 +1034,37 @@ __device__ __forceinline__ uint32_t seg_byte(const uint8_t *raw, const SegRec &r
     return v;
 }
 
+// a band's totals for the exchange with the other ranks: {bits, last 7 bits}, and its flags
+__global__ void k_band_totals(const unsigned long long *bits, const unsigned long long *tails, const uint32_t *ovf,
+                              uint32_t S, unsigned long long *out2, uint32_t *flags)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    unsigned long long total = 0, tail = 0;
+    uint32_t f = 0;
+    for (uint32_t q = 0; q < S; ++q) {
+        total += bits[q];
+        if (bits[q]) tail = tails[q];
+        f |= ovf[q];
+    }
+    out2[0] = total;
+    out2[1] = tail & 0x7Full;
+    if (f) atomicOr(flags, f);
+}
+
 __global__ void k_seg_prefix(const __grid_constant__ SegParams P)
 {
     if (threadIdx.x) return;
     const uint32_t i = blockIdx.x;
     unsigned long long start = P.base_bit, byte_off = 0;
-    uint32_t tail_prev = P.base_tail, tile_off = 0, bad = 0;
+    uint32_t tail_prev = P.base_tail, tile_off = 0, bad = 0, last_band = P.last_band;
+    if (P.base_dev) { start = P.base_dev[0]; tail_prev = (uint32_t)P.base_dev[1]; last_band = (uint32_t)P.base_dev[2]; }
     for (uint32_t s = 0; s < P.S; ++s) {
         const uint32_t q = i * P.S + s;
         SegRec r;
         r.nbits = P.bits[q];
         r.phase = (uint32_t)(start & 7);
         r.tail_in = tail_prev & ((1u << r.phase) - 1u);
-        r.last = (s == P.S - 1 && P.last_band) ? 1u : 0u;
+        r.last = (s == P.S - 1 && last_band) ? 1u : 0u;
         const unsigned long long tbits = r.phase + r.nbits;
         r.nbytes = (tbits >> 3) + ((r.last && (tbits & 7)) ? 1 : 0);
         r.byte_off = byte_off;
@@ -1194,6 +1221,25 @@ int launch_splice(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64_t nbits, uint
     return 0;
 }
 
+static void make_huff_dev(const HuffTables &t, HuffDev *Tp)
+{
+    HuffDev &T = *Tp;
+    memset(&T, 0, sizeof T);
+    for (int k = 0; k < 2; ++k) {
+        for (int cat = 0; cat < 12; ++cat)
+            if (t.len[k][cat])
+                T.dc[k][cat] = ((uint32_t)t.code[k][cat] << (32 - t.len[k][cat])) | (uint32_t)(t.len[k][cat] + cat);
+        for (int rs = 0; rs < 256; ++rs) {
+            const int cat = rs & 15, run = rs >> 4;
+            if (!t.len[2 + k][rs] || cat > 10) continue;
+            const uint32_t e = ((uint32_t)t.code[2 + k][rs] << (32 - t.len[2 + k][rs])) | (uint32_t)(t.len[2 + k][rs] + cat);
+            if (rs == 0x00) T.ac[k][AC_EOB] = e;
+            else if (rs == 0xF0) T.ac[k][AC_ZRL] = e;
+            else if (cat >= 1) T.ac[k][run * AC_STRIDE + cat - 1] = e;
+        }
+    }
+}
+
 // How many segments per image: enough chains to keep a look-back short (~64 chains in flight), none
 // shorter than 48 chunks.  1 = do not segment.
 static uint32_t segments_for(uint32_t n, uint64_t total_mcus, uint64_t bpm)
@@ -1252,7 +1298,7 @@ static SegPlan plan_segments(uint32_t n, uint32_t S, uint64_t total_mcus, uint64
 static int launch_segmented(pixo_b200_ctx *ctx, EntParams P, const HuffDev &T, uint32_t n, const FrameGeometry &g,
                             const SegPlan &sp, uint8_t *seg_scratch, uint8_t *raw_area, uint8_t *d_out, uint64_t out_cap,
                             uint64_t *d_out_len, uint32_t *d_overflow, uint64_t base_bit, uint32_t base_tail,
-                            bool last_stream, bool code, bool splice)
+                            bool last_stream, bool code, bool splice, const uint64_t *base_dev = nullptr)
 {
     cudaStream_t st = ctx->stream;
     const uint64_t bpm = g.y_per_mcu + (g.has_chroma ? 2 : 0);
@@ -1291,6 +1337,7 @@ static int launch_segmented(pixo_b200_ctx *ctx, EntParams P, const HuffDev &T, u
     Q.tails = reinterpret_cast<const unsigned long long *>(raw_area + sp.off_tails);
     Q.S = sp.S; Q.max_tiles = sp.max_tiles;
     Q.base_bit = base_bit; Q.base_tail = base_tail; Q.last_band = last_stream ? 1u : 0u;
+    Q.base_dev = reinterpret_cast<const unsigned long long *>(base_dev);
     Q.rec = reinterpret_cast<SegRec *>(seg_scratch + sp.off_rec);
     Q.ntiles = reinterpret_cast<uint32_t *>(seg_scratch + sp.off_ntiles);
     Q.cnt = reinterpret_cast<uint32_t *>(seg_scratch + sp.off_cnt);
@@ -1346,25 +1393,13 @@ int launch_jpeg_entropy(pixo_b200_ctx *ctx, const int16_t *d_y, size_t y_stride,
     P.out = d_out; P.out_cap = out_cap;
     P.out_tail = reinterpret_cast<unsigned long long *>(d_scratch + pl.off_tail);
     for (int k = 0; k < 3; ++k) P.dc_seed[k] = dc_seed ? dc_seed[k] : 0;
+    P.dc_seed_dev = nullptr;
     *d_out_len = P.out_len;
     *d_overflow = P.overflow;
     if (raw) *d_raw_tail = reinterpret_cast<uint64_t *>(P.out_tail);
 
     HuffDev T;
-    memset(&T, 0, sizeof T);
-    for (int k = 0; k < 2; ++k) {
-        for (int cat = 0; cat < 12; ++cat)
-            if (t.len[k][cat])
-                T.dc[k][cat] = ((uint32_t)t.code[k][cat] << (32 - t.len[k][cat])) | (uint32_t)(t.len[k][cat] + cat);
-        for (int rs = 0; rs < 256; ++rs) {
-            const int cat = rs & 15, run = rs >> 4;
-            if (!t.len[2 + k][rs] || cat > 10) continue;
-            const uint32_t e = ((uint32_t)t.code[2 + k][rs] << (32 - t.len[2 + k][rs])) | (uint32_t)(t.len[2 + k][rs] + cat);
-            if (rs == 0x00) T.ac[k][AC_EOB] = e;
-            else if (rs == 0xF0) T.ac[k][AC_ZRL] = e;
-            else if (cat >= 1) T.ac[k][run * AC_STRIDE + cat - 1] = e;
-        }
-    }
+    make_huff_dev(t, &T);
     cudaStream_t st = ctx->stream;
     PIXO_CUDA(ctx, cudaMemsetAsync(d_scratch, 0, pl.zero_bytes, st));
     P.seg_per_img = 1; P.nblocks_last = P.nblocks; P.seg_y_stride = P.seg_c_stride = 0;
@@ -1425,6 +1460,65 @@ int launch_band_splice_segments(pixo_b200_ctx *ctx, const uint8_t *d_raw, uint64
     *d_overflow = reinterpret_cast<uint32_t *>(d_scratch + 8);
     return launch_segmented(ctx, P, T, 1, g, sp, reinterpret_cast<uint8_t *>(ctx->d_raw.ptr), const_cast<uint8_t *>(d_raw),
                             d_out, out_cap, *d_out_len, *d_overflow, base_bit, base_tail, last, false, true);
+}
+
+// Stream-ordered band coding: predictors from device memory in, {bits, tail} and flags to device
+// memory out, no host synchronisation.  Always uses the segment machinery (S >= 1) with the strings
+// in the caller's buffer.
+int launch_band_entropy_async(pixo_b200_ctx *ctx, const int16_t *d_y, const int16_t *d_cb, const int16_t *d_cr,
+                              const FrameGeometry &g, const HuffTables &t, const int *d_seed, uint8_t *d_raw,
+                              uint64_t raw_cap, uint64_t *d_bits_tail, uint32_t *d_flags)
+{
+    const uint64_t bpm = g.y_per_mcu + (g.has_chroma ? 2 : 0);
+    const uint64_t mcu_raw = (uint64_t)g.y_per_mcu * 64 * (g.has_chroma ? 3 : 1);
+    uint32_t S = ctx->no_segments ? 1 : segments_for(1, g.total_mcus(), bpm);
+    SegPlan sp = plan_segments(1, S, g.total_mcus(), bpm, mcu_raw);
+    if (sp.raw_total > raw_cap && sp.S > 1) sp = plan_segments(1, 1, g.total_mcus(), bpm, mcu_raw);
+    if (sp.raw_total > raw_cap)
+        return set_error(ctx, PIXO_B200_ERR_OUTPUT_TOO_SMALL, "raw capacity %llu too small (need %zu)",
+                         (unsigned long long)raw_cap, sp.raw_total);
+    if ((g.ny + 2 * g.nc) > 0xFFFFFFFFull)
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "entropy stage: too many blocks per call");
+    PIXO_TRY(ensure_dev(ctx, ctx->d_raw, sp.total));
+    auto *seg_scratch = reinterpret_cast<uint8_t *>(ctx->d_raw.ptr);
+    EntParams P;
+    memset(&P, 0, sizeof P);
+    P.y = d_y; P.cb = d_cb; P.cr = d_cr;
+    P.bpm = (uint32_t)bpm; P.y_per_mcu = g.y_per_mcu;
+    P.dc_seed_dev = d_seed;
+    HuffDev T;
+    make_huff_dev(t, &T);
+    pixo_b200_ctx::BandInfo bi;
+    bi.segments = sp.S; bi.bpm = (uint32_t)bpm; bi.y_per_mcu = g.y_per_mcu; bi.has_chroma = g.has_chroma;
+    bi.mcus = g.total_mcus();
+    ctx->bands[d_raw] = bi;
+    PIXO_TRY(launch_segmented(ctx, P, T, 1, g, sp, seg_scratch, d_raw, nullptr, 0, nullptr, nullptr, 0, 0, false, true, false));
+    k_band_totals<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long *>(d_raw + sp.off_bits),
+                                             reinterpret_cast<const unsigned long long *>(d_raw + sp.off_tails),
+                                             reinterpret_cast<const uint32_t *>(seg_scratch + sp.off_ent + sp.ent.off_ovf), sp.S,
+                                             reinterpret_cast<unsigned long long *>(d_bits_tail), d_flags);
+    ctx->launches += 1;
+    PIXO_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+int launch_band_splice_async(pixo_b200_ctx *ctx, const uint8_t *d_raw, const uint64_t *d_offset, uint8_t *d_out,
+                             uint64_t out_cap, uint64_t *d_out_len, uint32_t *d_flags)
+{
+    auto it = ctx->bands.find(d_raw);
+    if (it == ctx->bands.end())
+        return set_error(ctx, PIXO_B200_ERR_INVALID_ARGUMENT, "this raw buffer was not coded by pixo_b200_jpeg_band_entropy_dev_async");
+    const pixo_b200_ctx::BandInfo bi = it->second;
+    FrameGeometry g;
+    g.y_per_mcu = bi.y_per_mcu; g.has_chroma = bi.has_chroma;
+    const SegPlan sp = plan_segments(1, bi.segments, bi.mcus, bi.bpm, (uint64_t)g.y_per_mcu * 64 * (g.has_chroma ? 3 : 1));
+    PIXO_TRY(ensure_dev(ctx, ctx->d_raw, sp.total));
+    EntParams P;
+    memset(&P, 0, sizeof P);
+    HuffDev T;
+    memset(&T, 0, sizeof T);
+    return launch_segmented(ctx, P, T, 1, g, sp, reinterpret_cast<uint8_t *>(ctx->d_raw.ptr), const_cast<uint8_t *>(d_raw),
+                            d_out, out_cap, d_out_len, d_flags, 0, 0, false, false, true, d_offset);
 }
 
 size_t band_raw_bytes_segmented(const FrameGeometry &g)

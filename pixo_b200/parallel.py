@@ -292,6 +292,118 @@ def tiled_scan_parts(coder, optimize_huffman: bool, rank: int, world: int, dst: 
     return (parts if rank == dst else None), hist
 
 
+class ThreadComm:
+    """all_gather / gather among `world` THREADS of one process (one band per thread, every band with
+    a context of its own on the same GPU): lets the multi-rank flow run - collectives included - where
+    there is only one device.  Device work is synchronised before tensors change hands."""
+
+    def __init__(self, world: int):
+        import threading
+        self.world = world
+        self.slots = [None] * world
+        self.barrier = threading.Barrier(world)
+
+    def all_gather(self, rank, t):
+        import torch
+        torch.cuda.current_stream().synchronize()
+        self.slots[rank] = t
+        self.barrier.wait()
+        out = torch.stack([x.clone() for x in self.slots])
+        torch.cuda.current_stream().synchronize()
+        self.barrier.wait()
+        return out
+
+    def gather(self, rank, t, dst):
+        allv = self.all_gather(rank, t)
+        return [allv[r] for r in range(self.world)] if rank == dst else None
+
+
+class _DistComm:
+    def __init__(self, world):
+        self.world = world
+
+    def all_gather(self, rank, t):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return t.reshape(1, *t.shape)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t)
+        return torch.stack(out)
+
+    def gather(self, rank, t, dst):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return [t]
+        bufs = [torch.empty_like(t) for _ in range(self.world)] if rank == dst else None
+        dist.gather(t, bufs, dst=dst)
+        return bufs
+
+
+def tiled_scan_parts_async(coder, nonempty: list[bool], rank: int, world: int, dst: int = 0, comm=None):
+    """`tiled_scan_parts` without host round trips: every value that crosses a band boundary stays
+    on the device (pixo_b200_jpeg_band_*_async), the collectives are queued on the same stream as the
+    kernels, and the host waits once - for the byte counts it needs to size the final gather.
+    Standard Huffman tables only (optimised tables need the all-reduced statistics on the host).
+    `coder` is a DeviceBandCoder whose context runs on torch's current stream; nonempty[r] = band r
+    holds at least one MCU (known from the band plan)."""
+    import torch
+    dev, lib, ctx = coder.dev, coder.lib, coder.ctx
+    i64 = torch.int64
+    comm = comm or _DistComm(world)
+    all_gather = lambda t: comm.all_gather(rank, t)
+
+    prev = next((r for r in range(rank - 1, -1, -1) if nonempty[r]), None)
+    is_last = coder.ny > 0 and not any(nonempty[rank + 1:])
+    # 1. DC predictors: the last DC of every band's three arrays
+    if coder.ny:
+        ld = torch.stack([coder.d_y[coder.ny - 1, 0], coder.d_cb[coder.nc - 1, 0] if coder.nc else coder.d_y[0, 0] * 0,
+                          coder.d_cr[coder.nc - 1, 0] if coder.nc else coder.d_y[0, 0] * 0]).to(torch.int32)
+    else:
+        ld = torch.zeros(3, dtype=torch.int32, device=dev)
+    g = all_gather(ld)
+    seed = (g[prev] if prev is not None else torch.zeros(3, dtype=torch.int32, device=dev)).contiguous()
+    # 2. this band's code as a raw bit string
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    bits_tail = torch.zeros(2, dtype=i64, device=dev)
+    if coder.ny:
+        w, bh = coder.geo[0], coder.geo[1]
+        cap = (w * bh * 3 + (1 << 20)) // 16 * 16
+        if coder.raw is None or coder.raw.numel() < cap:
+            coder.raw = torch.empty(cap, dtype=torch.uint8, device=dev)
+        _lib.check(ctx.handle, lib.pixo_b200_jpeg_band_entropy_dev_async(
+            ctx.handle, coder._p(coder.d_y), coder._p(coder.d_cb), coder._p(coder.d_cr), *coder.geo, int(seed.data_ptr()),
+            None, int(coder.raw.data_ptr()), coder.raw.numel() // 16 * 16, int(bits_tail.data_ptr()), int(flags.data_ptr())))
+    # 3. bit offsets: bits of all bands before this one; the previous non-empty band's last 7 bits
+    bt = all_gather(bits_tail)
+    start = bt[:rank, 0].sum() if rank else torch.zeros((), dtype=i64, device=dev)
+    tail_prev = bt[prev, 1] if prev is not None else torch.zeros((), dtype=i64, device=dev)
+    offset = torch.stack([start, tail_prev, torch.full((), int(is_last), dtype=i64, device=dev)]).contiguous()
+    # 4. splice
+    out_len = torch.zeros(1, dtype=i64, device=dev)
+    if coder.ny:
+        cap = coder.raw.numel() * 2 + 64
+        if coder.out is None or coder.out.numel() < cap:
+            coder.out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        _lib.check(ctx.handle, lib.pixo_b200_jpeg_band_splice_dev_async(
+            ctx.handle, int(coder.raw.data_ptr()), int(offset.data_ptr()), int(coder.out.data_ptr()), coder.out.numel(),
+            int(out_len.data_ptr()), int(flags.data_ptr())))
+    # 5. the one host wait: byte counts (and flags) of all bands
+    info = all_gather(torch.cat([out_len, flags.to(i64)])).cpu().numpy()
+    if int(info[:, 1].max()):
+        raise _lib.PixoError(_lib.ERR_CUDA, f"band entropy stage reported flags {info[:, 1].tolist()}")
+    sizes = info[:, 0]
+    body = coder.out[: int(sizes[rank])] if coder.ny else torch.empty(0, dtype=torch.uint8, device=dev)
+    if world == 1:
+        return [body], None
+    mx = int(max(sizes.max(), 1))
+    pad = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    pad[: body.numel()] = body
+    bufs = comm.gather(rank, pad, dst)
+    return ([bufs[r][: int(sizes[r])] for r in range(world)] if rank == dst else None), None
+
+
 def encode_tiled_local(coders: list, width: int, height: int, color_type: int, quality: int, subsampling: int,
                        optimize_huffman: bool = False) -> bytes:
     """The same stage sequence with every band in THIS process (one GPU context, or the host

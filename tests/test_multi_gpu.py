@@ -66,6 +66,47 @@ def test_tiled_frame_bands_coded_in_segments(po, gpu_ctx, monkeypatch):
         assert parallel.encode_tiled_local(coders, w, h, 2, q, 1, opt) == po.jpeg_encode(frame, w, h, 2, q, 1, 0, opt)
 
 
+@pytest.mark.parametrize("w,h,world,segs", [(1024, 640, 4, None), (640, 400, 3, "2"), (100, 40, 5, None)])
+def test_stream_ordered_band_flow_with_thread_ranks(po, monkeypatch, w, h, world, segs):
+    """The flow without host round trips (pixo_b200_jpeg_band_*_async: predictors, bit counts and
+    offsets stay in device memory) with `world` ranks as threads of this process, a context and a
+    stream each: the collectives are real exchanges between the ranks' device tensors."""
+    import threading
+    import torch
+    import pixo_b200
+    from pixo_b200 import parallel, synthetic
+    if segs:
+        monkeypatch.setenv("PIXO_B200_SEGMENTS", segs)
+    frame = synthetic.noise(w, h, 3, 21)
+    bands = parallel.plan_bands(w, h, world)
+    nonempty = [b.y_blocks > 0 for b in bands]
+    for q in (80, 100):
+        comm = parallel.ThreadComm(world)
+        res, errs = {}, []
+
+        def work(rank):
+            try:
+                torch.cuda.set_device(0)
+                stream = torch.cuda.Stream()
+                with torch.cuda.stream(stream):
+                    ctx = pixo_b200.Context(0)
+                    ctx.set_stream(stream.cuda_stream)
+                    coders, _keep = _device_coders(ctx, frame, w, h, 2, 1, q, world)
+                    parts, _ = parallel.tiled_scan_parts_async(coders[rank], nonempty, rank, world, comm=comm)
+                    if rank == 0:
+                        res["jpg"] = parallel.assemble_tiled(parts, None, w, h, 2, q, 1)
+                    assert ctx.host_fallbacks == 0
+            except BaseException as e:   # noqa: BLE001 - re-raised in the main thread
+                errs.append(e)
+                comm.barrier.abort()
+
+        ths = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in ths: t.start()
+        for t in ths: t.join()
+        assert not errs, errs
+        assert res["jpg"] == po.jpeg_encode(frame, w, h, 2, q, 1), q
+
+
 def test_c4_full_size_16384_tiled_and_whole(po, gpu_ctx):
     """BASELINE config C4 at its stated size: one 16 384 x 16 384 RGB frame (805 MB, 6.3 M blocks),
     q=80 4:2:0 - eight bands with the distributed entropy stage AND the plain single-context encode,
@@ -105,7 +146,18 @@ def _nccl_worker(rank, world, port, w, h, q, opt, out_path):
     ctx = pixo_b200.Context(rank)
     frame = synthetic.noise(w, h, 3, 42)
     coders, _keep = _device_coders(ctx, frame, w, h, 2, 1, q, world)
-    jpg = parallel.encode_tiled(coders[rank], w, h, 2, q, 1, opt, rank, world)
+    if opt:
+        jpg = parallel.encode_tiled(coders[rank], w, h, 2, q, 1, opt, rank, world)
+    else:   # the stream-ordered flow (needs the context on torch's current stream)
+        stream = torch.cuda.Stream()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            ctx.set_stream(stream.cuda_stream)
+            bands = parallel.plan_bands(w, h, world)
+            parts, _ = parallel.tiled_scan_parts_async(coders[rank], [b.y_blocks > 0 for b in bands], rank, world)
+            jpg = parallel.assemble_tiled(parts, None, w, h, 2, q, 1) if rank == 0 else None
+            stream.synchronize()
+        ctx.set_stream(None)
     assert ctx.host_fallbacks == 0
     if rank == 0:
         open(out_path, "wb").write(jpg)
