@@ -512,7 +512,8 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t red[5][PNG_THREADS / 32];
     __shared__ unsigned long long red64[3][PNG_THREADS / 32];
-    __shared__ int s_filter;
+    __shared__ int s_filter, s_need_paeth;
+    __shared__ unsigned long long s_score[5], s_best;
     __shared__ uint4 vstage[PNG_THREADS / 32][33];   // emit_vec: a warp's filtered vectors, slot l + 1 = lane l, slot 0 = carry
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t img = blockIdx.y;
@@ -562,6 +563,7 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
     unsigned long long accA = 0, accBpos = 0, accBneg = 0;
     const unsigned long long Ntot = (unsigned long long)P.height * n_out;
 
+    bool prev_needed_paeth = false;   // the band's first row takes the two-phase route
     for (uint32_t r = r0; r < r1; ++r) {
         if (r + 1 < r1) load_row(r + 1, bufs[(r + 1) % 3], true);
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -591,24 +593,32 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
             const bool fast = P.strategy == PIXO_B200_FILTER_ADAPTIVE_FAST;
             // every word below `full` is whole: no masking there; the ragged last word (rows whose
             // length is not a multiple of 4) is scored by one thread with its mask
-            auto score = [&](uint32_t k, uint32_t mask, bool all_five) {
+            // Two phases, like the reference's ladder: the cheap candidates first (None, Sub, Up, Average:
+            // 12 of the 37 arithmetic instructions a word costs), and Paeth (25) only for rows whose
+            // ladder has not ended by then ("immediately wins if <= early", src/png/filter.rs:338-372 /
+            // :492-511) - on smooth rows Sub or Up ends it.  The result is identical; only the time is
+            // data dependent, as it is in the reference.
+            // mode 0: the cheap candidates, 1: Paeth alone, 2: all of them in one pass
+            auto score = [&](uint32_t k, uint32_t mask, bool all_five, int mode) {
                 uint32_t x, a, b, c, unused;
                 operands(k, x, a, b, c, unused);
+                if (mode) T[4] += __vsadu4(__vabsdiffu4(x, paeth_pred4(a, b, c)) & mask, 0x80808080u);
+                if (mode == 1) return;
                 if (all_five) {
                     T[0] += __vsadu4(x & mask, 0x80808080u);
                     T[3] += __vsadu4(__vabsdiffu4(x, __vhaddu4(a, b)) & mask, 0x80808080u);
                 }
                 T[1] += __vsadu4(__vabsdiffu4(x, a) & mask, 0x80808080u);
                 T[2] += __vsadu4(__vabsdiffu4(x, b) & mask, 0x80808080u);
-                T[4] += __vsadu4(__vabsdiffu4(x, paeth_pred4(a, b, c)) & mask, 0x80808080u);
             };
             // Four consecutive words per thread (one LDS.128 per row buffer): the left neighbours of
             // words 1-3 are already in registers, word 0's comes from the previous lane by shuffle,
             // so a word costs half a shared-memory load instead of four; pixels of four bytes need
             // no funnel shift at all (left = the previous word).
             const uint32_t nv = full >> 2;
-            auto score4 = [&](auto a0tag, auto fivetag) {
+            auto score4 = [&](auto a0tag, auto fivetag, auto modetag) {
                 constexpr bool A0 = decltype(a0tag)::value, FIVE = decltype(fivetag)::value;
+                constexpr int MODE = decltype(modetag)::value;
                 for (uint32_t vb = (uint32_t)tid & ~31u; vb < nv; vb += PNG_THREADS) {
                     const uint32_t v = vb + lane;
                     const bool valid = v < nv;
@@ -626,65 +636,88 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
 #pragma unroll
                         for (int i = 1; i < 5; ++i) {
                             const uint32_t a = A0 ? x[i - 1] : __funnelshift_r(x[i - 1], x[i], ashift);
-                            const uint32_t c = A0 ? b[i - 1] : __funnelshift_r(b[i - 1], b[i], ashift);
-                            if (FIVE) {
-                                T[0] += __vsadu4(x[i], 0x80808080u);
-                                T[3] += __vsadu4(__vabsdiffu4(x[i], __vhaddu4(a, b[i])), 0x80808080u);
+                            if (MODE) {
+                                const uint32_t c = A0 ? b[i - 1] : __funnelshift_r(b[i - 1], b[i], ashift);
+                                T[4] += __vsadu4(__vabsdiffu4(x[i], paeth_pred4(a, b[i], c)), 0x80808080u);
                             }
-                            T[1] += __vsadu4(__vabsdiffu4(x[i], a), 0x80808080u);
-                            T[2] += __vsadu4(__vabsdiffu4(x[i], b[i]), 0x80808080u);
-                            T[4] += __vsadu4(__vabsdiffu4(x[i], paeth_pred4(a, b[i], c)), 0x80808080u);
+                            if (MODE != 1) {
+                                if (FIVE) {
+                                    T[0] += __vsadu4(x[i], 0x80808080u);
+                                    T[3] += __vsadu4(__vabsdiffu4(x[i], __vhaddu4(a, b[i])), 0x80808080u);
+                                }
+                                T[1] += __vsadu4(__vabsdiffu4(x[i], a), 0x80808080u);
+                                T[2] += __vsadu4(__vabsdiffu4(x[i], b[i]), 0x80808080u);
+                            }
                         }
                     }
                 }
             };
             using std::true_type; using std::false_type;
-            if (ashift == 0) { if (fast) score4(true_type{}, false_type{}); else score4(true_type{}, true_type{}); }
-            else { if (fast) score4(false_type{}, false_type{}); else score4(false_type{}, true_type{}); }
-            // the up-to-three whole words after the last vector, and the ragged last word
-            if (fast) {
-                for (uint32_t k = nv * 4 + tid; k < full; k += PNG_THREADS) score(k, 0xFFFFFFFFu, false);
-                if (full < nw && tid == (int)(full % PNG_THREADS)) score(full, tailmask, false);
-            } else {
-                for (uint32_t k = nv * 4 + tid; k < full; k += PNG_THREADS) score(k, 0xFFFFFFFFu, true);
-                if (full < nw && tid == (int)(full % PNG_THREADS)) score(full, tailmask, true);
-            }
+            auto score_row = [&](auto modetag) {
+                constexpr int MODE = decltype(modetag)::value;
+                if (ashift == 0) { if (fast) score4(true_type{}, false_type{}, modetag); else score4(true_type{}, true_type{}, modetag); }
+                else { if (fast) score4(false_type{}, false_type{}, modetag); else score4(false_type{}, true_type{}, modetag); }
+                // the up-to-three whole words after the last vector, and the ragged last word
+                for (uint32_t k = nv * 4 + tid; k < full; k += PNG_THREADS) score(k, 0xFFFFFFFFu, !fast, MODE);
+                if (full < nw && tid == (int)(full % PNG_THREADS)) score(full, tailmask, !fast, MODE);
+            };
+            auto reduce_scores = [&](int f0, int f1) {   // scores f0..f1-1 -> s_score[] (sum |i8|)
 #pragma unroll
-            for (int f = 0; f < 5; ++f) {
-                const uint32_t v = __reduce_add_sync(0xffffffffu, T[f]);   // REDUX: one instruction per score
-                if (lane == 0) red[f][warp] = v;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                unsigned long long s[5];
-                for (int f = 0; f < 5; ++f) {
-                    unsigned long long t = 0;
-                    for (int w = 0; w < PNG_THREADS / 32; ++w) t += red[f][w];
-                    s[f] = 512ull * nw - t;   // score_filter: sum |i8|
+                for (int f = 0; f < 5; ++f) {   // static indices: T[] stays in registers
+                    if (f < f0 || f >= f1) continue;
+                    const uint32_t v = __reduce_add_sync(0xffffffffu, T[f]);   // REDUX: one instruction per score
+                    if (lane == 0) red[f][warp] = v;
                 }
+                __syncthreads();
+                if (tid == 0)
+                    for (int f = f0; f < f1; ++f) {
+                        unsigned long long t = 0;
+                        for (int w = 0; w < PNG_THREADS / 32; ++w) t += red[f][w];
+                        s_score[f] = 512ull * nw - t;   // score_filter: sum |i8|
+                    }
+            };
+            // Rows resemble their neighbours: when the row above needed Paeth, all candidates are scored
+            // in one pass over the row (no second read, one reduction); when its ladder ended early,
+            // the cheap ones go first.
+            const bool fused = prev_needed_paeth;   // uniform
+            if (fused) { score_row(std::integral_constant<int, 2>{}); reduce_scores(0, 5); }
+            else { score_row(std::integral_constant<int, 0>{}); reduce_scores(0, 4); }
+            if (tid == 0) {
+                const unsigned long long *sc = s_score;
                 int best;
+                bool done;
+                unsigned long long bs;
                 if (fast) {   // adaptive_filter_fast, src/png/filter.rs:474-527
                     const unsigned long long early = (unsigned long long)rb / 8 + 1;
-                    best = 1;
-                    unsigned long long bs = s[1];
-                    if (bs > early) {
-                        if (s[2] < bs) { bs = s[2]; best = 2; }
-                        if (bs > early && s[4] < bs) best = 4;
+                    best = 1; bs = sc[1];
+                    done = bs <= early;
+                    if (!done) {
+                        if (sc[2] < bs) { bs = sc[2]; best = 2; }
+                        done = bs <= early;
                     }
                 } else {      // adaptive_filter, src/png/filter.rs:302-393
                     const unsigned long long early = (unsigned long long)rb / 4 + 1;
-                    best = 0;
-                    unsigned long long bs = s[0];
-                    bool done = bs <= early;
-                    for (int f = 1; f < 5 && !done; ++f)
-                        if (s[f] < bs) {
-                            bs = s[f]; best = f;
-                            if (f < 4 && (bs == 0 || bs <= early)) done = true;
+                    best = 0; bs = sc[0];
+                    done = bs <= early;
+                    for (int f = 1; f < 4 && !done; ++f)
+                        if (sc[f] < bs) {
+                            bs = sc[f]; best = f;
+                            if (bs == 0 || bs <= early) done = true;
                         }
                 }
+                if (fused && !done && sc[4] < bs) best = 4;   // Paeth replaces on strict <
                 s_filter = best;
+                s_best = bs;
+                s_need_paeth = done ? 0 : 1;
             }
             __syncthreads();
+            prev_needed_paeth = s_need_paeth != 0;
+            if (!fused && prev_needed_paeth) {      // uniform
+                score_row(std::integral_constant<int, 1>{});
+                reduce_scores(4, 5);
+                if (tid == 0 && s_score[4] < s_best) s_filter = 4;
+                __syncthreads();
+            }
             filter = s_filter;
         }
 
