@@ -95,15 +95,6 @@ struct EntParams {
                            // (measured: 706 -> 727 us per 32 4K frames - the mask test and the larger code cost more than the
                            // four instructions per symbol save)
 #endif
-#ifndef HUFF_LB_FIRST1
-#define HUFF_LB_FIRST1 0
-#endif
-#ifndef HUFF_TICKET_EARLY
-#define HUFF_TICKET_EARLY 0   // 1: the next ticket is drawn a phase ahead (its latency hides under phase A)
-#endif
-#ifndef HUFF_PREFETCH
-#define HUFF_PREFETCH 0       // 1: the chunk's coefficient lines are prefetched into L2 when its ticket is known
-#endif
 constexpr int CB = 32;             // blocks per chunk == one warp
 static_assert(CB * 4 == 128, "the slot word stride is spelled out in code_block's PTX");
 constexpr int HUFF_WARPS = 4;      // warps per CTA (they only share the tables)
@@ -164,21 +155,12 @@ __device__ __forceinline__ unsigned long long look_back(const unsigned long long
     while (base >= 0) {
         unsigned long long v[LB_GROUPS];
         const unsigned long long *p = st + (base - lane);
-#if HUFF_LB_FIRST1
-        // the nearest inclusive prefix is almost always among the 32 nearest predecessors: the first
-        // step reads only those, later steps (rare) read 32 * LB_GROUPS at a time
-        const int ngroups = first ? 1 : LB_GROUPS;
-#else
-        constexpr int ngroups = LB_GROUPS;
-#endif
 #pragma unroll
-        for (int k = 0; k < LB_GROUPS; ++k)
-            if (k < ngroups) v[k] = base - lane - 32 * k >= 0 ? ld_status(p - 32 * k) : ST_PFX;
+        for (int k = 0; k < LB_GROUPS; ++k) v[k] = base - lane - 32 * k >= 0 ? ld_status(p - 32 * k) : ST_PFX;
         unsigned long long step = 0;
         bool retry = false, done = false;
 #pragma unroll
         for (int k = 0; k < LB_GROUPS; ++k) {
-            if (k >= ngroups) break;
             const uint32_t flag = (uint32_t)(v[k] >> 62);
             const uint32_t inv = __ballot_sync(0xffffffffu, flag == 0);
             const uint32_t pm = __ballot_sync(0xffffffffu, flag == 2);
@@ -196,7 +178,7 @@ __device__ __forceinline__ unsigned long long look_back(const unsigned long long
         excl += step;
         if (first) { tl = __shfl_sync(0xffffffffu, (uint32_t)(v[0] >> 55) & 0x7Fu, 0); first = false; }
         if (done) break;
-        base -= 32 * ngroups;
+        base -= 32 * LB_GROUPS;
     }
     return (excl & ST_VAL) | ((unsigned long long)tl << 55) | (fault ? 1ull << 62 : 0ull);
 }
@@ -851,53 +833,11 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
     ChunkState cur, pend;
     bool have_pend = false;
     int buf = 0;
-    // L2 prefetch of the coefficient lines a chunk will read (plain scan only: no restart intervals, no
-    // segments).  The chunk's 32 blocks are ~32 * y_per_mcu / bpm consecutive Y blocks and ~32 / bpm of
-    // each chroma array; a few lines too many at the end are the next chunk's.
-    auto prefetch_chunk = [&](uint32_t id) {
-#if HUFF_PREFETCH
-        if (RAW || P.rst_blocks) return;
-        const uint32_t chunk = id / P.nimages, img = id - chunk * P.nimages;
-        const uint32_t m0 = chunk * CB / P.bpm;
-        const uint32_t nm = CB / P.bpm + 2;                       // MCUs the chunk can touch
-        const uint32_t mcus = P.nblocks / P.bpm;
-        const uint32_t yb = m0 * P.y_per_mcu + lane;
-        if (lane < nm * P.y_per_mcu && yb < mcus * P.y_per_mcu)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.y + (size_t)img * P.y_stride + (size_t)yb * 64));
-        if (P.bpm > 1) {
-            const uint32_t half = lane >> 4, cbk = m0 + (lane & 15);
-            if ((lane & 15u) < nm && cbk < mcus)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"((half ? P.cr : P.cb) + (size_t)img * P.c_stride + (size_t)cbk * 64));
-        }
-#else
-        (void)id;
-#endif
-    };
-    auto draw = [&]() -> uint32_t {   // lane 0 holds the ticket; broadcast where it is needed
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(P.ticket, 1u);
-        return t;
-    };
-#if HUFF_TICKET_EARLY
-    uint32_t id = __shfl_sync(0xffffffffu, draw(), 0);
     for (;;) {
+        uint32_t id = 0;
+        if (lane == 0) id = atomicAdd(P.ticket, 1u);
+        id = __shfl_sync(0xffffffffu, id, 0);
         const bool have = id < total_chunks;
-        uint32_t next = 0;
-        if (have) { next = draw(); prefetch_chunk(id); }   // not read until the phases below are done
-        if (have_pend) phase_a(pend);
-        if (have) phase_w(id, buf, cur);
-        if (have_pend) phase_b(pend);
-        if (!have) break;
-        pend = cur;
-        have_pend = true;
-        buf ^= 1;
-        id = __shfl_sync(0xffffffffu, next, 0);
-    }
-#else
-    for (;;) {
-        const uint32_t id = __shfl_sync(0xffffffffu, draw(), 0);
-        const bool have = id < total_chunks;
-        if (have) prefetch_chunk(id);
         if (have_pend) phase_a(pend);
         if (have) phase_w(id, buf, cur);
         if (have_pend) phase_b(pend);
@@ -906,7 +846,6 @@ k_huff(const __grid_constant__ EntParams P, const __grid_constant__ HuffDev Tp)
         have_pend = true;
         buf ^= 1;
     }
-#endif
 }
 
 }  // namespace

@@ -797,13 +797,16 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
             const uint32_t per = (((nv + PNG_THREADS / 32 - 1) / (PNG_THREADS / 32)) + 31) & ~31u;   // vectors per warp
             const uint32_t v_lo = warp * per, v_hi = min(nv, v_lo + per);
             uint4 *stg = vstage[warp];
+            // the row's byte phase, uniform: chunk v = bytes [16 - o, 16) of vector v-1 ++ bytes [0, 16 - o) of v
+            const uint32_t o = 16u - sh16, kq = o >> 2, bs = (o & 3u) * 8u;
             if (v_lo < v_hi) {
                 if (lane == 0) {
                     uint32_t f[4] = {0, 0, 0, 0};
                     if (v_lo > 0 && sh16) fvec(v_lo - 1, false, f);
                     stg[0] = make_uint4(f[0], f[1], f[2], f[3]);
                 }
-                for (uint32_t vb = v_lo; vb < v_hi; vb += 32) {
+                uint8_t *dst = abase + 16 * (size_t)(v_lo + lane);      // this lane's aligned chunk, 512 bytes on per round
+                for (uint32_t vb = v_lo; vb < v_hi; vb += 32, dst += 512) {
                     const uint32_t v = vb + lane;
                     const bool valid = v < v_hi;
                     uint32_t f[4];
@@ -821,22 +824,25 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
                     if (lane == 31) stg[0] = make_uint4(f[0], f[1], f[2], f[3]);   // carry into the next round
                     if (valid) {
                         if (v > 0 || sh16 == 0) {
-                            const uint32_t W[9] = {pv.x, pv.y, pv.z, pv.w, f[0], f[1], f[2], f[3], 0u};
-                            const uint32_t o = 16u - sh16, bs = (o & 3u) * 8u;
                             uint4 q;
-                            switch (o >> 2) {   // uniform: the row's byte phase
-                            case 0: q = make_uint4(__funnelshift_r(W[0], W[1], bs), __funnelshift_r(W[1], W[2], bs), __funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs)); break;
-                            case 1: q = make_uint4(__funnelshift_r(W[1], W[2], bs), __funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs)); break;
-                            case 2: q = make_uint4(__funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs), __funnelshift_r(W[5], W[6], bs)); break;
-                            case 3: q = make_uint4(__funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs), __funnelshift_r(W[5], W[6], bs), __funnelshift_r(W[6], W[7], bs)); break;
-                            default: q = make_uint4(W[4], W[5], W[6], W[7]); break;
-                            }
-                            *reinterpret_cast<uint4 *>(abase + 16 * (size_t)v) = q;
-                        } else {   // v == 0, sh16 > 0: the row's first 16 - sh16 bytes share chunk 0 with the row before
-                            for (uint32_t i = 0; i < 16u - sh16; ++i) orow[1 + i] = (uint8_t)(f[i >> 2] >> (8 * (i & 3)));
+                            // (an if-ladder on the uniform kq: a switch becomes an indirect branch through a
+                            // constant-bank jump table, ~15 instructions per vector)
+                            if (kq == 4) q = make_uint4(f[0], f[1], f[2], f[3]);
+                            else if (kq == 3) q = make_uint4(__funnelshift_r(pv.w, f[0], bs), __funnelshift_r(f[0], f[1], bs), __funnelshift_r(f[1], f[2], bs), __funnelshift_r(f[2], f[3], bs));
+                            else if (kq == 2) q = make_uint4(__funnelshift_r(pv.z, pv.w, bs), __funnelshift_r(pv.w, f[0], bs), __funnelshift_r(f[0], f[1], bs), __funnelshift_r(f[1], f[2], bs));
+                            else if (kq == 1) q = make_uint4(__funnelshift_r(pv.y, pv.z, bs), __funnelshift_r(pv.z, pv.w, bs), __funnelshift_r(pv.w, f[0], bs), __funnelshift_r(f[0], f[1], bs));
+                            else q = make_uint4(__funnelshift_r(pv.x, pv.y, bs), __funnelshift_r(pv.y, pv.z, bs), __funnelshift_r(pv.z, pv.w, bs), __funnelshift_r(pv.w, f[0], bs));
+                            *reinterpret_cast<uint4 *>(dst) = q;
                         }
-                        if (v == nv - 1 && sh16)   // the last sh16 bytes of the last vector start the next chunk
-                            for (uint32_t i = 16u - sh16; i < 16u; ++i) orow[1 + 16 * (size_t)v + i] = (uint8_t)(f[i >> 2] >> (8 * (i & 3)));
+                        // The row's two ragged ends go out byte by byte, read back from the lane's own staging
+                        // slot (indexing f[] with a run-time index would put it in local memory for every vector).
+                        const bool head = v == 0 && sh16 != 0;            // first 16 - sh16 bytes share chunk 0 with the row before
+                        const bool tail = v == nv - 1 && sh16 != 0;       // the last sh16 bytes start the chunk after the last
+                        if (head || tail) {
+                            const uint8_t *fb = reinterpret_cast<const uint8_t *>(&stg[lane + 1]);
+                            if (head) for (uint32_t i = 0; i < o; ++i) orow[1 + i] = fb[i];
+                            if (tail) for (uint32_t i = o; i < 16u; ++i) orow[1 + 16 * (size_t)v + i] = fb[i];
+                        }
                     }
                     __syncwarp();
                 }
