@@ -35,6 +35,36 @@ def test_filters_match_oracle(po, gpu_ctx, w, h, bpp):
             assert ad == po.adler32(ref) == zlib.adler32(ref.tobytes())
 
 
+@pytest.mark.parametrize("bpp", [3, 4])
+@pytest.mark.parametrize("w,h", [(300, 96), (1024, 70), (2051, 53)])
+def test_rows_whose_ladder_ends_early_next_to_rows_that_need_paeth(po, gpu_ctx, w, h, bpp):
+    # The band kernel scores Paeth only while a row's ladder is open and switches between a one-pass
+    # and a two-pass scoring of the row by what the row above needed: flat rows (Sub or Up wins at
+    # once), noise rows (all five scored) and every order of the two, across band borders (16 rows).
+    rng = np.random.default_rng(7)
+    noise = po.gen_noise(w, h, bpp, 9).reshape(h, w * bpp)
+    flat = np.repeat(rng.integers(0, 256, (h, 1, bpp), dtype=np.uint8), w, axis=1).reshape(h, w * bpp)
+    ramp = ((np.arange(w * bpp) // bpp)[None, :] + np.arange(h)[:, None]).astype(np.uint8)
+    patterns = {
+        "alternate": np.arange(h) % 2 == 0,
+        "runs of 5": (np.arange(h) // 5) % 2 == 0,
+        "band border": (np.arange(h) // 16) % 2 == 0,
+        "random": rng.integers(0, 2, h).astype(bool),
+    }
+    for name, pick in patterns.items():
+        for calm in (flat, ramp):
+            img = np.where(pick[:, None], calm, noise).reshape(-1)
+            for st in (FilterStrategy.Adaptive, FilterStrategy.AdaptiveFast, FilterStrategy.MinSum):
+                opts = PngOptions(w, h, ColorType.Rgba, st)
+                got, ad = png.apply_filters(img, w, h, bpp, opts, with_adler=True, ctx=gpu_ctx)
+                ref = po.apply_filters(img, w, h, bpp, int(st))
+                assert np.array_equal(got, ref), (name, st, w, h, bpp, np.flatnonzero(got != ref)[:5])
+                assert ad == zlib.adler32(ref.tobytes())
+        # both kinds of row really occur: the winners include None/Sub/Up rows and Paeth or Average rows
+        types = set(ref.reshape(h, w * bpp + 1)[:, 0].tolist())
+        assert len(types) >= 2, types
+
+
 @pytest.mark.parametrize("ct,bpp", [(3, 4), (1, 2), (2, 3)])
 @pytest.mark.parametrize("w,h", [(3, 2), (65, 64), (100, 33), (300, 20), (1000, 70), (4099, 35)])
 def test_optimize_alpha_fused(po, gpu_ctx, w, h, ct, bpp):
