@@ -920,13 +920,63 @@ __device__ __forceinline__ uint32_t splice_byte(const SpliceParams &P, unsigned 
     return v;
 }
 
+// The same sixteen bytes at once.  T is the raw string shifted right by `phase` bits behind the inherited
+// bits, so four big-endian words of T are four funnel shifts over the raw words (and the raw byte before
+// them).  Only for a thread whose piece lies wholly inside the raw string, short of its last byte (no
+// padding, no missing bytes), at a 16-byte aligned address; the ragged ends take the byte-wise path.
+__device__ __forceinline__ bool t_words16(const uint8_t *raw, unsigned long long rb, uint32_t phase, uint32_t tail_in,
+                                          unsigned long long m0, uint32_t (&O)[4])
+{
+    if (m0 + 16 >= rb || (reinterpret_cast<uintptr_t>(raw + m0) & 15)) return false;
+    const uint4 L = *reinterpret_cast<const uint4 *>(raw + m0);
+    const uint32_t pb = m0 ? raw[m0 - 1] : tail_in;
+    const uint32_t A0 = __byte_perm(L.x, 0, 0x0123), A1 = __byte_perm(L.y, 0, 0x0123);
+    const uint32_t A2 = __byte_perm(L.z, 0, 0x0123), A3 = __byte_perm(L.w, 0, 0x0123);
+    O[0] = __funnelshift_r(A0, pb, phase);
+    O[1] = __funnelshift_r(A1, A0, phase);
+    O[2] = __funnelshift_r(A2, A1, phase);
+    O[3] = __funnelshift_r(A3, A2, phase);
+    return true;
+}
+__device__ __forceinline__ uint32_t ff_count16(const uint32_t (&O)[4])
+{
+    return __popc(ff_bytes(O[0])) + __popc(ff_bytes(O[1])) + __popc(ff_bytes(O[2])) + __popc(ff_bytes(O[3]));
+}
+// sixteen stuffing-free bytes (four big-endian words) -> sb[dst .. dst + 16) at any byte alignment:
+// three aligned word stores plus at most three single bytes at either end
+__device__ __forceinline__ void put16(uint8_t *sb, uint32_t dst, const uint32_t (&O)[4])
+{
+    uint32_t m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = __byte_perm(O[k], 0, 0x0123);   // memory order
+    const uint32_t al = dst & 3u, sh8 = 8u * al;
+    uint8_t *base = sb + (dst - al);
+    uint32_t *wb = reinterpret_cast<uint32_t *>(base);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) wb[k] = __funnelshift_l(m[k - 1], m[k], sh8);
+    if (al == 0) {
+        wb[0] = m[0];
+    } else {
+        base[3] = (uint8_t)(m[0] >> (24u - sh8));
+        if (al < 3) base[2] = (uint8_t)(m[0] >> (16u - sh8));
+        if (al < 2) base[1] = (uint8_t)m[0];
+        base[16] = (uint8_t)(m[3] >> (32u - sh8));
+        if (al > 1) base[17] = (uint8_t)(m[3] >> (40u - sh8));
+        if (al > 2) base[18] = (uint8_t)(m[3] >> 24);
+    }
+}
+
 __global__ void __launch_bounds__(SPL_THREADS) k_splice_count(const __grid_constant__ SpliceParams P)
 {
     __shared__ uint32_t red[SPL_THREADS / 32];
     const unsigned long long m0 = (unsigned long long)blockIdx.x * SPL_TILE + threadIdx.x * 16;
-    uint32_t c = 0;
-    for (int i = 0; i < 16; ++i)
-        if (m0 + i < P.nbytes) c += splice_byte(P, m0 + i) == 0xFFu;
+    uint32_t c = 0, O[4];
+    if (t_words16(P.raw, (P.nbits + 7) >> 3, P.s, P.tail_in, m0, O)) {
+        c = ff_count16(O);
+    } else {
+        for (int i = 0; i < 16; ++i)
+            if (m0 + i < P.nbytes) c += splice_byte(P, m0 + i) == 0xFFu;
+    }
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -941,7 +991,7 @@ __global__ void __launch_bounds__(SPL_THREADS) k_splice_emit(const __grid_consta
 {
     __shared__ unsigned long long s_before;
     __shared__ uint32_t wsum[SPL_THREADS / 32];
-    __shared__ uint8_t sb[2 * SPL_TILE];
+    __shared__ __align__(16) uint8_t sb[2 * SPL_TILE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // 0xFF bytes in the tiles before this one
     unsigned long long before = 0;
@@ -951,10 +1001,15 @@ __global__ void __launch_bounds__(SPL_THREADS) k_splice_emit(const __grid_consta
     __syncthreads();
     if (lane == 0 && before) atomicAdd(&s_before, before);
     const unsigned long long m0 = (unsigned long long)blockIdx.x * SPL_TILE + tid * 16;
-    uint32_t v[16], c = 0;
-    for (int i = 0; i < 16; ++i) {
-        v[i] = m0 + i < P.nbytes ? splice_byte(P, m0 + i) : 0x100u;
-        c += v[i] == 0xFFu;
+    uint32_t v[16], c = 0, O[4];
+    const bool fast = t_words16(P.raw, (P.nbits + 7) >> 3, P.s, P.tail_in, m0, O);
+    if (fast) {
+        c = ff_count16(O);
+    } else {
+        for (int i = 0; i < 16; ++i) {
+            v[i] = m0 + i < P.nbytes ? splice_byte(P, m0 + i) : 0x100u;
+            c += v[i] == 0xFFu;
+        }
     }
     // exclusive scan of the per-thread 0xFF counts over the CTA
     uint32_t inc = c;
@@ -967,10 +1022,16 @@ __global__ void __launch_bounds__(SPL_THREADS) k_splice_emit(const __grid_consta
     uint32_t woff = 0, total = 0;
     for (int i = 0; i < SPL_THREADS / 32; ++i) { if (i < warp) woff += wsum[i]; total += wsum[i]; }
     uint32_t dst = tid * 16 + woff + inc - c;
-    for (int i = 0; i < 16; ++i) {
-        if (v[i] > 0xFFu) break;
-        sb[dst++] = (uint8_t)v[i];
-        if (v[i] == 0xFFu) sb[dst++] = 0;
+    if (fast && c == 0) {
+        put16(sb, dst, O);
+    } else {
+        if (fast)
+            for (int i = 0; i < 16; ++i) v[i] = (O[i >> 2] >> (24 - 8 * (i & 3))) & 0xFFu;
+        for (int i = 0; i < 16; ++i) {
+            if (v[i] > 0xFFu) break;
+            sb[dst++] = (uint8_t)v[i];
+            if (v[i] == 0xFFu) sb[dst++] = 0;
+        }
     }
     __syncthreads();
     const unsigned long long tile_first = (unsigned long long)blockIdx.x * SPL_TILE;
@@ -1082,113 +1143,162 @@ __global__ void k_seg_prefix(const __grid_constant__ SegParams P)
     else if (tile_off == 0) P.out_len[i] = 0;
 }
 
-__device__ __forceinline__ uint32_t seg_of_tile(const SegParams &P, uint32_t i, uint32_t t)
+// A CTA of the splice kernels works through SPL_TPC consecutive tiles of one image (one tile per CTA
+// left the kernels latency-bound: 17 000 CTAs for a 70 MB scan, each behind a chain of dependent loads).
+// The image's segment records are read once into shared memory.
+constexpr int SPL_TPC = 8;
+constexpr int SEG_MAX = 64;
+
+__device__ __forceinline__ void load_seg_table(const SegParams &P, uint32_t i, SegRec *tab)
 {
-    uint32_t s = 0;
-    while (s + 1 < P.S && P.rec[i * P.S + s + 1].tile_off <= t) ++s;   // S <= 64; the records sit in L1/L2
-    return s;
+    if (threadIdx.x < P.S) tab[threadIdx.x] = P.rec[i * P.S + threadIdx.x];
+    __syncthreads();
+}
+// the segment tile t belongs to: the last one whose first tile is <= t (tile_off is non-decreasing and
+// tab[0].tile_off == 0).  Whole CTA, one barrier: thread s looks at record s.
+__device__ __forceinline__ uint32_t seg_of_tile(const SegRec *tab, uint32_t S, uint32_t t)
+{
+    return (uint32_t)__syncthreads_count(threadIdx.x < S && tab[threadIdx.x].tile_off <= t) - 1u;
+}
+
+// nout staged bytes -> outp[g0 ..).  The stage was filled from index shb = (address of outp + g0) & 15 on,
+// so stage and destination agree modulo 16: whole 16-byte pieces, single bytes at the two ragged ends.
+__device__ __forceinline__ void copy_out16(uint8_t *outp, unsigned long long g0, const uint8_t *sb, uint32_t shb,
+                                           uint32_t nout, int tid)
+{
+    uint8_t *gdst = outp + g0 - shb;   // 16-byte aligned
+    const uint32_t end = shb + nout;
+    const uint32_t full_lo = (shb + 15u) >> 4, full_hi = end >> 4;
+    for (uint32_t c16 = full_lo + tid; c16 < full_hi; c16 += SPL_THREADS)
+        *reinterpret_cast<uint4 *>(gdst + c16 * 16) = *reinterpret_cast<const uint4 *>(sb + c16 * 16);
+    if (tid < 16) {                       // ragged head
+        const uint32_t hb = shb + tid;
+        if (hb < min(full_lo * 16u, end)) gdst[hb] = sb[hb];
+    } else if (tid < 32) {                // ragged tail
+        const uint32_t tb = max(full_hi, full_lo) * 16u + (tid - 16);
+        if (full_hi >= full_lo && tb < end) gdst[tb] = sb[tb];
+    }
 }
 
 __global__ void __launch_bounds__(SPL_THREADS) k_seg_count(const __grid_constant__ SegParams P)
 {
-    __shared__ uint32_t red[SPL_THREADS / 32];
-    const uint32_t i = blockIdx.y, t = blockIdx.x;
-    if (t >= P.ntiles[i]) return;
-    const uint32_t s = seg_of_tile(P, i, t);
-    const SegRec r = P.rec[i * P.S + s];
-    const uint8_t *raw = P.raw + (size_t)(i * P.S + s) * P.raw_cap;
-    const unsigned long long m0 = (unsigned long long)(t - r.tile_off) * SPL_TILE + threadIdx.x * 16;
-    uint32_t c = 0;
-    for (int k = 0; k < 16; ++k)
-        if (m0 + k < r.nbytes) c += seg_byte(raw, r, m0 + k) == 0xFFu;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __shared__ uint32_t red[SPL_TPC][SPL_THREADS / 32];
+    __shared__ SegRec tab[SEG_MAX];
+    const uint32_t i = blockIdx.y, t0 = blockIdx.x * SPL_TPC, nt = P.ntiles[i];
+    if (t0 >= nt) return;
+    load_seg_table(P, i, tab);
+    const uint32_t t1 = min(nt, t0 + SPL_TPC);
+    for (uint32_t t = t0; t < t1; ++t) {
+        const uint32_t s = seg_of_tile(tab, P.S, t);
+        const SegRec &r = tab[s];
+        const uint8_t *raw = P.raw + (size_t)(i * P.S + s) * P.raw_cap;
+        const unsigned long long m0 = (unsigned long long)(t - r.tile_off) * SPL_TILE + threadIdx.x * 16;
+        uint32_t c = 0, O[4];
+        if (t_words16(raw, (r.nbits + 7) >> 3, r.phase, r.tail_in, m0, O)) {
+            c = ff_count16(O);
+        } else {
+            for (int k = 0; k < 16; ++k)
+                if (m0 + k < r.nbytes) c += seg_byte(raw, r, m0 + k) == 0xFFu;
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        if ((threadIdx.x & 31) == 0) red[t - t0][threadIdx.x >> 5] = c;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < t1 - t0) {
         uint32_t tot = 0;
-        for (int k = 0; k < SPL_THREADS / 32; ++k) tot += red[k];
-        P.cnt[(size_t)i * P.max_tiles + t] = tot;
+        for (int k = 0; k < SPL_THREADS / 32; ++k) tot += red[threadIdx.x][k];
+        P.cnt[(size_t)i * P.max_tiles + t0 + threadIdx.x] = tot;
     }
 }
 
 // exclusive prefix of an image's tile counts, in place (one CTA per image)
 __global__ void __launch_bounds__(1024) k_seg_scan(const __grid_constant__ SegParams P)
 {
-    __shared__ uint32_t part[1024];
+    __shared__ uint32_t wtot[32];
     const uint32_t i = blockIdx.x, n = P.ntiles[i];
     uint32_t *c = P.cnt + (size_t)i * P.max_tiles;
     const uint32_t per = (n + 1023) / 1024, lo = threadIdx.x * per, hi = min(n, lo + per);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t sum = 0;
     for (uint32_t k = lo; k < hi; ++k) sum += c[k];
-    part[threadIdx.x] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {   // Hillis-Steele over the 1024 partial sums
-        const uint32_t v = threadIdx.x >= (unsigned)o ? part[threadIdx.x - o] : 0u;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    uint32_t inc = sum;                        // inclusive scan of the 1024 partial sums: warp, then warp totals
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
     }
-    uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = wtot[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        wtot[lane] = w;
+    }
+    __syncthreads();
+    uint32_t run = inc - sum + (warp ? wtot[warp - 1] : 0u);
     for (uint32_t k = lo; k < hi; ++k) { const uint32_t v = c[k]; c[k] = run; run += v; }
 }
 
 __global__ void __launch_bounds__(SPL_THREADS) k_seg_emit(const __grid_constant__ SegParams P)
 {
     __shared__ uint32_t wsum[SPL_THREADS / 32];
-    __shared__ __align__(16) uint8_t sb[2 * SPL_TILE];
-    const uint32_t i = blockIdx.y, t = blockIdx.x, nt = P.ntiles[i];
-    if (t >= nt) return;
+    __shared__ __align__(16) uint8_t sb[2 * SPL_TILE + 32];
+    __shared__ SegRec tab[SEG_MAX];
+    const uint32_t i = blockIdx.y, t0 = blockIdx.x * SPL_TPC, nt = P.ntiles[i];
+    if (t0 >= nt) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t s = seg_of_tile(P, i, t);
-    const SegRec r = P.rec[i * P.S + s];
-    const uint8_t *raw = P.raw + (size_t)(i * P.S + s) * P.raw_cap;
-    const unsigned long long tile_first = (unsigned long long)(t - r.tile_off) * SPL_TILE;
-    const unsigned long long m0 = tile_first + tid * 16;
-    uint32_t v[16], c = 0;
-    for (int k = 0; k < 16; ++k) {
-        v[k] = m0 + k < r.nbytes ? seg_byte(raw, r, m0 + k) : 0x100u;
-        c += v[k] == 0xFFu;
-    }
-    uint32_t inc = c;
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t nb = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += nb;
-    }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    uint32_t woff = 0, total = 0;
-    for (int k = 0; k < SPL_THREADS / 32; ++k) { if (k < warp) woff += wsum[k]; total += wsum[k]; }
-    uint32_t dst = tid * 16 + woff + inc - c;
-    for (int k = 0; k < 16; ++k) {
-        if (v[k] > 0xFFu) break;
-        sb[dst++] = (uint8_t)v[k];
-        if (v[k] == 0xFFu) sb[dst++] = 0;
-    }
-    __syncthreads();
-    const unsigned long long tile_n = min((unsigned long long)SPL_TILE, r.nbytes - tile_first);
-    const unsigned long long g0 = r.byte_off + tile_first + P.cnt[(size_t)i * P.max_tiles + t];
-    const uint32_t nout = (uint32_t)tile_n + total;
+    load_seg_table(P, i, tab);
     uint8_t *outp = P.out + (size_t)i * P.out_cap;
-    if (g0 + nout <= P.out_cap) {
-        // 16-byte stores where source and destination allow, bytes at the ragged ends
-        const uint32_t head = (uint32_t)((16 - ((reinterpret_cast<uintptr_t>(outp) + g0) & 15)) & 15);
-        for (uint32_t k = tid; k < min(head, nout); k += SPL_THREADS) outp[g0 + k] = sb[k];
-        if (nout > head) {
-            const uint32_t nv = (nout - head) >> 4;
-            if ((head & 3) == 0) {
-                for (uint32_t k = tid; k < nv; k += SPL_THREADS) {
-                    const uint32_t *w = reinterpret_cast<const uint32_t *>(sb + head + 16 * k);
-                    *reinterpret_cast<uint4 *>(outp + g0 + head + 16 * (size_t)k) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            } else {
-                for (uint32_t k = tid; k < nv * 16; k += SPL_THREADS) outp[g0 + head + k] = sb[head + k];
+    const uint32_t t1 = min(nt, t0 + SPL_TPC);
+    for (uint32_t t = t0; t < t1; ++t) {
+        const uint32_t s = seg_of_tile(tab, P.S, t);
+        const SegRec &r = tab[s];
+        const uint8_t *raw = P.raw + (size_t)(i * P.S + s) * P.raw_cap;
+        const unsigned long long tile_first = (unsigned long long)(t - r.tile_off) * SPL_TILE;
+        const unsigned long long m0 = tile_first + tid * 16;
+        const unsigned long long g0 = r.byte_off + tile_first + P.cnt[(size_t)i * P.max_tiles + t];
+        const uint32_t shb = (uint32_t)((reinterpret_cast<uintptr_t>(outp) + g0) & 15u);
+        uint32_t v[16], c = 0, O[4];
+        const bool fast = t_words16(raw, (r.nbits + 7) >> 3, r.phase, r.tail_in, m0, O);
+        if (fast) {
+            c = ff_count16(O);
+        } else {
+            for (int k = 0; k < 16; ++k) {
+                v[k] = m0 + k < r.nbytes ? seg_byte(raw, r, m0 + k) : 0x100u;
+                c += v[k] == 0xFFu;
             }
-            for (uint32_t k = head + nv * 16 + tid; k < nout; k += SPL_THREADS) outp[g0 + k] = sb[k];
         }
-    } else if (tid == 0) {
-        atomicOr(&P.overflow[i], 1u);
+        uint32_t inc = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t nb = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += nb;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+        for (int k = 0; k < SPL_THREADS / 32; ++k) { if (k < warp) woff += wsum[k]; total += wsum[k]; }
+        uint32_t dst = shb + tid * 16 + woff + inc - c;
+        if (fast && c == 0) {
+            put16(sb, dst, O);
+        } else {
+            if (fast)
+                for (int k = 0; k < 16; ++k) v[k] = (O[k >> 2] >> (24 - 8 * (k & 3))) & 0xFFu;
+            for (int k = 0; k < 16; ++k) {
+                if (v[k] > 0xFFu) break;
+                sb[dst++] = (uint8_t)v[k];
+                if (v[k] == 0xFFu) sb[dst++] = 0;
+            }
+        }
+        __syncthreads();
+        const unsigned long long tile_n = min((unsigned long long)SPL_TILE, r.nbytes - tile_first);
+        const uint32_t nout = (uint32_t)tile_n + total;
+        if (g0 + nout <= P.out_cap) copy_out16(outp, g0, sb, shb, nout, tid);
+        else if (tid == 0) atomicOr(&P.overflow[i], 1u);
+        if (tid == 0 && t == nt - 1) P.out_len[i] = g0 + nout;   // the size needed, also when it did not fit
+        __syncthreads();   // the stage and wsum are rewritten by the next tile
     }
-    if (tid == 0 && t == nt - 1) P.out_len[i] = g0 + nout;   // the size needed, also when it did not fit
 }
 
 }  // namespace
@@ -1244,7 +1354,7 @@ static void make_huff_dev(const HuffTables &t, HuffDev *Tp)
 // shorter than 48 chunks.  1 = do not segment.
 static uint32_t segments_for(uint32_t n, uint64_t total_mcus, uint64_t bpm)
 {
-    if (const char *e = getenv("PIXO_B200_SEGMENTS")) return (uint32_t)std::max(1, atoi(e));
+    if (const char *e = getenv("PIXO_B200_SEGMENTS")) return (uint32_t)std::min(SEG_MAX, std::max(1, atoi(e)));   // test hook
     // Measured on B200: for 4K frames (6 075 chunks) the four extra launches cost more than the
     // shorter chains save (k_huff 72 -> 111 us for one frame, 715 -> 1110 us for 32); a 16 384^2 frame
     // (196 608 chunks on ONE chain) is where the look-back distance hurts.  So: few images, each long.
@@ -1346,9 +1456,9 @@ static int launch_segmented(pixo_b200_ctx *ctx, EntParams P, const HuffDev &T, u
     Q.overflow = d_overflow;
     Q.raw_overflow = code ? P.overflow : nullptr;   // a band's flags were checked by the host when it was coded
     k_seg_prefix<<<n, 32, 0, st>>>(Q);
-    k_seg_count<<<dim3(sp.max_tiles, n), SPL_THREADS, 0, st>>>(Q);
+    k_seg_count<<<dim3((sp.max_tiles + SPL_TPC - 1) / SPL_TPC, n), SPL_THREADS, 0, st>>>(Q);
     k_seg_scan<<<n, 1024, 0, st>>>(Q);
-    k_seg_emit<<<dim3(sp.max_tiles, n), SPL_THREADS, 0, st>>>(Q);
+    k_seg_emit<<<dim3((sp.max_tiles + SPL_TPC - 1) / SPL_TPC, n), SPL_THREADS, 0, st>>>(Q);
     ctx->launches += 4;
     PIXO_CUDA(ctx, cudaGetLastError());
     return 0;
