@@ -1112,42 +1112,83 @@ __global__ void k_band_totals(const unsigned long long *bits, const unsigned lon
     if (f) atomicOr(flags, f);
 }
 
-__global__ void k_seg_prefix(const __grid_constant__ SegParams P)
+// exclusive prefix over the CTA's SPL_THREADS values (every thread calls; `sh` holds one word per warp)
+template <typename T>
+__device__ __forceinline__ T cta_exclusive_scan(T x, T *sh, T *total)
 {
-    if (threadIdx.x) return;
-    const uint32_t i = blockIdx.x;
-    unsigned long long start = P.base_bit, byte_off = 0;
-    uint32_t tail_prev = P.base_tail, tile_off = 0, bad = 0, last_band = P.last_band;
-    if (P.base_dev) { start = P.base_dev[0]; tail_prev = (uint32_t)P.base_dev[1]; last_band = (uint32_t)P.base_dev[2]; }
-    for (uint32_t s = 0; s < P.S; ++s) {
-        const uint32_t q = i * P.S + s;
-        SegRec r;
-        r.nbits = P.bits[q];
-        r.phase = (uint32_t)(start & 7);
-        r.tail_in = tail_prev & ((1u << r.phase) - 1u);
-        r.last = (s == P.S - 1 && last_band) ? 1u : 0u;
-        const unsigned long long tbits = r.phase + r.nbits;
-        r.nbytes = (tbits >> 3) + ((r.last && (tbits & 7)) ? 1 : 0);
-        r.byte_off = byte_off;
-        r.tile_off = tile_off;
-        P.rec[q] = r;
-        byte_off += r.nbytes;
-        tile_off += (uint32_t)((r.nbytes + SPL_TILE - 1) / SPL_TILE);
-        start += r.nbits;
-        if (r.nbits) tail_prev = (uint32_t)P.tails[q];
-        if (P.raw_overflow) bad |= P.raw_overflow[q];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T inc = x;
+    for (int o = 1; o < 32; o <<= 1) {
+        const T v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
     }
-    P.ntiles[i] = tile_off;
-    // a raw segment that did not fit (or a faulted chain): the caller codes the image again unsegmented
-    if (bad || tile_off > P.max_tiles) { P.overflow[i] = 4u | (bad & 2u); P.ntiles[i] = 0; P.out_len[i] = 0; }
-    else if (tile_off == 0) P.out_len[i] = 0;
+    __syncthreads();              // sh may still be read from a previous scan
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    T before = 0, all = 0;
+    for (int w = 0; w < SPL_THREADS / 32; ++w) { const T v = sh[w]; if (w < warp) before += v; all += v; }
+    *total = all;
+    return before + inc - x;
+}
+
+// Per image: every segment's record (bit phase, inherited bits, byte and tile offsets) from the
+// segments' bit counts.  One CTA per image, thread s = segment s (S <= SEG_MAX == SPL_THREADS): three
+// prefix sums (bits, bytes, tiles) and a "nearest earlier non-empty segment" scan for the inherited bits.
+__global__ void __launch_bounds__(SPL_THREADS) k_seg_prefix(const __grid_constant__ SegParams P)
+{
+    __shared__ unsigned long long sh64[SPL_THREADS / 32];
+    __shared__ uint32_t sh32[SPL_THREADS / 32];
+    __shared__ int shmax[SPL_THREADS / 32];
+    const uint32_t i = blockIdx.x, s = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long base = P.base_bit;
+    uint32_t base_tail = P.base_tail, last_band = P.last_band;
+    if (P.base_dev) { base = P.base_dev[0]; base_tail = (uint32_t)P.base_dev[1]; last_band = (uint32_t)P.base_dev[2]; }
+    const bool live = s < P.S;
+    const uint32_t q = i * P.S + s;
+    const unsigned long long nbits = live ? P.bits[q] : 0ull;
+    const uint32_t bad_here = (live && P.raw_overflow) ? P.raw_overflow[q] : 0u;
+    unsigned long long total_bits;
+    const unsigned long long start = base + cta_exclusive_scan<unsigned long long>(nbits, sh64, &total_bits);
+    SegRec r;
+    r.nbits = nbits;
+    r.phase = (uint32_t)(start & 7);
+    r.last = (live && s == P.S - 1 && last_band) ? 1u : 0u;
+    const unsigned long long tbits = r.phase + r.nbits;
+    r.nbytes = live ? (tbits >> 3) + ((r.last && (tbits & 7)) ? 1 : 0) : 0ull;
+    unsigned long long total_bytes;
+    r.byte_off = cta_exclusive_scan<unsigned long long>(r.nbytes, sh64, &total_bytes);
+    uint32_t total_tiles;
+    r.tile_off = cta_exclusive_scan<uint32_t>((uint32_t)((r.nbytes + SPL_TILE - 1) / SPL_TILE), sh32, &total_tiles);
+    // the bits inherited in the first byte: the last 7 bits of the nearest earlier segment that has any
+    int near = (live && nbits) ? (int)s : -1;      // inclusive running maximum, then shifted by one
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, near, o);
+        if (lane >= o) near = max(near, v);
+    }
+    if (lane == 31) shmax[warp] = near;
+    __syncthreads();
+    int prev = __shfl_up_sync(0xffffffffu, near, 1);
+    if (lane == 0) prev = -1;
+    for (int w = 0; w < warp; ++w) prev = max(prev, shmax[w]);
+    const uint32_t tail_prev = prev >= 0 ? (uint32_t)P.tails[i * P.S + prev] : base_tail;
+    r.tail_in = tail_prev & ((1u << r.phase) - 1u);
+    if (live) P.rec[q] = r;
+    const uint32_t bad = (uint32_t)__syncthreads_or((int)bad_here);
+    if (s == 0) {
+        P.ntiles[i] = total_tiles;
+        // a raw segment that did not fit (or a faulted chain): the caller codes the image again unsegmented
+        if (bad || total_tiles > P.max_tiles) { P.overflow[i] = 4u | (bad & 2u); P.ntiles[i] = 0; P.out_len[i] = 0; }
+        else if (total_tiles == 0) P.out_len[i] = 0;
+    }
 }
 
 // A CTA of the splice kernels works through SPL_TPC consecutive tiles of one image (one tile per CTA
 // left the kernels latency-bound: 17 000 CTAs for a 70 MB scan, each behind a chain of dependent loads).
 // The image's segment records are read once into shared memory.
 constexpr int SPL_TPC = 8;
-constexpr int SEG_MAX = 64;
+constexpr int SEG_MAX = 256;
+static_assert(SEG_MAX == SPL_THREADS, "thread s of a splice CTA looks at segment record s");
 
 __device__ __forceinline__ void load_seg_table(const SegParams &P, uint32_t i, SegRec *tab)
 {
@@ -1350,8 +1391,8 @@ static void make_huff_dev(const HuffTables &t, HuffDev *Tp)
     }
 }
 
-// How many segments per image: enough chains to keep a look-back short (~64 chains in flight), none
-// shorter than 48 chunks.  1 = do not segment.
+// How many segments per image: enough chains to keep a look-back short (~256 chains in flight), none
+// shorter than 512 chunks.  1 = do not segment.
 static uint32_t segments_for(uint32_t n, uint64_t total_mcus, uint64_t bpm)
 {
     if (const char *e = getenv("PIXO_B200_SEGMENTS")) return (uint32_t)std::min(SEG_MAX, std::max(1, atoi(e)));   // test hook
@@ -1360,8 +1401,11 @@ static uint32_t segments_for(uint32_t n, uint64_t total_mcus, uint64_t bpm)
     // (196 608 chunks on ONE chain) is where the look-back distance hurts.  So: few images, each long.
     const uint64_t chunks = total_mcus * bpm / CB;
     if (n > 8 || chunks < 16384) return 1;
-    uint32_t S = 64 / n;
-    while (S > 1 && chunks / S < 1024) S >>= 1;
+    // 16 384^2 frame on one B200, whole device path: 16 segments 1.75 ms, 32: 1.46, 64: 1.27, 128: 1.19,
+    // 256: 1.16 (k_huff<RAW> 729 -> 594 us from 64 to 256: with ~7000 chunks in flight a chain of 1/256
+    // keeps the nearest inclusive prefix inside one 32-wide look-back step)
+    uint32_t S = SEG_MAX / n;
+    while (S > 1 && chunks / S < 512) S >>= 1;
     return S < 2 ? 1 : S;
 }
 
@@ -1455,7 +1499,7 @@ static int launch_segmented(pixo_b200_ctx *ctx, EntParams P, const HuffDev &T, u
     Q.out_len = reinterpret_cast<unsigned long long *>(d_out_len);
     Q.overflow = d_overflow;
     Q.raw_overflow = code ? P.overflow : nullptr;   // a band's flags were checked by the host when it was coded
-    k_seg_prefix<<<n, 32, 0, st>>>(Q);
+    k_seg_prefix<<<n, SPL_THREADS, 0, st>>>(Q);
     k_seg_count<<<dim3((sp.max_tiles + SPL_TPC - 1) / SPL_TPC, n), SPL_THREADS, 0, st>>>(Q);
     k_seg_scan<<<n, 1024, 0, st>>>(Q);
     k_seg_emit<<<dim3((sp.max_tiles + SPL_TPC - 1) / SPL_TPC, n), SPL_THREADS, 0, st>>>(Q);
