@@ -310,10 +310,12 @@ def jpeg_config(env: Env, name: str, w: int, h: int, n_total: int, qualities, ss
     from oracle import pyoracle as po      # checker only
     from pixo_b200 import jpeg, synthetic
     torch, lib = env.torch, env.lib
-    mine = list(range(env.rank, n_total, env.world))
+    # contiguous blocks: the frame content alternates (gradient / noise), so a round-robin split over an
+    # even number of ranks would hand one rank all the noise frames and time only that rank
+    mine = list(range(env.rank * n_total // env.world, (env.rank + 1) * n_total // env.world))
     n = len(mine)
     bases = [synthetic.noise(w, h, 3, 42 + k) if k % 2 else synthetic.gradient_rgb(w, h) for k in range(4)]
-    # frame k of this rank is global frame first + k*world: build with that index
+    # frame k of this rank is global frame mine[k]: build with that index
     rows = h
     d_bases = [torch.from_numpy(b).to(env.dev).reshape(rows, -1) for b in bases]
     d_px = torch.empty((n, w * h * 3), dtype=torch.uint8, device=env.dev)
@@ -481,7 +483,9 @@ def c5_config(env: Env, steps: int) -> dict:
     torch, lib = env.torch, env.lib
     w, h, bpp, n_total = 3840, 2160, 4, 64
     rb = w * bpp
-    mine = list(range(env.rank, n_total, env.world))
+    # contiguous blocks: the frame content alternates (gradient / noise), so a round-robin split over an
+    # even number of ranks would hand one rank all the noise frames and time only that rank
+    mine = list(range(env.rank * n_total // env.world, (env.rank + 1) * n_total // env.world))
     n = len(mine)
     g3 = synthetic.gradient_rgb(w, h).reshape(h, w, 3)
     bases = [synthetic.noise(w, h, 4, 42 + k) if k % 2 else
