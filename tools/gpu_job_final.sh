@@ -22,5 +22,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pn
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_huff -s 2 -c 1 -f -o gpurun_out/huff_final2 python tools/prof_run.py encode 32 4 > gpurun_out/ncu_huff.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_jpeg_420 -s 2 -c 1 -f -o gpurun_out/k1_final2 python tools/prof_run.py encode 32 4 > gpurun_out/ncu_k1.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_jpeg_444 -s 1 -c 1 -f -o gpurun_out/k444_final2 python tools/prof_444.py > gpurun_out/ncu_k444.log 2>&1
-tail -1 gpurun_out/ncu_png.log gpurun_out/ncu_huff.log gpurun_out/ncu_k1.log gpurun_out/ncu_k444.log
+for f in png huff k1 k444; do tail -n 1 gpurun_out/ncu_$f.log; done
 ls -la gpurun_out/*final2* gpurun_out/launches_*.csv
