@@ -43,9 +43,10 @@ def adler(nbytes, reps=10):
     ms = e0.elapsed_time(e1) / reps
     print(f"adler32 {nbytes} B: {ms*1e3:.1f} us  {nbytes/ms/1e6:.1f} GB/s")
 
-run(3840, 2160, 4, 16, 6)
-run(3840, 2160, 4, 16, 6, smooth=True)
-run(3840, 2160, 4, 16, 7)
+N = int(os.environ.get("PNG_N", "16"))   # frames per call
+run(3840, 2160, 4, N, 6)
+run(3840, 2160, 4, N, 6, smooth=True)
+run(3840, 2160, 4, N, 7)
 run(3840, 2160, 4, 16, 4)
 run(3840, 2160, 4, 16, 1)
 run(3840, 2160, 3, 16, 6)
