@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
             if (fused) { score_row(std::integral_constant<int, 2>{}); reduce_scores(0, 5); }
             else { score_row(std::integral_constant<int, 0>{}); reduce_scores(0, 4); }
             if (tid == 0) {
-                const unsigned long long *sc = s_score;
+                const volatile unsigned long long *sc = s_score;
                 int best;
                 bool done;
                 unsigned long long bs;
@@ -715,7 +715,10 @@ __global__ void __launch_bounds__(PNG_THREADS, PNG_BAND_MIN_BLOCKS) k_png_band(c
             if (!fused && prev_needed_paeth) {      // uniform
                 score_row(std::integral_constant<int, 1>{});
                 reduce_scores(4, 5);
-                if (tid == 0 && s_score[4] < s_best) s_filter = 4;
+                if (tid == 0) {   // (volatile: no other thread may read these words speculatively while thread 0 writes them)
+                    const volatile unsigned long long *sc = s_score;
+                    if (sc[4] < *(const volatile unsigned long long *)&s_best) s_filter = 4;
+                }
                 __syncthreads();
             }
             filter = s_filter;
