@@ -16,9 +16,12 @@
 //     raw byte is read from HBM once and the next row streams in under the current row's
 //     arithmetic.  Candidates are scored on 4-byte words, four consecutive words per thread
 //     (|i8(x - pred)| = 128 - ||x - pred| - 128|: two VABSDIFF4 per candidate; Paeth is a
-//     23-instruction byte-SIMD predictor), the five scores are reduced (REDUX + one shared-memory
-//     step), the reference's decision ladder is replayed, only the winner is re-derived, shifted to
-//     the output stream's byte phase and written as aligned words.  The row's Adler-32 contribution
+//     23-instruction byte-SIMD predictor), the scores are reduced (REDUX + one shared-memory
+//     step) and the reference's decision ladder is replayed.  Paeth - two thirds of the scoring
+//     arithmetic - is scored only while the ladder is still open: in the same pass as the others when
+//     the row above needed it, in a second pass otherwise.  Only the winner is re-derived, 16 bytes
+//     per thread, shifted to the output stream's byte phase through a per-warp staging array and
+//     written as aligned 16-byte stores.  The row's Adler-32 contribution
 //     (A = sum d, B = sum (n-i) d, position-weighted to the end of the image) rides along; the last
 //     CTA of an image folds the accumulators into the checksum.
 //   k_png_filter (one CTA per row, rows staged in 32 KB segments): Bigrams (65 536-bit "seen"
